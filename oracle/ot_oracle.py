@@ -1,0 +1,436 @@
+"""CPU oracle for the entropic-OT (Sinkhorn) MRI<->PET alignment path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package imports this file.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
+/ ``--impl reference`` legs may import it, and there only as the checker or as
+the timed CPU arm -- never as a fallback for the CUDA path.
+
+It restates, in float64 NumPy, the algorithm the reference runs on this path.
+All ``file:line`` citations are relative to ``/root/reference``.
+
+Parity status
+-------------
+* ``sinkhorn_knopp`` / ``init_matrix`` / ``fot_cost_pot`` / ``mdict_to_matrix``
+  are PINNED: ``tests/golden/make_golden.py`` executes the reference's own code
+  (``perturbot/perturbot/match/utils.py`` imported by file path, and the
+  function bodies of ``MRI_PET_OT_nojax.py:91-145`` and
+  ``perturbot/perturbot/match/fot.py:14-152`` compiled from the reference file
+  with ``ot`` / ``ott`` replaced by stubs) and the resulting vectors are
+  committed under ``tests/golden/``; ``tests/test_oracle.py`` checks the oracle
+  against them.
+* ``sinkhorn_log_ott`` restates ott-jax 0.6.0 ``linear.solve`` semantics
+  (``OT_environment.yml:227``), and ``err_norm="l2"`` restates POT 0.9.6.post1
+  (``OT_environment.yml:232``).  Neither library is vendored nor installable
+  here, the reference ships no tests/golden vectors for them, so for these two
+  flavours **parity is unpinned**: they are restatements of the published
+  algorithms anchored on the reference's call sites
+  (``MRI_PET_OT_nojax.py:143``, ``perturbot/perturbot/match/fot.py:129-134``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = [
+    "synthetic_embeddings", "sqeuclid_cost", "cosine_cost", "init_matrix",
+    "fot_cost_pot", "fot_cost_ott", "mdict_to_matrix", "sinkhorn_knopp",
+    "sinkhorn_log", "sinkhorn_log_ott", "plan_from_potentials", "fot_bcd_ott",
+    "get_feature_coupling_pot", "get_coupling_fot", "plan_guard_rownorm",
+    "apply_plan_T", "barycentric", "cosine_loss", "ot_cost", "envelope_grads",
+]
+
+
+# --------------------------------------------------------------------------
+# synthetic inputs
+# --------------------------------------------------------------------------
+def synthetic_embeddings(n, m, d, config_index=0, seed_base=20251118):
+    """X = randn(n,d); Y = randn(m,d) + 0.5*randn(1,d); rows L2-normalised, fp32.
+
+    Uses torch's CPU generator so bench.py, the tests and the golden script all
+    see the same bits ("Synthetic inputs").
+    """
+    import torch
+
+    gen = torch.Generator(device="cpu").manual_seed(seed_base + config_index)
+    X = torch.randn(n, d, generator=gen, dtype=torch.float32)
+    Y = torch.randn(m, d, generator=gen, dtype=torch.float32)
+    Y = Y + 0.5 * torch.randn(1, d, generator=gen, dtype=torch.float32)
+    X = X / X.norm(dim=1, keepdim=True)
+    Y = Y / Y.norm(dim=1, keepdim=True)
+    return X.numpy(), Y.numpy()
+
+
+# --------------------------------------------------------------------------
+# cost construction
+# --------------------------------------------------------------------------
+def sqeuclid_cost(X, Y):
+    """C_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  (north-star sample x sample cost).
+
+    Same algebra as the reference's feature cost with Ts = I
+    (``MRI_PET_OT_nojax.py:121-136``).
+    """
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    return (X * X).sum(1)[:, None] + (Y * Y).sum(1)[None, :] - 2.0 * (X @ Y.T)
+
+
+def cosine_cost(X, Y):
+    """C_ij = 1 - cos(x_i, y_j): the same contraction on pre-normalised rows."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    Xn = X / np.maximum(np.linalg.norm(X, axis=1, keepdims=True), 1e-300)
+    Yn = Y / np.maximum(np.linalg.norm(Y, axis=1, keepdims=True), 1e-300)
+    return 1.0 - Xn @ Yn.T
+
+
+def init_matrix(X1, X2, v1, v2):
+    """COOT square-loss factorisation (``perturbot/perturbot/match/utils.py:125-184``).
+
+    constC = (X1^2) v1 (+) (X2^2) v2 ; hC1 = X1 ; hC2 = 2 X2, so that the cost is
+    ``constC - hC1 . T . hC2^T``.
+    """
+    # No up-cast of X1/X2: the reference squares in the input dtype (float32
+    # embeddings) and only promotes to float64 in the product with the weights.
+    X1 = np.asarray(X1)
+    X2 = np.asarray(X2)
+    c1 = np.dot(X1 ** 2, np.asarray(v1, dtype=np.float64))
+    c2 = np.dot(np.asarray(v2, dtype=np.float64), (X2 ** 2).T)
+    return c1[:, None] + c2[None, :], X1, 2 * X2
+
+
+def mdict_to_matrix(M_dict, source_labels, target_labels):
+    """Block-diagonal scatter by label (``baseline_models_fusion.py:233-239``)."""
+    source_labels = np.asarray(source_labels)
+    target_labels = np.asarray(target_labels)
+    out = np.zeros((len(source_labels), len(target_labels)))
+    for l, M in M_dict.items():
+        out[np.ix_(np.where(source_labels == l)[0], np.where(target_labels == l)[0])] = M
+    return out
+
+
+def _ts_from_dict_sorted(X_dict, Y_dict, Ts):
+    """Block-diagonal Ts in sorted-label order (``MRI_PET_OT_nojax.py:105-119``)."""
+    keys = sorted(X_dict.keys())
+    n_x = sum(len(X_dict[l]) for l in keys)
+    n_y = sum(len(Y_dict[l]) for l in keys)
+    out = np.zeros((n_x, n_y))
+    ix = iy = 0
+    for l in keys:
+        nx, ny = len(X_dict[l]), len(Y_dict[l])
+        if l in Ts:
+            out[ix:ix + nx, iy:iy + ny] = Ts[l]
+        ix += nx
+        iy += ny
+    return out
+
+
+def fot_cost_pot(X, Y, Ts):
+    """Feature cost of ``get_feature_coupling_pot`` (``MRI_PET_OT_nojax.py:121-136``).
+
+    M_kl = sum_ij |X_ik - Y_jl|^2 Ts_ij, with w1 = Ts.sum(1), w2 = Ts.sum(0).
+    No normalisation of Ts or of M.
+    """
+    # dtype promotion exactly as the reference: squares in the input dtype
+    # (float32 embeddings), products promoted to float64 by the float64 Ts.
+    X = np.asarray(X)
+    Y = np.asarray(Y)
+    Ts = np.asarray(Ts, dtype=np.float64)
+    w1 = Ts.sum(axis=1)
+    w2 = Ts.sum(axis=0)
+    t1 = (X ** 2).T @ w1
+    t2 = (Y ** 2).T @ w2
+    t3 = -2 * X.T @ Ts @ Y
+    return t1[:, None] + t2[None, :] + t3
+
+
+def fot_cost_ott(X, Y, Ts):
+    """Feature cost of ``fot_numpy`` (``perturbot/perturbot/match/fot.py:108-128``).
+
+    Ts is normalised to unit mass first; the marginals are taken with the axes
+    *swapped* relative to ``fot_cost_pot`` (w1 = Ts.sum(0), w2 = Ts.sum(1)),
+    exactly as the reference does -- only consistent when n == n'.
+    """
+    X = np.asarray(X)
+    Y = np.asarray(Y)
+    Ts = np.asarray(Ts, dtype=np.float64)
+    Ts = Ts / Ts.sum()
+    w1 = Ts.sum(axis=0)
+    w2 = Ts.sum(axis=1)
+    constC, hC1, hC2 = init_matrix(X.T, Y.T, w1, w2)
+    return constC - np.dot(hC1, Ts).dot(hC2.T), Ts
+
+
+# --------------------------------------------------------------------------
+# Sinkhorn, kernel domain (POT / in-tree mirror semantics)
+# --------------------------------------------------------------------------
+def sinkhorn_knopp(a, b, M=None, reg=None, K=None, numItermax=1000, stopThr=1e-9,
+                   err_norm="l2", check_every=10, log=False):
+    """Kernel-domain Sinkhorn-Knopp.
+
+    Follows ``perturbot/perturbot/match/utils.py:6-115`` line by line (init
+    ``u=1/n, v=1/m`` :36-40; ``Kp`` :45; ``v=b/(K^T u)``, ``u=1/(Kp v)`` :51-53;
+    zero/NaN/Inf guard restoring the previous duals :55-79; error every 10th
+    iteration on the column marginal :80-89; return ``diag(u) K diag(v)``
+    :111-115).
+
+    ``err_norm="l2sq"`` + ``stop "<="`` is the in-tree mirror (squared norm,
+    ``while err > stopThr``); ``err_norm="l2"`` + strict ``<`` is POT 0.9.6
+    ``sinkhorn_knopp`` as called at ``MRI_PET_OT_nojax.py:143`` (upstream,
+    unverifiable here).  Pass either ``K`` (mirror) or ``(M, reg)`` (POT).
+    ``log["n_iter"]`` is the number of completed (v,u) updates; ``log["niter"]``
+    is POT's loop index at exit.
+    """
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if K is None:
+        M = np.asarray(M, dtype=np.float64)
+        K = np.exp(M / (-reg))
+    else:
+        K = np.asarray(K, dtype=np.float64)
+    n, m = len(a), len(b)
+    u = np.ones(n) / n
+    v = np.ones(m) / m
+    Kp = (1.0 / a).reshape(-1, 1) * K
+    errs = []
+    err = 1.0
+    cpt = 0
+    flag = 0
+    while cpt < numItermax:
+        uprev, vprev = u, v
+        KtU = K.T @ u
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            v = b / KtU
+            u = 1.0 / (Kp @ v)
+        if (np.any(KtU == 0) or np.any(np.isnan(u)) or np.any(np.isnan(v))
+                or np.any(np.isinf(u)) or np.any(np.isinf(v))):
+            u, v = uprev, vprev
+            flag = 1  # "numerical errors": previous iterate returned
+            break
+        if cpt % check_every == 0:
+            # column marginal of diag(u) K diag(v), same op order as utils.py:88
+            col = np.sum(u.reshape(-1, 1) * (K * v), axis=0)
+            if err_norm == "l2sq":
+                err = float(np.linalg.norm(col - b) ** 2)
+            elif err_norm == "l2":
+                err = float(np.linalg.norm(col - b))
+            elif err_norm == "l1":
+                err = float(np.abs(col - b).sum())
+            else:
+                raise ValueError(err_norm)
+            errs.append(err)
+            stop = err <= stopThr if err_norm == "l2sq" else err < stopThr
+            if stop:
+                cpt += 1
+                break
+        cpt += 1
+    P = u.reshape(-1, 1) * K * v.reshape(1, -1)
+    if log:
+        return P, {"err": errs, "u": u, "v": v, "n_iter": cpt, "niter": max(cpt - 1, 0),
+                   "numerical_error": flag}
+    return P
+
+
+# --------------------------------------------------------------------------
+# Sinkhorn, log domain (the engine's own arithmetic, in float64)
+# --------------------------------------------------------------------------
+def _lse(x, axis):
+    mx = np.max(x, axis=axis, keepdims=True)
+    mx = np.where(np.isfinite(mx), mx, 0.0)
+    return (np.log(np.sum(np.exp(x - mx), axis=axis, keepdims=True)) + mx).squeeze(axis)
+
+
+def plan_from_potentials(C, f, g, eps):
+    return np.exp((f[:, None] + g[None, :] - np.asarray(C, dtype=np.float64)) / eps)
+
+
+def sinkhorn_log(C, a, b, eps, max_iter=1000, tol=1e-9, err_norm="l2", check_every=10,
+                 check_phase=1, stop_inclusive=False, f0=None, g0=None, log=False):
+    """Log-domain Sinkhorn with a pluggable stopping rule.
+
+    One iteration = ``g <- eps log b - eps LSE_i((f_i - C_ij)/eps)`` then
+    ``f <- eps log a - eps LSE_j((g_j - C_ij)/eps)`` -- the same map as the
+    kernel-domain ``v`` then ``u`` update with ``f = eps log u``, ``g = eps log v``
+    (SURVEY.md Appendix A).  After iteration ``it`` (1-based) the column marginal
+    error of ``exp((f+g-C)/eps)`` is evaluated when
+    ``it % check_every == check_phase % check_every``:
+    ``check_phase=1`` reproduces POT / the mirror (``cpt % 10 == 0`` with a
+    0-based counter), ``check_phase=0`` reproduces ott's ``inner_iterations``.
+    """
+    C = np.asarray(C, dtype=np.float64)
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    n, m = C.shape
+    f = np.zeros(n) if f0 is None else np.asarray(f0, dtype=np.float64).copy()
+    g = np.zeros(m) if g0 is None else np.asarray(g0, dtype=np.float64).copy()
+    la, lb = np.log(a), np.log(b)
+    errs = []
+    err = np.inf
+    it = 0
+    converged = False
+    while it < max_iter:
+        g = eps * lb - eps * _lse((f[:, None] - C) / eps, axis=0)
+        f = eps * la - eps * _lse((g[None, :] - C) / eps, axis=1)
+        it += 1
+        if it % check_every == check_phase % check_every:
+            col = np.exp((f[:, None] + g[None, :] - C) / eps).sum(axis=0)
+            d = col - b
+            if err_norm == "l2sq":
+                err = float(d @ d)
+            elif err_norm == "l2":
+                err = float(np.sqrt(d @ d))
+            elif err_norm == "l1":
+                err = float(np.abs(d).sum())
+            else:
+                raise ValueError(err_norm)
+            errs.append(err)
+            if (err <= tol) if stop_inclusive else (err < tol):
+                converged = True
+                break
+    P = plan_from_potentials(C, f, g, eps)
+    if log:
+        return P, {"err": errs, "f": f, "g": g, "n_iter": it, "converged": converged}
+    return P
+
+
+def sinkhorn_log_ott(M, eps, a=None, b=None, max_iterations=2000, threshold=1e-3,
+                     inner_iterations=10, scale_cost="max_cost", log=False):
+    """ott-jax 0.6.0 ``linear.solve(Geometry(cost_matrix=M, epsilon=eps,
+    scale_cost="max_cost"), max_iterations=N).matrix`` as called at
+    ``perturbot/perturbot/match/fot.py:129-134`` (upstream, unverifiable here):
+    cost divided by its max, eps absolute on the scaled cost, zero-initialised
+    potentials, g-then-f updates, L1 error of the b-marginal every
+    ``inner_iterations``, stop when ``err < threshold``.
+    """
+    M = np.asarray(M, dtype=np.float64)
+    n, m = M.shape
+    a = np.ones(n) / n if a is None else np.asarray(a, dtype=np.float64)
+    b = np.ones(m) / m if b is None else np.asarray(b, dtype=np.float64)
+    if scale_cost == "max_cost":
+        C = M / M.max()
+    elif scale_cost in (None, 1.0, "none"):
+        C = M
+    else:
+        raise ValueError(scale_cost)
+    P, lg = sinkhorn_log(C, a, b, eps, max_iter=max_iterations, tol=threshold, err_norm="l1",
+                         check_every=inner_iterations, check_phase=0, log=True)
+    lg["scaled_cost"] = C
+    return (P, lg) if log else P
+
+
+# --------------------------------------------------------------------------
+# the reference's callers (a1, a3)
+# --------------------------------------------------------------------------
+def get_feature_coupling_pot(data, Ts, eps=5e-3, numItermax=2000, stopThr=1e-9, err_norm="l2"):
+    """``MRI_PET_OT_nojax.py:91-145``: sorted-label concat, block-diagonal Ts,
+    feature cost, uniform feature marginals, ``ot.sinkhorn(a,b,M,reg=eps,
+    numItermax=2000)``.  Returns ``(Tv, {})``."""
+    X_dict, Y_dict = data
+    keys = sorted(X_dict.keys())
+    X = np.concatenate([X_dict[l] for l in keys])
+    Y = np.concatenate([Y_dict[l] for l in keys])
+    if isinstance(Ts, dict):
+        Ts = _ts_from_dict_sorted(X_dict, Y_dict, Ts)
+    M = fot_cost_pot(X, Y, Ts)
+    a = np.ones(X.shape[1]) / X.shape[1]
+    b = np.ones(Y.shape[1]) / Y.shape[1]
+    Tv = sinkhorn_knopp(a, b, M=M, reg=eps, numItermax=numItermax, stopThr=stopThr,
+                        err_norm=err_norm)
+    return Tv, {}
+
+
+def fot_bcd_ott(X1, X2, Ts, reg2, niter=2000, log=False):
+    """BCD shell of ``fot_numpy`` (``perturbot/perturbot/match/fot.py:104-152``):
+    Ts fixed => the cost is identical every round; exit when
+    ``|Tv - Tv_old|_F < 1e-16`` or ``|cost_old - cost| < 1e-7`` (:145)."""
+    M, _ = fot_cost_ott(X1, X2, Ts)
+    d1, d2 = X1.shape[1], X2.shape[1]
+    Tv = np.ones((d1, d2)) / (d1 * d2)
+    cost = np.inf
+    costs = []
+    rounds = 0
+    for _ in range(niter):
+        Tv_old, cost_old = Tv, cost
+        Tv = sinkhorn_log_ott(M, reg2)
+        delta = np.linalg.norm(Tv - Tv_old)
+        cost = float(np.sum(M * Tv))
+        costs.append(cost)
+        rounds += 1
+        if delta < 1e-16 or abs(cost_old - cost) < 1e-7:
+            break
+    if log:
+        return Tv, cost, {"cost": costs, "rounds": rounds}
+    return Tv, cost
+
+
+def get_coupling_fot(data, Ts, eps=5e-3):
+    """``perturbot/perturbot/match/fot.py:155-220`` (first-seen label order)."""
+    X_dict, Y_dict = data
+    keys = list(X_dict.keys())
+    if isinstance(Ts, dict):
+        Ts = mdict_to_matrix(
+            Ts,
+            np.concatenate([np.ones(X_dict[l].shape[0]) * l for l in keys]),
+            np.concatenate([np.ones(Y_dict[l].shape[0]) * l for l in keys]),
+        )
+    X = np.concatenate([X_dict[l] for l in keys])
+    Y = np.concatenate([Y_dict[l] for l in keys])
+    Tv, cost, lg = fot_bcd_ott(X, Y, Ts, reg2=eps, niter=2000, log=True)
+    return Tv, lg
+
+
+# --------------------------------------------------------------------------
+# epilogues (a6)
+# --------------------------------------------------------------------------
+def plan_guard_rownorm(T):
+    """NaN -> 1e-8, then row-normalise with zero-row guard
+    (``MRI_PET_OT_nojax.py:704-715``)."""
+    T = np.asarray(T, dtype=np.float64).copy()
+    T[np.isnan(T)] = 1e-8
+    rs = T.sum(axis=1, keepdims=True)
+    rs[rs == 0] = 1e-8
+    return T / rs
+
+
+def apply_plan_T(V, T):
+    """``pet @ T.t()`` (``MRI_PET_OT_OT_per_epoch_attn.py:728``,
+    ``MRI_PET_OT_nojax.py:718``)."""
+    return np.asarray(V, dtype=np.float64) @ np.asarray(T, dtype=np.float64).T
+
+
+def barycentric(P, Y):
+    """``(T / rowsum) @ Y`` with ``rowsum == 0 -> 1e-30``
+    (``perturbot/perturbot/eval/match.py:202-206``)."""
+    P = np.asarray(P, dtype=np.float64)
+    marg = P.sum(axis=-1)
+    marg = np.where(marg == 0, 1e-30, marg)
+    return (P / marg[:, None]) @ np.asarray(Y, dtype=np.float64)
+
+
+def cosine_loss(x, y):
+    """``1 - mean_i cos(x_i, y_i)`` with F.normalize's 1e-12 floor
+    (``MRI_PET_OT_nojax.py:552-560``)."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    y = np.atleast_2d(np.asarray(y, dtype=np.float64))
+    xn = x / np.maximum(np.linalg.norm(x, axis=1, keepdims=True), 1e-12)
+    yn = y / np.maximum(np.linalg.norm(y, axis=1, keepdims=True), 1e-12)
+    num = (xn * yn).sum(1)
+    den = np.maximum(np.linalg.norm(xn, axis=1) * np.linalg.norm(yn, axis=1), 1e-8)
+    return float(1.0 - (num / den).mean())
+
+
+def ot_cost(P, C):
+    """Transport cost <P, C> (``perturbot/perturbot/match/fot.py:137``)."""
+    return float(np.sum(np.asarray(P, dtype=np.float64) * np.asarray(C, dtype=np.float64)))
+
+
+def envelope_grads(X, Y, P):
+    """Envelope-theorem gradients of <P, C(X,Y)> for the squared-Euclidean cost
+    with P held fixed: dX = 2 (diag(P1) X - P Y), dY = 2 (diag(P^T1) Y - P^T X).
+    New capability (the reference never differentiates through OT,
+    ``MRI_PET_OT_nojax.py:683-684``); validated against torch-fp64 autograd in
+    tests, not against the reference."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    P = np.asarray(P, dtype=np.float64)
+    dX = 2.0 * (P.sum(1)[:, None] * X - P @ Y)
+    dY = 2.0 * (P.sum(0)[:, None] * Y - P.T @ X)
+    return dX, dY

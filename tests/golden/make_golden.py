@@ -1,0 +1,181 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE's own code.
+
+Run in the build container only (needs /root/reference, which does not exist on
+the GPU box):  ``python tests/golden/make_golden.py``
+
+What is executed, unmodified, from /root/reference:
+  * ``perturbot/perturbot/match/utils.py`` (imported by file path):
+    ``sinkhorn_scaling`` (:6-115) and ``init_matrix_np`` (:125-184);
+  * the function ``get_feature_coupling_pot`` (``MRI_PET_OT_nojax.py:91-145``),
+    compiled from the reference file's AST.  Its only external call,
+    ``ot.sinkhorn`` (POT, not installed), is bound to a stub that forwards to the
+    reference's own ``sinkhorn_scaling(a, b, exp(-M/reg), ...)`` -- the in-tree
+    mirror of POT's loop;
+  * the function ``fot_numpy`` (``perturbot/perturbot/match/fot.py:14-152``),
+    compiled from the AST, with ``init_matrix_np`` bound to the reference's and
+    ``ott`` (not installed) bound to a stub that forwards to the oracle's
+    restatement of ott-jax 0.6.0 ``linear.solve`` -- so the cost construction,
+    Ts normalisation, swapped marginals and BCD exit rule in the golden are the
+    reference's, the inner solve is the restatement;
+  * ``mdict_to_matrix`` (``baseline_models_fusion.py:233-239``), compiled from the AST.
+
+No reference source text is copied into this repository: the functions are
+compiled in memory from the read-only tree and only their numerical outputs are
+saved.
+"""
+import ast
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from oracle import ot_oracle as orc  # noqa: E402
+
+
+def load_ref_utils():
+    spec = importlib.util.spec_from_file_location(
+        "ref_match_utils", os.path.join(REF, "perturbot/perturbot/match/utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def extract_function(path, name, namespace):
+    """Compile one (possibly nested-in-class) function definition from a reference file."""
+    with open(path) as fh:
+        tree = ast.parse(fh.read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            node.decorator_list = []
+            node.returns = None
+            for arg in node.args.args + node.args.kwonlyargs:
+                arg.annotation = None
+            mod = ast.Module(body=[node], type_ignores=[])
+            ast.fix_missing_locations(mod)
+            exec(compile(mod, path, "exec"), namespace)
+            return namespace[name]
+    raise KeyError(name)
+
+
+def main():
+    ref_utils = load_ref_utils()
+    out = {}
+
+    # ---- reference callables -------------------------------------------------
+    ot_stub = types.SimpleNamespace(
+        sinkhorn=lambda a, b, M, reg, numItermax=1000, stopThr=1e-9, **kw:
+        ref_utils.sinkhorn_scaling(a, b, np.exp(M / (-reg)), numItermax=numItermax,
+                                   stopThr=stopThr))
+    ns_pot = {"np": np, "ot": ot_stub}
+    ref_feature_coupling = extract_function(
+        os.path.join(REF, "MRI_PET_OT_nojax.py"), "get_feature_coupling_pot", ns_pot)
+
+    class _Geom:
+        def __init__(self, cost_matrix, epsilon, scale_cost):
+            self.cost_matrix, self.epsilon, self.scale_cost = cost_matrix, epsilon, scale_cost
+
+    class _Out:
+        def __init__(self, matrix):
+            self.matrix = matrix
+
+    def _solve(geom, max_iterations=2000, **kw):
+        return _Out(orc.sinkhorn_log_ott(geom.cost_matrix, geom.epsilon,
+                                         max_iterations=max_iterations,
+                                         scale_cost=geom.scale_cost))
+
+    ns_fot = {"np": np, "init_matrix_np": ref_utils.init_matrix_np,
+              "random_gamma_init": ref_utils.random_gamma_init,
+              "linear": types.SimpleNamespace(solve=_solve),
+              "geometry": types.SimpleNamespace(Geometry=_Geom)}
+    ref_fot_numpy = extract_function(
+        os.path.join(REF, "perturbot/perturbot/match/fot.py"), "fot_numpy", ns_fot)
+    ref_mdict = extract_function(
+        os.path.join(REF, "baseline_models_fusion.py"), "mdict_to_matrix", {"np": np})
+
+    # ---- case 1: BASELINE config 1, sample x sample, 64x64, d=512, eps=0.05, 200 its
+    X, Y = orc.synthetic_embeddings(64, 64, 512, config_index=0)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(64) / 64
+    b = np.ones(64) / 64
+    K = np.exp(-C / 0.05)
+    P200, lg200 = ref_utils.sinkhorn_scaling(a, b, K, numItermax=200, stopThr=0.0, log=True)
+    Pc, lgc = ref_utils.sinkhorn_scaling(a, b, K, numItermax=2000, stopThr=1e-9, log=True)
+    np.savez_compressed(
+        os.path.join(HERE, "c1_sample_64.npz"), X=X, Y=Y, C=C, eps=0.05,
+        P200=P200, err200=np.array(lg200["err"]), u200=lg200["u"], v200=lg200["v"],
+        Pconv=Pc, errconv=np.array(lgc["err"]), uconv=lgc["u"], vconv=lgc["v"])
+    out["c1_sample_64"] = (len(lg200["err"]), len(lgc["err"]))
+
+    # ---- case 2: reference-native feature problem, 512x512 from 64 samples (a1)
+    data = ({0: X}, {0: Y})
+    Ts = {0: np.eye(64) / 64}
+    Tv_pot, _ = ref_feature_coupling(data, Ts, eps=1e-2)
+    np.savez_compressed(os.path.join(HERE, "fot_pot_512.npz"), X=X, Y=Y, eps=1e-2, Tv=Tv_pot)
+
+    # two labels, unequal block sizes, dict Ts in unsorted insertion order
+    rng = np.random.default_rng(7)
+    Xd = {1: rng.standard_normal((5, 24)), 0: rng.standard_normal((7, 24))}
+    Yd = {1: rng.standard_normal((5, 16)), 0: rng.standard_normal((7, 16))}
+    Tsd = {1: np.full((5, 5), 1.0 / 25) / 2, 0: np.full((7, 7), 1.0 / 49) / 2}
+    Tv_pot2, _ = ref_feature_coupling((Xd, Yd), Tsd, eps=0.5)
+    np.savez_compressed(
+        os.path.join(HERE, "fot_pot_labels.npz"), X1=Xd[1], X0=Xd[0], Y1=Yd[1], Y0=Yd[0],
+        Ts1=Tsd[1], Ts0=Tsd[0], eps=0.5, Tv=Tv_pot2)
+
+    # ---- case 3: ott-flavoured FOT (a3): reference cost/BCD shell + restated inner solve
+    Tv_ott, cost_ott, lg_ott = ref_fot_numpy(X, Y, np.eye(64) / 64, reg=1e-2, reg2=1e-2,
+                                             niter=2000, log=True, verbose=False)
+    np.savez_compressed(os.path.join(HERE, "fot_ott_512.npz"), X=X, Y=Y, eps=1e-2,
+                        Tv=Tv_ott, cost=cost_ott, costs=np.array(lg_ott["cost"]))
+
+    # ---- case 4: init_matrix_np / mdict_to_matrix
+    X1 = rng.standard_normal((9, 6))
+    X2 = rng.standard_normal((11, 5))
+    v1 = rng.random(6)
+    v2 = rng.random(5)
+    constC, hC1, hC2 = ref_utils.init_matrix_np(X1, X2, v1, v2)
+    src = np.array([0, 1, 1, 0, 2, 1.0])
+    tgt = np.array([1, 0, 2, 2, 1.0])
+    Md = {0: rng.random((2, 1)), 1: rng.random((3, 2)), 2: rng.random((1, 2))}
+    Mtot = ref_mdict(None, Md, src, tgt)
+    np.savez_compressed(os.path.join(HERE, "helpers.npz"), X1=X1, X2=X2, v1=v1, v2=v2,
+                        constC=constC, hC1=hC1, hC2=hC2, src=src, tgt=tgt,
+                        M0=Md[0], M1=Md[1], M2=Md[2], Mtot=Mtot)
+
+    # ---- case 5: reference-native 2048x2048 feature problem (summary only: 32 MiB plan)
+    Xb, Yb = orc.synthetic_embeddings(128, 128, 2048, config_index=10)
+    Xb = np.abs(Xb) * 8.0  # post-ReLU-like magnitudes
+    Yb = np.abs(Yb) * 8.0
+    Tv_big, _ = ref_feature_coupling(({0: Xb}, {0: Yb}), {0: np.eye(128) / 128}, eps=5e-3)
+    np.savez_compressed(
+        os.path.join(HERE, "fot_pot_2048_summary.npz"), eps=5e-3, scale=8.0,
+        rowsum=Tv_big.sum(1), colsum=Tv_big.sum(0), rows=Tv_big[::256],
+        fro=np.linalg.norm(Tv_big), total=Tv_big.sum())
+
+    # ---- case 6: BASELINE config 3 shape, 4096x4096 (potentials + errors only)
+    X3, Y3 = orc.synthetic_embeddings(4096, 4096, 512, config_index=2)
+    C3 = orc.sqeuclid_cost(X3, Y3)
+    a3 = np.ones(4096) / 4096
+    K3 = np.exp(-C3 / 0.05)
+    P3, lg3 = ref_utils.sinkhorn_scaling(a3, a3, K3, numItermax=200, stopThr=0.0, log=True)
+    P3c, lg3c = ref_utils.sinkhorn_scaling(a3, a3, K3, numItermax=2000, stopThr=1e-9, log=True)
+    np.savez_compressed(
+        os.path.join(HERE, "c3_cohort_4096_summary.npz"), eps=0.05,
+        u200=lg3["u"], v200=lg3["v"], err200=np.array(lg3["err"]),
+        rows200=P3[::512], cost200=float(np.sum(P3 * C3)),
+        uconv=lg3c["u"], vconv=lg3c["v"], errconv=np.array(lg3c["err"]),
+        bary_rows=orc.barycentric(P3, Y3)[::512])
+    out["c3"] = (len(lg3["err"]), len(lg3c["err"]))
+    print("golden vectors written:", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+"""The oracle against the golden vectors produced by the reference's own code
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ot_oracle as orc
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_knopp_matches_reference_mirror_c1(golden_dir):
+    g = _load(golden_dir, "c1_sample_64.npz")
+    a = b = np.ones(64) / 64
+    K = np.exp(-g["C"] / float(g["eps"]))
+    P, lg = orc.sinkhorn_knopp(a, b, K=K, numItermax=200, stopThr=0.0, err_norm="l2sq", log=True)
+    # same BLAS calls in the same order as perturbot/match/utils.py:51-53 -> bit-exact
+    assert np.array_equal(P, g["P200"])
+    assert np.array_equal(np.array(lg["err"]), g["err200"])
+    assert lg["n_iter"] == 200
+    P, lg = orc.sinkhorn_knopp(a, b, K=K, numItermax=2000, stopThr=1e-9, err_norm="l2sq", log=True)
+    assert np.array_equal(P, g["Pconv"])
+    assert len(lg["err"]) == len(g["errconv"]) and lg["n_iter"] == 11
+
+
+def test_cost_matches_golden(golden_dir):
+    g = _load(golden_dir, "c1_sample_64.npz")
+    X, Y = orc.synthetic_embeddings(64, 64, 512, config_index=0)
+    assert np.array_equal(X, g["X"]) and np.array_equal(Y, g["Y"])
+    assert np.array_equal(orc.sqeuclid_cost(X, Y), g["C"])
+
+
+def test_log_domain_equals_kernel_domain(golden_dir):
+    g = _load(golden_dir, "c1_sample_64.npz")
+    a = b = np.ones(64) / 64
+    eps = float(g["eps"])
+    f0 = eps * np.log(np.ones(64) / 64)  # u0 = 1/n  (utils.py:36-40)
+    P, lg = orc.sinkhorn_log(g["C"], a, b, eps, max_iter=200, tol=0.0, err_norm="l2sq",
+                             check_phase=1, stop_inclusive=False, f0=f0, log=True)
+    np.testing.assert_allclose(P, g["P200"], rtol=1e-10, atol=0)
+    np.testing.assert_allclose(eps * np.log(g["u200"]), lg["f"], rtol=0, atol=1e-12)
+    P, lg = orc.sinkhorn_log(g["C"], a, b, eps, max_iter=2000, tol=1e-9, err_norm="l2sq",
+                             check_phase=1, stop_inclusive=True, f0=f0, log=True)
+    assert lg["n_iter"] == 11 and lg["converged"]
+    np.testing.assert_allclose(P, g["Pconv"], rtol=1e-10, atol=0)
+
+
+def test_feature_coupling_pot_512(golden_dir):
+    g = _load(golden_dir, "fot_pot_512.npz")
+    Tv, _ = orc.get_feature_coupling_pot(({0: g["X"]}, {0: g["Y"]}), {0: np.eye(64) / 64},
+                                         eps=float(g["eps"]), err_norm="l2sq")
+    np.testing.assert_allclose(Tv, g["Tv"], rtol=1e-12, atol=0)
+
+
+def test_feature_coupling_pot_labels(golden_dir):
+    g = _load(golden_dir, "fot_pot_labels.npz")
+    Xd = {1: g["X1"], 0: g["X0"]}
+    Yd = {1: g["Y1"], 0: g["Y0"]}
+    Ts = {1: g["Ts1"], 0: g["Ts0"]}
+    Tv, _ = orc.get_feature_coupling_pot((Xd, Yd), Ts, eps=float(g["eps"]), err_norm="l2sq")
+    np.testing.assert_allclose(Tv, g["Tv"], rtol=1e-12, atol=0)
+
+
+def test_fot_ott_512(golden_dir):
+    g = _load(golden_dir, "fot_ott_512.npz")
+    Tv, lg = orc.get_coupling_fot(({0: g["X"]}, {0: g["Y"]}), {0: np.eye(64) / 64},
+                                  eps=float(g["eps"]))
+    np.testing.assert_allclose(Tv, g["Tv"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(lg["cost"], g["costs"], rtol=1e-12)
+    assert lg["rounds"] == 2  # Ts fixed => two identical solves (fot.py:145)
+
+
+def test_helpers(golden_dir):
+    g = _load(golden_dir, "helpers.npz")
+    constC, hC1, hC2 = orc.init_matrix(g["X1"], g["X2"], g["v1"], g["v2"])
+    np.testing.assert_allclose(constC, g["constC"], rtol=1e-14)
+    assert np.array_equal(hC1, g["hC1"]) and np.array_equal(hC2, g["hC2"])
+    Mtot = orc.mdict_to_matrix({0: g["M0"], 1: g["M1"], 2: g["M2"]}, g["src"], g["tgt"])
+    assert np.array_equal(Mtot, g["Mtot"])
+
+
+def test_feature_coupling_pot_2048_summary(golden_dir):
+    g = _load(golden_dir, "fot_pot_2048_summary.npz")
+    Xb, Yb = orc.synthetic_embeddings(128, 128, 2048, config_index=10)
+    Xb, Yb = np.abs(Xb) * float(g["scale"]), np.abs(Yb) * float(g["scale"])
+    Tv, _ = orc.get_feature_coupling_pot(({0: Xb}, {0: Yb}), {0: np.eye(128) / 128},
+                                         eps=float(g["eps"]), err_norm="l2sq")
+    np.testing.assert_allclose(Tv[::256], g["rows"], rtol=1e-10, atol=0)
+    np.testing.assert_allclose(Tv.sum(1), g["rowsum"], rtol=1e-12)
+    np.testing.assert_allclose(np.linalg.norm(Tv), g["fro"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("norm,phase,incl", [("l2sq", 1, True), ("l2", 1, False), ("l1", 0, False)])
+def test_stopping_rules_consistent(norm, phase, incl):
+    """kernel- and log-domain solvers stop at the same iteration under each rule."""
+    rng = np.random.default_rng(3)
+    centers = rng.standard_normal((4, 8))
+    X = centers[rng.integers(0, 4, 96)] + 0.3 * rng.standard_normal((96, 8))
+    Y = centers[rng.integers(0, 4, 80)] + 0.3 * rng.standard_normal((80, 8))
+    C = orc.sqeuclid_cost(X, Y)
+    C /= C.max()
+    a = np.ones(96) / 96
+    b = np.ones(80) / 80
+    eps = 0.02
+    tol = {"l2sq": 1e-9, "l2": 1e-7, "l1": 1e-3}[norm]
+    f0 = eps * np.log(a)
+    Pl, ll = orc.sinkhorn_log(C, a, b, eps, max_iter=2000, tol=tol, err_norm=norm,
+                              check_phase=phase, stop_inclusive=incl, f0=f0, log=True)
+    if phase == 1:
+        Pk, lk = orc.sinkhorn_knopp(a, b, M=C, reg=eps, numItermax=2000, stopThr=tol,
+                                    err_norm=norm, log=True)
+        assert lk["n_iter"] == ll["n_iter"] and ll["n_iter"] > 20
+        np.testing.assert_allclose(Pl, Pk, rtol=1e-8, atol=1e-300)
+    assert ll["converged"]
+
+
+def test_epilogues():
+    rng = np.random.default_rng(0)
+    T = rng.random((6, 6))
+    T[2] = 0.0
+    T[3, 1] = np.nan
+    Tn = orc.plan_guard_rownorm(T)
+    assert np.isfinite(Tn).all()
+    np.testing.assert_allclose(np.delete(Tn.sum(1), 2), 1.0)
+    V = rng.standard_normal((4, 6))
+    np.testing.assert_allclose(orc.apply_plan_T(V, Tn), V @ Tn.T)
+    P = rng.random((5, 7))
+    P[1] = 0
+    Yv = rng.standard_normal((7, 3))
+    B = orc.barycentric(P, Yv)
+    assert np.allclose(B[1], 0) and np.allclose(B[0], P[0] @ Yv / P[0].sum())
+    x = rng.standard_normal((4, 6))
+    assert abs(orc.cosine_loss(x, x)) < 1e-12
+    assert abs(orc.cosine_loss(x, -x) - 2) < 1e-12
+
+
+def test_envelope_grads_match_autograd():
+    import torch
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((7, 5))
+    Y = rng.standard_normal((9, 5))
+    P = rng.random((7, 9))
+    Xt = torch.tensor(X, requires_grad=True)
+    Yt = torch.tensor(Y, requires_grad=True)
+    C = (Xt * Xt).sum(1)[:, None] + (Yt * Yt).sum(1)[None, :] - 2 * Xt @ Yt.T
+    (torch.tensor(P) * C).sum().backward()
+    dX, dY = orc.envelope_grads(X, Y, P)
+    np.testing.assert_allclose(dX, Xt.grad.numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(dY, Yt.grad.numpy(), rtol=1e-12, atol=1e-12)
