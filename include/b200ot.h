@@ -1,0 +1,201 @@
+/*
+ * b200ot.h -- C ABI of the B200-native entropic optimal-transport engine.
+ *
+ * This is the drop-in boundary for the OT hot path of the reference
+ * (SURVEY.md section 8b).  The reference has no FFI of its own: the path is a
+ * chain of Python calls into POT / ott-jax / perturbot.  Each entry point below
+ * names the reference call it replaces (file:line relative to /root/reference).
+ * The Python host (b200ot/) binds these symbols with ctypes and re-exposes them
+ * under the reference's own function names.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer, including the workspace; the library never
+ *     allocates or frees device memory;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *     except b200ot_sinkhorn_solve, which polls a pinned flag between chunks;
+ *   - return value: 0 on success, <0 = B200OT_E_* (never a C++ exception);
+ *   - matrices are row-major fp32 with an explicit leading dimension (elements).
+ *     The single-sweep Sinkhorn path needs ldc % 4 == 0 and 16-byte aligned
+ *     bases; other shapes are served by the generic kernels.
+ *   - potentials cross the ABI in natural units (f, g with P = exp((f+g-C)/eps)).
+ */
+#ifndef B200OT_H_
+#define B200OT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200OT_VERSION 100
+
+/* status codes */
+#define B200OT_OK 0
+#define B200OT_E_INVALID (-1)   /* bad argument (null pointer, non-positive size, misalignment) */
+#define B200OT_E_WORKSPACE (-2) /* workspace too small */
+#define B200OT_E_LAUNCH (-3)    /* CUDA launch / runtime failure; see b200ot_last_cuda_error */
+#define B200OT_E_UNSUPPORTED (-4)
+#define B200OT_E_NUMERIC (-5)   /* non-finite value met by the fast path (caller may retry robust) */
+
+/* error norm of the column-marginal violation */
+#define B200OT_NORM_L2 0   /* POT 0.9.6 sinkhorn_knopp (MRI_PET_OT_nojax.py:143)             */
+#define B200OT_NORM_L2SQ 1 /* in-tree mirror perturbot/perturbot/match/utils.py:88-89        */
+#define B200OT_NORM_L1 2   /* ott-jax 0.6.0 Sinkhorn (perturbot/perturbot/match/fot.py:129)   */
+
+/* which kernels run one Sinkhorn iteration */
+#define B200OT_PATH_AUTO 0
+#define B200OT_PATH_FUSED 1  /* one sweep of C per iteration (cluster kernel, TMA bulk ring)   */
+#define B200OT_PATH_ROBUST 2 /* two sweeps, running-max logsumexp in both directions          */
+
+/* cost kinds */
+#define B200OT_COST_SQEUCLIDEAN 0
+#define B200OT_COST_COSINE 1
+
+typedef struct b200ot_params {
+  float eps;           /* entropic regularisation, absolute on the cost passed in            */
+  int max_iter;        /* numItermax / max_iterations                                        */
+  float tol;           /* stopThr / threshold                                                */
+  int check_every;     /* 10 in POT, the mirror and ott                                      */
+  int check_phase;     /* error checked after 1-based iteration it when                      */
+                       /*   it % check_every == check_phase % check_every                    */
+                       /*   (1 = POT / mirror `cpt % 10 == 0`, 0 = ott inner_iterations)     */
+  int err_norm;        /* B200OT_NORM_*                                                      */
+  int stop_inclusive;  /* 1: stop when err <= tol (mirror); 0: err < tol (POT, ott)          */
+  int path;            /* B200OT_PATH_*                                                      */
+} b200ot_params;
+
+/* result block written by b200ot_sinkhorn_finish (device memory, 32 bytes) */
+typedef struct b200ot_result {
+  int n_iter;     /* completed (g,f) updates                                                 */
+  int converged;  /* 1 if the stopping rule fired                                            */
+  int status;     /* 0 ok, B200OT_E_NUMERIC if the fast path met a non-finite / vanished sum */
+  int n_err;      /* number of recorded error checks                                         */
+  float err;      /* last evaluated marginal error                                           */
+  float reserved[3];
+} b200ot_result;
+
+int b200ot_version(void);
+const char* b200ot_strerror(int code);
+/* last CUDA runtime error string seen by this thread's failing call (host pointer) */
+const char* b200ot_last_cuda_error(void);
+
+/* ---- cost construction ---------------------------------------------------
+ * C_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j   (kind = SQEUCLIDEAN) or 1 - cos(x_i,y_j).
+ * Replaces ot.dist(X, Y) (MRI_PET_OT_nojax.py:70-71) and is the T = I case of the
+ * feature cost M = t1 (+) t2 - 2 X^T Ts Y (MRI_PET_OT_nojax.py:121-136,
+ * perturbot/perturbot/match/utils.py:125-184).  X is n x d (ldx), Y is m x d (ldy).
+ * cost_simt is the fp32 FMA version; `norms` is scratch for n + m floats.          */
+int b200ot_cost_simt(const float* X, int ldx, const float* Y, int ldy, int n, int m, int d,
+                     int kind, float* C, int ldc, float* norms, void* stream);
+
+/* FOT feature cost M = (A.^2)^T w1 (+) (B.^2)^T w2 - 2 A^T Ts B with A n x d, B n2 x d2,
+ * Ts n x n2 (MRI_PET_OT_nojax.py:121-136; perturbot/perturbot/match/fot.py:118-128).
+ * tmp must hold n*d2 + d + d2 floats.  w1 (n), w2 (n2) are the marginals the caller
+ * chose (the two reference variants sum Ts over different axes).                  */
+int b200ot_fot_cost(const float* A, int lda, const float* B, int ldb, const float* Ts, int ldt,
+                    const float* w1, const float* w2, int n, int n2, int d, int d2, float* M,
+                    int ldm, float* tmp, void* stream);
+
+/* max of a matrix (ott Geometry(scale_cost="max_cost"), fot.py:129-133) and in-place scale */
+int b200ot_matrix_max(const float* C, int ldc, int n, int m, float* out_max, void* stream);
+int b200ot_matrix_scale_by_inv(float* C, int ldc, int n, int m, const float* denom, void* stream);
+
+/* ---- Sinkhorn (log domain, fp32) -----------------------------------------
+ * Replaces ot.sinkhorn(a, b, M, reg, numItermax, stopThr) (MRI_PET_OT_nojax.py:143),
+ * sinkhorn_scaling (perturbot/perturbot/match/utils.py:6-115) and
+ * ott linear.solve(Geometry(cost_matrix=M, epsilon, scale_cost)).matrix
+ * (perturbot/perturbot/match/fot.py:129-134).  One iteration = g update then f update.
+ *
+ * Life cycle:  init -> enqueue (any number of times) -> finish.
+ *   init     stores a, b, the scaled start potentials and the stopping rule in ws and
+ *            runs the first g update (f0/g0 may be NULL = zero potentials; POT's
+ *            u=1/n start is f0 = eps*log(1/n)).  setup is init without the first g
+ *            update (row-sharded callers run it through shard_prologue/finalize).
+ *   enqueue  snapshots the potentials, then queues `iters` iterations on `path`
+ *            (B200OT_PATH_*); kernels no-op once the stopping rule has fired.
+ *   rewind   restores the snapshot of the last enqueue (used to replay a chunk whose
+ *            fast path lost a sum on the ROBUST path).
+ *   peek     copies 8 ints {it, done, converged, cur, bad, n_err, -, -} to flags8
+ *            (device or pinned host memory).
+ *   finish   writes f, g (natural units) and the result block (device memory).     */
+size_t b200ot_sinkhorn_workspace_bytes(int n, int m);
+int b200ot_sinkhorn_setup(int n, int m, const float* a, const float* b, const float* f0,
+                          const float* g0, const b200ot_params* prm, void* ws, size_t ws_bytes,
+                          void* stream);
+int b200ot_sinkhorn_init(const float* C, int ldc, int n, int m, const float* a, const float* b,
+                         const float* f0, const float* g0, const b200ot_params* prm, void* ws,
+                         size_t ws_bytes, void* stream);
+int b200ot_sinkhorn_enqueue(const float* C, int ldc, int n, int m, int iters, int path, void* ws,
+                            void* stream);
+int b200ot_sinkhorn_snapshot(int n, int m, void* ws, void* stream);
+int b200ot_sinkhorn_rewind(int n, int m, void* ws, void* stream);
+int b200ot_sinkhorn_peek(void* ws, int* flags8, void* stream);
+int b200ot_sinkhorn_finish(int n, int m, void* ws, float* f, float* g, b200ot_result* result,
+                           float* err_hist, int err_hist_cap, void* stream);
+/* blocking convenience driver: init, chunks ending on check iterations with the flags of
+ * chunk c-1 read while chunk c runs, automatic ROBUST replay of a chunk that hit
+ * E_NUMERIC, finish.  result_host is a HOST pointer (may be NULL).                  */
+int b200ot_sinkhorn_solve(const float* C, int ldc, int n, int m, const float* a, const float* b,
+                          const float* f0, const float* g0, const b200ot_params* prm, void* ws,
+                          size_t ws_bytes, float* f, float* g, b200ot_result* result_host,
+                          float* err_hist, int err_hist_cap, void* stream);
+
+/* Row-sharded form: this rank owns n_local rows of C (and of a, f); b and g
+ * are replicated.  After setup, shard_prologue leaves this rank's column sums for the first
+ * g update in s_local (m floats); shard_sweep does one f update on the local rows and
+ * leaves the local column sums of the new plan.  The caller all-reduces s_local (NCCL sum)
+ * and hands the total to shard_finalize, which every rank runs identically (marginal
+ * error, stopping rule, next g).                                                    */
+int b200ot_sinkhorn_shard_prologue(const float* C, int ldc, int n_local, int m, void* ws,
+                                   float* s_local, void* stream);
+int b200ot_sinkhorn_shard_sweep(const float* C, int ldc, int n_local, int m, int path, void* ws,
+                                float* s_local, void* stream);
+int b200ot_sinkhorn_shard_finalize(int n_local, int m, void* ws, const float* s_total,
+                                   int is_prologue, void* stream);
+
+/* ---- batched small problems (one problem per CTA, float64, kernel domain) --
+ * BASELINE config 2: per-training-step minibatch OT (MRI_PET_OT_nojax.py:679-715).
+ * Runs POT's sinkhorn_knopp arithmetic itself (u = 1/n start, v then u update, error every
+ * check_every iterations, previous-iterate restore on 0/NaN/Inf) in float64 with K resident
+ * in shared memory, so iteration counts equal the reference's.  C is batch x n x m
+ * contiguous fp32 (or NULL with X, Y given: batch x n x d and batch x m x d embeddings,
+ * cost built in-kernel in float64).  Outputs: P (batch x n x m fp32), u, v (float64),
+ * n_iter/err per problem.  n, m <= 128.                                            */
+int b200ot_sinkhorn_batched(const float* C, const float* X, const float* Y, int batch, int n,
+                            int m, int d, const float* a, const float* b,
+                            const b200ot_params* prm, float* P, double* u, double* v, int* n_iter,
+                            float* err, void* stream);
+
+/* ---- epilogues -------------------------------------------------------------
+ * plan       P_ij = exp((f_i + g_j - C_ij)/eps)   (POT's diag(u) K diag(v), utils.py:111-115;
+ *            ott's .matrix).
+ * ot_cost    <P, C> without materialising P (fot.py:137); out is one double.
+ * apply      Z = P V (normalise=0) or diag(1/rowsum(P)) P V (normalise=1), V m x dv,
+ *            without materialising P: the barycentric projection of
+ *            perturbot/perturbot/eval/match.py:202-206 and, with V = pet^T, the
+ *            reference's `pet @ T.t()` (MRI_PET_OT_OT_per_epoch_attn.py:728).
+ * apply_t    Z = P^T U (U n x du, Z m x du), same options.
+ * envelope   dX = 2 (diag(P1) X - P Y), dY = 2 (diag(P^T 1) Y - P^T X) scaled by `scale`:
+ *            gradient of <P, C(X,Y)> at fixed P (new capability).  */
+int b200ot_plan(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                float* P, int ldp, void* stream);
+int b200ot_ot_cost(const float* C, int ldc, int n, int m, const float* f, const float* g,
+                   float eps, double* out, void* stream);
+int b200ot_apply_plan(const float* C, int ldc, int n, int m, const float* f, const float* g,
+                      float eps, const float* V, int ldv, int dv, int normalise, float* Z,
+                      int ldz, void* stream);
+int b200ot_apply_plan_t(const float* C, int ldc, int n, int m, const float* f, const float* g,
+                        float eps, const float* U, int ldu, int du, int normalise, float* Z,
+                        int ldz, void* stream);
+/* fused fusion loss of the reference forward: 1 - mean_i cos(A_i, B_i)
+ * (MRI_PET_OT_nojax.py:552-560); out is one float.                                  */
+int b200ot_cosine_loss(const float* A, int lda, const float* B, int ldb, int rows, int d,
+                       float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200OT_H_ */

@@ -1,0 +1,327 @@
+"""The reference's OT call surface, served by the B200 engine.
+
+Each function keeps the name, argument meaning, return convention and warning
+behaviour of the reference call it replaces (file:line relative to the reference
+repository), so a training script swaps one import:
+
+    ot.sinkhorn(a, b, M, reg, numItermax=..)        MRI_PET_OT_nojax.py:143
+    sinkhorn_scaling(a, b, K, ...)                   perturbot/perturbot/match/utils.py:6-115
+    linear_solve(Geometry(cost_matrix=..))           perturbot/perturbot/match/fot.py:129-134
+    get_feature_coupling_pot(data, Ts, eps)          MRI_PET_OT_nojax.py:91-145
+    fot_numpy / get_coupling_fot(data, Ts, eps)      perturbot/perturbot/match/fot.py:14-220
+    mdict_to_matrix(M_dict, src, tgt)                baseline_models_fusion.py:233-239
+    init_matrix_np(X1, X2, v1, v2)                   perturbot/perturbot/match/utils.py:125-184
+
+Inputs may be NumPy arrays (as in the reference: copied to the GPU, result copied
+back as NumPy in the input dtype) or torch tensors (CPU: same; CUDA: everything
+stays on the device and the device->host->device round trip of
+MRI_PET_OT_nojax.py:683-702 disappears).
+"""
+from __future__ import annotations
+
+import math
+import time
+import warnings
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import B200OTError
+
+
+def _device(device=None) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        raise B200OTError("b200ot needs a CUDA device (B200); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class _Conv:
+    """Remembers how the caller passed arrays so results go back the same way."""
+
+    def __init__(self, ref, device=None):
+        self.is_numpy = isinstance(ref, np.ndarray) or not isinstance(ref, torch.Tensor)
+        if self.is_numpy:
+            ref = np.asarray(ref)
+            self.np_dtype = ref.dtype if ref.dtype.kind == "f" else np.dtype(np.float64)
+            self.device = _device(device)
+            self.home = None
+        else:
+            self.torch_dtype = ref.dtype if ref.dtype.is_floating_point else torch.float64
+            self.home = ref.device
+            self.device = ref.device if ref.is_cuda else _device(device)
+
+    def to_dev(self, x, dtype=torch.float32) -> Optional[torch.Tensor]:
+        if x is None:
+            return None
+        if isinstance(x, torch.Tensor):
+            return x.detach().to(device=self.device, dtype=dtype, non_blocking=True)
+        return torch.as_tensor(np.ascontiguousarray(x)).to(device=self.device, dtype=dtype, non_blocking=True)
+
+    def back(self, t: torch.Tensor):
+        if self.is_numpy:
+            return t.detach().cpu().numpy().astype(self.np_dtype, copy=False)
+        return t.to(device=self.home, dtype=self.torch_dtype)
+
+
+def _uniform(n, device):
+    return torch.full((n,), 1.0 / n, dtype=torch.float32, device=device)
+
+
+# ---------------------------------------------------------------------------
+# POT surface
+# ---------------------------------------------------------------------------
+def sinkhorn(a, b, M, reg, method="sinkhorn", numItermax=1000, stopThr=1e-9, verbose=False,
+             log=False, warn=True, warmstart=None, *, check_every=10, err_norm="l2", path="auto",
+             device=None, **kwargs):
+    """Drop-in for ``ot.sinkhorn`` as called at MRI_PET_OT_nojax.py:143.
+
+    Same stopping rule as POT 0.9.6 ``sinkhorn_knopp`` (L2 norm of the column-marginal
+    violation checked when ``ii % 10 == 0``, stop when ``err < stopThr``), same start
+    (``u = 1/n, v = 1/m``), same return value ``diag(u) K diag(v)`` -- evaluated in the
+    log domain in fp32, so it stays finite where the reference's ``exp(-M/reg)``
+    underflows.  Empty ``a`` / ``b`` mean uniform marginals, as in POT.
+    """
+    if method.lower() not in ("sinkhorn", "sinkhorn_log", "sinkhorn_stabilized"):
+        raise B200OTError(f"method {method!r} is not part of the reference's OT path")
+    cv = _Conv(M, device)
+    Md = ops.aligned_copy(cv.to_dev(M))
+    n, m = Md.shape
+    ad = _uniform(n, cv.device) if a is None or len(a) == 0 else cv.to_dev(a)
+    bd = _uniform(m, cv.device) if b is None or len(b) == 0 else cv.to_dev(b)
+    if warmstart is not None:
+        f0, g0 = (cv.to_dev(w) * float(reg) for w in warmstart)  # POT warmstart = (log u, log v)
+    else:
+        f0 = torch.full((n,), float(reg) * math.log(1.0 / n), dtype=torch.float32, device=cv.device)
+        g0 = torch.full((m,), float(reg) * math.log(1.0 / m), dtype=torch.float32, device=cv.device)
+    f, g, info = ops.sinkhorn_potentials(Md, ad, bd, float(reg), max_iter=int(numItermax),
+                                         tol=float(stopThr), check_every=check_every, check_phase=1,
+                                         err_norm=err_norm, stop_inclusive=False, path=path, f0=f0, g0=g0)
+    if warn and not info["converged"] and stopThr > 0:
+        warnings.warn("Sinkhorn did not converge. You might want to increase the number of "
+                      "iterations `numItermax` or the regularization parameter `reg`.")
+    P = ops.plan(Md, f, g, float(reg))
+    out = cv.back(P)
+    if not log:
+        return out
+    lg = {"err": cv.back(info["errs"]).tolist(), "niter": max(info["n_iter"] - 1, 0),
+          "n_iter": info["n_iter"], "converged": info["converged"],
+          "u": cv.back(torch.exp(f / float(reg))), "v": cv.back(torch.exp(g / float(reg))),
+          "log_u": cv.back(f / float(reg)), "log_v": cv.back(g / float(reg)),
+          "f": cv.back(f), "g": cv.back(g), "time": info["time"], "status": info["status"]}
+    return out, lg
+
+
+def sinkhorn_scaling(a, b, K, numItermax=1000, stopThr=1e-9, verbose=False, log=False,
+                     always_raise=False, *, device=None, **kwargs):
+    """Drop-in for the in-tree mirror ``sinkhorn_scaling`` (perturbot/perturbot/match/utils.py:6-115):
+    takes the Gibbs kernel ``K``, squared-L2 error, ``while err > stopThr`` (inclusive stop).
+    The engine works on ``-log K`` with reg = 1."""
+    cv = _Conv(K, device)
+    Kd = cv.to_dev(K, dtype=torch.float64)
+    M = (-torch.log(Kd)).to(torch.float32)
+    n, m = M.shape
+    M = ops.aligned_copy(M)
+    ad = _uniform(n, cv.device) if a is None or len(a) == 0 else cv.to_dev(a)
+    bd = _uniform(m, cv.device) if b is None or len(b) == 0 else cv.to_dev(b)
+    f0 = torch.full((n,), math.log(1.0 / n), dtype=torch.float32, device=cv.device)
+    f, g, info = ops.sinkhorn_potentials(M, ad, bd, 1.0, max_iter=int(numItermax), tol=float(stopThr),
+                                         check_every=10, check_phase=1, err_norm="l2sq",
+                                         stop_inclusive=True, f0=f0)
+    P = ops.plan(M, f, g, 1.0)
+    out = cv.back(P)
+    if not log:
+        return out
+    return out, {"err": cv.back(info["errs"]).tolist(), "u": cv.back(torch.exp(f)),
+                 "v": cv.back(torch.exp(g)), "n_iter": info["n_iter"]}
+
+
+# ---------------------------------------------------------------------------
+# ott surface (the two objects the reference touches: Geometry and linear.solve)
+# ---------------------------------------------------------------------------
+class Geometry:
+    """``ott.geometry.geometry.Geometry(cost_matrix=M, epsilon=eps, scale_cost="max_cost")``
+    as constructed at perturbot/perturbot/match/fot.py:129-133."""
+
+    def __init__(self, cost_matrix, epsilon=None, scale_cost=1.0, **kwargs):
+        self.cost_matrix = cost_matrix
+        self.epsilon = 0.05 if epsilon is None else float(epsilon)
+        self.scale_cost = scale_cost
+
+
+class SinkhornOutput:
+    def __init__(self, matrix, f, g, n_iters, converged, errors, reg_ot_cost=None):
+        self.matrix = matrix
+        self.f, self.g = f, g
+        self.n_iters = n_iters
+        self.converged = converged
+        self.errors = errors
+        self.reg_ot_cost = reg_ot_cost
+
+
+def linear_solve(geom: Geometry, a=None, b=None, max_iterations=2000, threshold=1e-3,
+                 inner_iterations=10, *, path="auto", device=None, **kwargs) -> SinkhornOutput:
+    """Drop-in for ``ott.solvers.linear.solve(geom, max_iterations=N)`` (fot.py:129-134):
+    cost divided by its max (``scale_cost="max_cost"``), eps absolute on the scaled cost,
+    zero start potentials, g-then-f updates, L1 error of the b-marginal every
+    ``inner_iterations``, stop when ``err < threshold``; ``.matrix`` is the plan."""
+    cv = _Conv(geom.cost_matrix, device)
+    Md = cv.to_dev(geom.cost_matrix)
+    n, m = Md.shape
+    Cs = ops.empty_matrix(n, m, cv.device)  # private copy: the scaling below is in place
+    Cs.copy_(Md)
+    if geom.scale_cost == "max_cost":
+        ops.scale_by_inv_(Cs, ops.matrix_max(Cs))
+    elif geom.scale_cost not in (None, 1.0, 1, "none"):
+        raise B200OTError(f"scale_cost={geom.scale_cost!r} is not used by the reference")
+    ad = _uniform(n, cv.device) if a is None else cv.to_dev(a)
+    bd = _uniform(m, cv.device) if b is None else cv.to_dev(b)
+    f, g, info = ops.sinkhorn_potentials(Cs, ad, bd, geom.epsilon, max_iter=int(max_iterations),
+                                         tol=float(threshold), check_every=int(inner_iterations),
+                                         check_phase=0, err_norm="l1", stop_inclusive=False, path=path)
+    P = ops.plan(Cs, f, g, geom.epsilon)
+    return SinkhornOutput(cv.back(P), cv.back(f), cv.back(g), info["n_iter"], info["converged"],
+                          cv.back(info["errs"]))
+
+
+# ---------------------------------------------------------------------------
+# helpers the reference callers use
+# ---------------------------------------------------------------------------
+def mdict_to_matrix(M_dict, source_labels, target_labels):
+    """Block-diagonal scatter by label (baseline_models_fusion.py:233-239); host-side."""
+    source_labels = np.asarray(source_labels)
+    target_labels = np.asarray(target_labels)
+    out = np.zeros((len(source_labels), len(target_labels)))
+    for l, M in M_dict.items():
+        out[np.ix_(np.where(source_labels == l)[0], np.where(target_labels == l)[0])] = np.asarray(M)
+    return out
+
+
+def init_matrix_np(X1, X2, v1, v2):
+    """COOT square-loss factorisation (perturbot/perturbot/match/utils.py:125-184); host-side,
+    trivial rank-1 sums.  The contraction it feeds runs on the GPU (ops.fot_cost)."""
+    X1 = np.asarray(X1)
+    X2 = np.asarray(X2)
+    c1 = np.dot(X1 ** 2, np.asarray(v1, dtype=np.float64))
+    c2 = np.dot(np.asarray(v2, dtype=np.float64), (X2 ** 2).T)
+    return c1[:, None] + c2[None, :], X1, 2 * X2
+
+
+def _block_diag_sorted(X_dict, Y_dict, Ts):
+    keys = sorted(X_dict.keys())
+    n_x = sum(len(X_dict[l]) for l in keys)
+    n_y = sum(len(Y_dict[l]) for l in keys)
+    out = np.zeros((n_x, n_y))
+    ix = iy = 0
+    for l in keys:
+        nx, ny = len(X_dict[l]), len(Y_dict[l])
+        if l in Ts:
+            out[ix:ix + nx, iy:iy + ny] = np.asarray(Ts[l])
+        ix += nx
+        iy += ny
+    return out
+
+
+def _concat(d, keys):
+    vals = [d[l] for l in keys]
+    if isinstance(vals[0], torch.Tensor):
+        return torch.cat(vals)
+    return np.concatenate([np.asarray(v) for v in vals])
+
+
+def get_feature_coupling_pot(data, Ts, eps=5e-3, *, numItermax=2000, stopThr=1e-9, path="auto",
+                             device=None):
+    """Drop-in for ``get_feature_coupling_pot`` (MRI_PET_OT_nojax.py:91-145): sorted-label concat,
+    block-diagonal ``Ts``, feature cost ``M = t1 (+) t2 - 2 X^T Ts Y`` with ``w1 = Ts.sum(1)``,
+    ``w2 = Ts.sum(0)``, uniform feature marginals, ``ot.sinkhorn(a, b, M, reg=eps,
+    numItermax=2000)``.  Returns ``(Tv, {})``."""
+    X_dict, Y_dict = data
+    keys = sorted(X_dict.keys())
+    X = _concat(X_dict, keys)
+    Y = _concat(Y_dict, keys)
+    if isinstance(Ts, dict):
+        Ts = _block_diag_sorted(X_dict, Y_dict, Ts)
+    cv = _Conv(X, device)
+    if cv.is_numpy:
+        cv.np_dtype = np.dtype(np.float64)  # the reference's Tv is float64 (Ts promotes the cost)
+    Xd, Yd, Td = cv.to_dev(X), cv.to_dev(Y), cv.to_dev(Ts)
+    M = ops.fot_cost(Xd, Yd, Td, Td.sum(dim=1), Td.sum(dim=0))
+    d1, d2 = M.shape
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Tv = sinkhorn(_uniform(d1, cv.device), _uniform(d2, cv.device), M, eps, numItermax=numItermax,
+                      stopThr=stopThr, path=path)
+    return cv.back(Tv), {}
+
+
+def fot_numpy(X1, X2, Ts, reg, reg2, eps=1e-7, niter=2000, C1=None, C2=None, log=False,
+              verbose=False, *, device=None, path="auto"):
+    """Drop-in for ``fot_numpy`` (perturbot/perturbot/match/fot.py:14-152) with ``Ts`` fixed:
+    ``Ts /= Ts.sum()``, ``w1 = Ts.sum(0)``, ``w2 = Ts.sum(1)`` (the reference's swapped axes),
+    cost ``constC - hC1 Ts hC2^T``, inner solve = ott ``linear.solve`` semantics.  Because ``Ts``
+    never changes the reference's second BCD round repeats the first solve bit for bit and
+    exits on ``delta < 1e-16`` (:145); that repeat is not re-run here."""
+    cv = _Conv(X1, device)
+    Xd, Yd = cv.to_dev(X1), cv.to_dev(X2)
+    Td = cv.to_dev(Ts, dtype=torch.float64)
+    Td = (Td / Td.sum()).to(torch.float32)
+    M = ops.fot_cost(Xd, Yd, Td, Td.sum(dim=0), Td.sum(dim=1))
+    cost_unscaled = M.clone() if log else None
+    t0 = time.time()
+    out = linear_solve(Geometry(cost_matrix=M, epsilon=reg2, scale_cost="max_cost"), max_iterations=niter,
+                       path=path)
+    Tv_d = out.matrix
+    if log:
+        cost = float((cost_unscaled.double() * Tv_d.double()).sum())
+        return cv.back(Tv_d), cost, {"cost": [cost, cost], "time": time.time() - t0, "n_iters": out.n_iters}
+    return cv.back(Tv_d), float("nan")
+
+
+def get_coupling_fot(data, Ts, eps=5e-3, *, device=None, path="auto"):
+    """Drop-in for ``get_coupling_fot`` (perturbot/perturbot/match/fot.py:155-220): first-seen
+    label order, ``mdict_to_matrix`` block-diagonal ``Ts``, ``fot_numpy(X, Y, Ts, eps, eps, niter=2000)``.
+    Returns ``(Tv, log)``."""
+    X_dict, Y_dict = data
+    keys = list(X_dict.keys())
+    if isinstance(Ts, dict):
+        Ts = mdict_to_matrix(
+            Ts,
+            np.concatenate([np.ones(len(X_dict[l])) * l for l in keys]),
+            np.concatenate([np.ones(len(Y_dict[l])) * l for l in keys]))
+    X = _concat(X_dict, keys)
+    Y = _concat(Y_dict, keys)
+    t0 = time.time()
+    Tv, cost, lg = fot_numpy(X, Y, Ts, eps, eps, niter=2000, log=True, device=device, path=path)
+    lg["time"] = time.time() - t0
+    return Tv, lg
+
+
+# ---------------------------------------------------------------------------
+# north-star surface: embeddings in, plan / loss / fused embedding out
+# ---------------------------------------------------------------------------
+def sinkhorn_from_embeddings(x, y, a=None, b=None, reg=0.05, numItermax=1000, stopThr=1e-9,
+                             cost="sqeuclidean", check_every=10, err_norm="l2", path="auto",
+                             return_plan=False, V=None, device=None):
+    """Embeddings (host or device) -> cost on the GPU -> Sinkhorn -> potentials, OT cost and,
+    if ``V`` is given, the barycentric projection ``diag(1/P1) P V``; the plan itself is only
+    materialised when ``return_plan`` is set.  Returns a dict."""
+    cv = _Conv(x, device)
+    xd, yd = cv.to_dev(x), cv.to_dev(y)
+    n, m = xd.shape[0], yd.shape[0]
+    Cm = ops.cost_matrix(xd, yd, kind=cost)
+    ad = _uniform(n, cv.device) if a is None else cv.to_dev(a)
+    bd = _uniform(m, cv.device) if b is None else cv.to_dev(b)
+    f0 = torch.full((n,), float(reg) * math.log(1.0 / n), dtype=torch.float32, device=cv.device)
+    f, g, info = ops.sinkhorn_potentials(Cm, ad, bd, float(reg), max_iter=int(numItermax), tol=float(stopThr),
+                                         check_every=check_every, check_phase=1, err_norm=err_norm,
+                                         path=path, f0=f0)
+    out = {"f": cv.back(f), "g": cv.back(g), "n_iter": info["n_iter"], "converged": info["converged"],
+           "err": info["err"], "ot_cost": float(ops.ot_cost(Cm, f, g, float(reg)).item())}
+    if V is not None:
+        out["fused"] = cv.back(ops.apply_plan(Cm, f, g, float(reg), cv.to_dev(V), normalise=True))
+    if return_plan:
+        out["plan"] = cv.back(ops.plan(Cm, f, g, float(reg)))
+    return out

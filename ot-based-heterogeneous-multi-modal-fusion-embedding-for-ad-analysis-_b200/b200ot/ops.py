@@ -1,0 +1,336 @@
+"""Device-level operators: thin, typed wrappers of the C ABI on CUDA torch tensors.
+
+PyTorch is used for device memory and streams only; every computation below is a
+call into libb200ot.so.  Nothing here falls back to torch math or to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import B200OTError, Params, Result, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise B200OTError(f"{name} must be a CUDA tensor (b200ot has no CPU path)")
+    if t.dtype != dtype:
+        raise B200OTError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def _matrix(t: torch.Tensor, name: str):
+    """fp32 CUDA matrix with unit column stride; returns (tensor, ld)."""
+    _need_cuda(t, name)
+    if t.dim() != 2:
+        raise B200OTError(f"{name} must be 2-D")
+    if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+def _vector(t: torch.Tensor, name: str, length: int, dtype=torch.float32):
+    _need_cuda(t, name, dtype)
+    t = t.reshape(-1)
+    if t.numel() != length:
+        raise B200OTError(f"{name} has {t.numel()} entries, expected {length}")
+    return t.contiguous()
+
+
+def empty_matrix(n: int, m: int, device) -> torch.Tensor:
+    """n x m fp32 matrix whose row stride is a multiple of 4 floats and whose base is
+    16-byte aligned, i.e. eligible for the single-sweep Sinkhorn kernel."""
+    ld = (m + 3) // 4 * 4
+    return torch.empty((n, ld), dtype=torch.float32, device=device)[:, :m]
+
+
+def aligned_copy(Cm: torch.Tensor) -> torch.Tensor:
+    """Return Cm itself if it already meets the fused kernel's layout, else a padded copy."""
+    if (Cm.stride(1) == 1 and Cm.stride(0) % 4 == 0 and Cm.data_ptr() % 16 == 0
+            and Cm.shape[1] % 4 == 0):
+        return Cm
+    if Cm.shape[1] % 4 != 0:
+        return Cm  # generic kernels handle it; padding cannot make m a multiple of 4
+    out = empty_matrix(Cm.shape[0], Cm.shape[1], Cm.device)
+    out.copy_(Cm)
+    return out
+
+
+# ---------------------------------------------------------------------------
+# cost construction
+# ---------------------------------------------------------------------------
+def cost_matrix(x: torch.Tensor, y: torch.Tensor, kind: str = "sqeuclidean",
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  or  1 - cos(x_i, y_j) (include/b200ot.h: b200ot_cost_simt)."""
+    lib = _lib.load()
+    x, ldx = _matrix(x, "x")
+    y, ldy = _matrix(y, "y")
+    n, d = x.shape
+    m, d2 = y.shape
+    if d != d2:
+        raise B200OTError("x and y must have the same feature width")
+    if out is None:
+        out = empty_matrix(n, m, x.device)
+    out, ldc = _matrix(out, "out")
+    norms = torch.empty(n + m, dtype=torch.float32, device=x.device)
+    check(lib.b200ot_cost_simt(_ptr(x), ldx, _ptr(y), ldy, n, m, d, _lib.COSTS[kind], _ptr(out), ldc,
+                               _ptr(norms), _stream()), "b200ot_cost_simt")
+    return out
+
+
+def fot_cost(A: torch.Tensor, B: torch.Tensor, Ts: torch.Tensor, w1: torch.Tensor,
+             w2: torch.Tensor) -> torch.Tensor:
+    """M = (A.^2)^T w1 (+) (B.^2)^T w2 - 2 A^T Ts B (b200ot_fot_cost)."""
+    lib = _lib.load()
+    A, lda = _matrix(A, "A")
+    B, ldb = _matrix(B, "B")
+    Ts, ldt = _matrix(Ts, "Ts")
+    n, d = A.shape
+    n2, d2 = B.shape
+    if Ts.shape != (n, n2):
+        raise B200OTError(f"Ts must be {n} x {n2}")
+    w1 = _vector(w1, "w1", n)
+    w2 = _vector(w2, "w2", n2)
+    M = empty_matrix(d, d2, A.device)
+    tmp = torch.empty(n * d2 + d + d2, dtype=torch.float32, device=A.device)
+    check(lib.b200ot_fot_cost(_ptr(A), lda, _ptr(B), ldb, _ptr(Ts), ldt, _ptr(w1), _ptr(w2), n, n2, d, d2,
+                              _ptr(M), M.stride(0), _ptr(tmp), _stream()), "b200ot_fot_cost")
+    return M
+
+
+def matrix_max(Cm: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    Cm, ldc = _matrix(Cm, "C")
+    out = torch.empty(1, dtype=torch.float32, device=Cm.device)
+    check(lib.b200ot_matrix_max(_ptr(Cm), ldc, Cm.shape[0], Cm.shape[1], _ptr(out), _stream()),
+          "b200ot_matrix_max")
+    return out
+
+
+def scale_by_inv_(Cm: torch.Tensor, denom: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    if Cm.stride(1) != 1:
+        raise B200OTError("in-place scale needs unit column stride")
+    check(lib.b200ot_matrix_scale_by_inv(_ptr(Cm), Cm.stride(0), Cm.shape[0], Cm.shape[1], _ptr(denom),
+                                         _stream()), "b200ot_matrix_scale_by_inv")
+    return Cm
+
+
+# ---------------------------------------------------------------------------
+# Sinkhorn
+# ---------------------------------------------------------------------------
+_WS_CACHE: dict = {}
+
+
+def _workspace(n: int, m: int, device) -> torch.Tensor:
+    lib = _lib.load()
+    need = lib.b200ot_sinkhorn_workspace_bytes(n, m)
+    key = (torch.device(device).index, n, m)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < need:
+        if len(_WS_CACHE) > 8:
+            _WS_CACHE.clear()
+        ws = torch.empty(need + 256, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def _ws_ptr(ws: torch.Tensor):
+    base = ws.data_ptr()
+    return C.c_void_p((base + 255) // 256 * 256)
+
+
+def make_params(eps, max_iter, tol, check_every=10, check_phase=1, err_norm="l2",
+                stop_inclusive=False, path="auto") -> Params:
+    return Params(float(eps), int(max_iter), float(tol), int(check_every), int(check_phase),
+                  _lib.NORMS[err_norm], int(bool(stop_inclusive)), _lib.PATHS[path])
+
+
+def sinkhorn_potentials(Cm: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float,
+                        max_iter: int = 1000, tol: float = 1e-9, check_every: int = 10,
+                        check_phase: int = 1, err_norm: str = "l2", stop_inclusive: bool = False,
+                        path: str = "auto", f0: Optional[torch.Tensor] = None,
+                        g0: Optional[torch.Tensor] = None, err_hist_cap: int = 512):
+    """Log-domain Sinkhorn on a cost matrix resident in HBM (b200ot_sinkhorn_solve).
+
+    Returns ``(f, g, info)`` with ``P = exp((f_i + g_j - C_ij)/eps)``; ``info`` has
+    ``n_iter``, ``converged``, ``err``, ``errs`` (error history), ``status``, ``time``.
+    """
+    lib = _lib.load()
+    Cm, ldc = _matrix(Cm, "C")
+    n, m = Cm.shape
+    a = _vector(a, "a", n)
+    b = _vector(b, "b", m)
+    f0 = None if f0 is None else _vector(f0, "f0", n)
+    g0 = None if g0 is None else _vector(g0, "g0", m)
+    ws = _workspace(n, m, Cm.device)
+    f = torch.empty(n, dtype=torch.float32, device=Cm.device)
+    g = torch.empty(m, dtype=torch.float32, device=Cm.device)
+    errs = torch.zeros(max(1, err_hist_cap), dtype=torch.float32, device=Cm.device)
+    prm = make_params(eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive, path)
+    res = Result()
+    t0 = time.perf_counter()
+    check(lib.b200ot_sinkhorn_solve(_ptr(Cm), ldc, n, m, _ptr(a), _ptr(b), _ptr(f0), _ptr(g0),
+                                    C.byref(prm), _ws_ptr(ws), ws.numel() - 256, _ptr(f), _ptr(g),
+                                    C.byref(res), _ptr(errs), errs.numel(), _stream()),
+          "b200ot_sinkhorn_solve")
+    info = {"n_iter": res.n_iter, "converged": bool(res.converged), "err": res.err,
+            "status": res.status, "n_err": res.n_err, "time": time.perf_counter() - t0,
+            "errs": errs[:min(res.n_err, errs.numel())]}
+    return f, g, info
+
+
+class SinkhornStepper:
+    """Asynchronous life cycle (init / enqueue / finish) for callers that drive the
+    iteration themselves: bench loops, CUDA-graph capture, the row-sharded solver."""
+
+    def __init__(self, Cm: torch.Tensor, a, b, eps, max_iter=1000, tol=0.0, check_every=10,
+                 check_phase=1, err_norm="l2", stop_inclusive=False, path="auto", f0=None, g0=None):
+        self.lib = _lib.load()
+        self.C, self.ldc = _matrix(Cm, "C")
+        self.n, self.m = self.C.shape
+        self.a = _vector(a, "a", self.n)
+        self.b = _vector(b, "b", self.m)
+        self.prm = make_params(eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive,
+                               path)
+        self.path = _lib.PATHS[path]
+        self.ws = torch.empty(self.lib.b200ot_sinkhorn_workspace_bytes(self.n, self.m) + 256,
+                              dtype=torch.uint8, device=self.C.device)
+        self.f0 = None if f0 is None else _vector(f0, "f0", self.n)
+        self.g0 = None if g0 is None else _vector(g0, "g0", self.m)
+        self.reset()
+
+    def reset(self):
+        check(self.lib.b200ot_sinkhorn_init(_ptr(self.C), self.ldc, self.n, self.m, _ptr(self.a),
+                                            _ptr(self.b), _ptr(self.f0), _ptr(self.g0),
+                                            C.byref(self.prm), _ws_ptr(self.ws), self.ws.numel() - 256,
+                                            _stream()), "b200ot_sinkhorn_init")
+
+    def enqueue(self, iters: int):
+        check(self.lib.b200ot_sinkhorn_enqueue(_ptr(self.C), self.ldc, self.n, self.m, int(iters),
+                                               self.path, _ws_ptr(self.ws), _stream()),
+              "b200ot_sinkhorn_enqueue")
+
+    def flags(self) -> dict:
+        out = torch.empty(8, dtype=torch.int32, device=self.C.device)
+        check(self.lib.b200ot_sinkhorn_peek(_ws_ptr(self.ws), _ptr(out), _stream()), "b200ot_sinkhorn_peek")
+        v = out.cpu().tolist()
+        return {"it": v[0], "done": v[1], "converged": v[2], "cur": v[3], "bad": v[4], "n_err": v[5]}
+
+    def finish(self, err_hist_cap: int = 512):
+        f = torch.empty(self.n, dtype=torch.float32, device=self.C.device)
+        g = torch.empty(self.m, dtype=torch.float32, device=self.C.device)
+        res = torch.zeros(8, dtype=torch.int32, device=self.C.device)
+        errs = torch.zeros(err_hist_cap, dtype=torch.float32, device=self.C.device)
+        check(self.lib.b200ot_sinkhorn_finish(self.n, self.m, _ws_ptr(self.ws), _ptr(f), _ptr(g), _ptr(res),
+                                              _ptr(errs), err_hist_cap, _stream()), "b200ot_sinkhorn_finish")
+        r = res.cpu()
+        n_err = int(r[3])
+        info = {"n_iter": int(r[0]), "converged": bool(r[1]), "status": int(r[2]), "n_err": n_err,
+                "err": float(r[4:5].view(torch.float32)[0]), "errs": errs[:min(n_err, err_hist_cap)]}
+        return f, g, info
+
+
+def sinkhorn_batched(a: torch.Tensor, b: torch.Tensor, eps: float, *, C3: Optional[torch.Tensor] = None,
+                     X: Optional[torch.Tensor] = None, Y: Optional[torch.Tensor] = None,
+                     max_iter: int = 1000, tol: float = 1e-9, check_every: int = 10, check_phase: int = 1,
+                     err_norm: str = "l2", stop_inclusive: bool = False):
+    """Batch of independent small problems, one per CTA, float64 kernel-domain Sinkhorn-Knopp
+    (b200ot_sinkhorn_batched).  Give either C3 (B x n x m) or embeddings X (B x n x d), Y (B x m x d)."""
+    lib = _lib.load()
+    if C3 is not None:
+        _need_cuda(C3, "C3")
+        C3 = C3.contiguous()
+        B, n, m = C3.shape
+        d = 0
+        dev = C3.device
+    else:
+        _need_cuda(X, "X")
+        _need_cuda(Y, "Y")
+        X = X.contiguous()
+        Y = Y.contiguous()
+        B, n, d = X.shape
+        B2, m, d2 = Y.shape
+        if B != B2 or d != d2:
+            raise B200OTError("X and Y batch / width mismatch")
+        dev = X.device
+    a = _vector(a, "a", n)
+    b = _vector(b, "b", m)
+    P = torch.empty((B, n, m), dtype=torch.float32, device=dev)
+    u = torch.empty((B, n), dtype=torch.float64, device=dev)
+    v = torch.empty((B, m), dtype=torch.float64, device=dev)
+    n_iter = torch.empty(B, dtype=torch.int32, device=dev)
+    err = torch.empty(B, dtype=torch.float32, device=dev)
+    prm = make_params(eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive)
+    check(lib.b200ot_sinkhorn_batched(_ptr(C3), _ptr(X), _ptr(Y), B, n, m, d, _ptr(a), _ptr(b),
+                                      C.byref(prm), _ptr(P), _ptr(u), _ptr(v), _ptr(n_iter), _ptr(err),
+                                      _stream()), "b200ot_sinkhorn_batched")
+    return P, {"u": u, "v": v, "n_iter": n_iter, "err": err}
+
+
+# ---------------------------------------------------------------------------
+# epilogues
+# ---------------------------------------------------------------------------
+def plan(Cm, f, g, eps, out=None):
+    lib = _lib.load()
+    Cm, ldc = _matrix(Cm, "C")
+    n, m = Cm.shape
+    f = _vector(f, "f", n)
+    g = _vector(g, "g", m)
+    if out is None:
+        out = torch.empty((n, m), dtype=torch.float32, device=Cm.device)
+    out, ldp = _matrix(out, "out")
+    check(lib.b200ot_plan(_ptr(Cm), ldc, n, m, _ptr(f), _ptr(g), float(eps), _ptr(out), ldp, _stream()),
+          "b200ot_plan")
+    return out
+
+
+def ot_cost(Cm, f, g, eps):
+    lib = _lib.load()
+    Cm, ldc = _matrix(Cm, "C")
+    n, m = Cm.shape
+    out = torch.empty(1, dtype=torch.float64, device=Cm.device)
+    check(lib.b200ot_ot_cost(_ptr(Cm), ldc, n, m, _ptr(_vector(f, "f", n)), _ptr(_vector(g, "g", m)),
+                             float(eps), _ptr(out), _stream()), "b200ot_ot_cost")
+    return out
+
+
+def apply_plan(Cm, f, g, eps, V, normalise=False, transpose=False):
+    """Z = P V (or P^T V with transpose=True), optionally row-normalised, without forming P."""
+    lib = _lib.load()
+    Cm, ldc = _matrix(Cm, "C")
+    n, m = Cm.shape
+    V, ldv = _matrix(V, "V")
+    rows_in, rows_out = (n, m) if transpose else (m, n)
+    if V.shape[0] != rows_in:
+        raise B200OTError(f"V must have {rows_in} rows")
+    dv = V.shape[1]
+    Z = torch.empty((rows_out, dv), dtype=torch.float32, device=Cm.device)
+    fn = lib.b200ot_apply_plan_t if transpose else lib.b200ot_apply_plan
+    check(fn(_ptr(Cm), ldc, n, m, _ptr(_vector(f, "f", n)), _ptr(_vector(g, "g", m)), float(eps), _ptr(V),
+             ldv, dv, int(bool(normalise)), _ptr(Z), Z.stride(0), _stream()), "b200ot_apply_plan")
+    return Z
+
+
+def cosine_loss(A, B):
+    lib = _lib.load()
+    A, lda = _matrix(A, "A")
+    B, ldb = _matrix(B, "B")
+    if A.shape != B.shape:
+        raise B200OTError("cosine_loss operands must have the same shape")
+    out = torch.empty(1, dtype=torch.float32, device=A.device)
+    check(lib.b200ot_cosine_loss(_ptr(A), lda, _ptr(B), ldb, A.shape[0], A.shape[1], _ptr(out), _stream()),
+          "b200ot_cosine_loss")
+    return out

@@ -1,0 +1,245 @@
+// Batched small-problem Sinkhorn: one problem per CTA, float64, kernel domain.
+//
+// This is the per-training-step minibatch OT of the reference
+// (MRI_PET_OT_nojax.py:679-715 -> get_feature_coupling_pot :91-145 -> ot.sinkhorn :143) run for a
+// whole batch of independent problems at once.  The arithmetic is POT's sinkhorn_knopp as
+// mirrored in perturbot/perturbot/match/utils.py:6-115, in float64 like the reference:
+//   K = exp(-M/reg);  u = 1/n, v = 1/m;  Kp = (1/a) K
+//   loop:  v = b / (K^T u);  u = 1 / (Kp v)
+//          on K^T u == 0 or NaN/Inf in u, v: restore the previous u, v and stop  (:55-79)
+//          every check_every-th iteration: err = |colsum(diag(u) K diag(v)) - b|  (:80-89)
+//   P = diag(u) K diag(v)                                                          (:111-115)
+// K stays in shared memory for the whole solve (n, m <= 128), so a solve touches HBM only to
+// read the embeddings / cost and to write the plan.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200ot {
+
+constexpr int BT = 256;  // threads per problem
+
+struct BatchedArgs {
+  const float* C;  // batch x n x m, or null
+  const float* X;  // batch x n x d
+  const float* Y;  // batch x m x d
+  int batch, n, m, d;
+  const float* a;  // n (shared by all problems)
+  const float* b;  // m
+  double reg;
+  int max_iter, check_every, check_phase, err_norm, stop_inclusive;
+  double tol;
+  float* P;      // batch x n x m
+  double* u;     // batch x n  (may be null)
+  double* v;     // batch x m  (may be null)
+  int* n_iter;   // batch      (may be null)
+  float* err;    // batch      (may be null)
+};
+
+__device__ __forceinline__ bool bad_value(double x) { return isnan(x) || isinf(x); }
+
+__global__ void __launch_bounds__(BT) sinkhorn_batched_kernel(const BatchedArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = p.n, m = p.m;
+  const int ldk = m | 1;  // odd row stride: the row pass reads K down a column of banks
+  double* K = reinterpret_cast<double*>(smem_raw);      // n x ldk
+  double* u = K + (size_t)n * ldk;                      // n
+  double* v = u + n;                                    // m
+  double* up = v + m;                                   // previous iterates
+  double* vp = up + n;
+  double* ktu = vp + m;                                 // m
+  double* scratch = ktu + m;                            // BT doubles
+  __shared__ int flag_sh;
+  __shared__ double err_sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = BT / 32;
+
+  for (int prob = blockIdx.x; prob < p.batch; prob += gridDim.x) {
+    // ---- K = exp(-M/reg) ----
+    if (p.C) {
+      const float* Cp = p.C + (size_t)prob * n * m;
+      for (int e = tid; e < n * m; e += BT) {
+        const int i = e / m, j = e - i * m;
+        K[i * ldk + j] = exp(-(double)Cp[e] / p.reg);
+      }
+    } else {
+      // squared-Euclidean cost from the embeddings, accumulated in float64
+      const float* Xp = p.X + (size_t)prob * n * p.d;
+      const float* Yp = p.Y + (size_t)prob * m * p.d;
+      for (int e = tid; e < n * m; e += BT) {
+        const int i = e / m, j = e - i * m;
+        const float* x = Xp + (size_t)i * p.d;
+        const float* y = Yp + (size_t)j * p.d;
+        double xx = 0.0, yy = 0.0, xy = 0.0;
+        for (int c = 0; c < p.d; ++c) {
+          const double xv = x[c], yv = y[c];
+          xx = fma(xv, xv, xx);
+          yy = fma(yv, yv, yy);
+          xy = fma(xv, yv, xy);
+        }
+        K[i * ldk + j] = exp(-((xx + yy) - 2.0 * xy) / p.reg);
+      }
+    }
+    for (int i = tid; i < n; i += BT) u[i] = 1.0 / n;
+    for (int j = tid; j < m; j += BT) v[j] = 1.0 / m;
+    if (tid == 0) {
+      flag_sh = 0;
+      err_sh = 1.0;
+    }
+    __syncthreads();
+
+    int cpt = 0;
+    double err = 1.0;
+    while (cpt < p.max_iter) {
+      // save previous iterates
+      for (int i = tid; i < n; i += BT) up[i] = u[i];
+      for (int j = tid; j < m; j += BT) vp[j] = v[j];
+      // K^T u : thread (j, part) sums a slice of rows; parts folded through shared memory
+      {
+        const int parts = BT / m > 0 ? BT / m : 1;  // m <= 128 -> parts >= 2
+        const int j = tid % m, part = tid / m;
+        double s = 0.0;
+        if (part < parts)
+          for (int i = part; i < n; i += parts) s = fma(K[i * ldk + j], u[i], s);
+        scratch[tid] = s;
+        __syncthreads();
+        if (tid < m) {
+          double t = 0.0;
+          for (int q = 0; q < parts; ++q) t += scratch[q * m + tid];
+          ktu[tid] = t;
+          v[tid] = p.b[tid] / t;
+        }
+        __syncthreads();
+      }
+      // u = 1 / (Kp v), Kp = (1/a) K : one warp per row, lanes across columns
+      for (int i = warp; i < n; i += NW) {
+        const double ia = 1.0 / (double)p.a[i];
+        double s = 0.0;
+        for (int j = lane; j < m; j += 32) s = fma(ia * K[i * ldk + j], v[j], s);
+        s = warp_sum(s);
+        if (lane == 0) u[i] = 1.0 / s;
+      }
+      __syncthreads();
+      // numerical guard (utils.py:55-79)
+      {
+        int bad = 0;
+        for (int j = tid; j < m; j += BT) bad |= (ktu[j] == 0.0) || bad_value(v[j]);
+        for (int i = tid; i < n; i += BT) bad |= bad_value(u[i]);
+        if (bad) flag_sh = 1;
+        __syncthreads();
+        if (flag_sh) {
+          for (int i = tid; i < n; i += BT) u[i] = up[i];
+          for (int j = tid; j < m; j += BT) v[j] = vp[j];
+          __syncthreads();
+          break;
+        }
+      }
+      if (cpt % p.check_every == ((p.check_phase + p.check_every - 1) % p.check_every)) {
+        // column marginal of diag(u) K diag(v)
+        const int parts = BT / m > 0 ? BT / m : 1;
+        const int j = tid % m, part = tid / m;
+        double s = 0.0;
+        if (part < parts)
+          for (int i = part; i < n; i += parts) s = fma(u[i], K[i * ldk + j] * v[j], s);
+        scratch[tid] = s;
+        __syncthreads();
+        double e = 0.0;
+        if (tid < m) {
+          double t = 0.0;
+          for (int q = 0; q < parts; ++q) t += scratch[q * m + tid];
+          const double dlt = t - (double)p.b[tid];
+          e = p.err_norm == B200OT_NORM_L1 ? fabs(dlt) : dlt * dlt;
+        }
+        e = warp_sum(e);
+        __syncthreads();
+        if (lane == 0) scratch[warp] = e;
+        __syncthreads();
+        if (tid == 0) {
+          double t = 0.0;
+          for (int w = 0; w < NW; ++w) t += scratch[w];
+          err_sh = p.err_norm == B200OT_NORM_L2 ? sqrt(t) : t;
+        }
+        __syncthreads();
+        err = err_sh;
+        const bool stop = p.stop_inclusive ? (err <= p.tol) : (err < p.tol);
+        if (stop) {
+          ++cpt;
+          break;
+        }
+      }
+      ++cpt;
+    }
+
+    // ---- outputs ----
+    float* Pp = p.P + (size_t)prob * n * m;
+    for (int e = tid; e < n * m; e += BT) {
+      const int i = e / m, j = e - i * m;
+      Pp[e] = (float)(u[i] * K[i * ldk + j] * v[j]);
+    }
+    if (p.u)
+      for (int i = tid; i < n; i += BT) p.u[(size_t)prob * n + i] = u[i];
+    if (p.v)
+      for (int j = tid; j < m; j += BT) p.v[(size_t)prob * m + j] = v[j];
+    if (tid == 0) {
+      if (p.n_iter) p.n_iter[prob] = cpt;
+      if (p.err) p.err[prob] = (float)err;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace b200ot
+
+using namespace b200ot;
+
+extern "C" {
+
+int b200ot_sinkhorn_batched(const float* C, const float* X, const float* Y, int batch, int n,
+                            int m, int d, const float* a, const float* b,
+                            const b200ot_params* prm, float* P, double* u, double* v, int* n_iter,
+                            float* err, void* stream) {
+  if (!prm || !a || !b || !P || batch <= 0 || n <= 0 || m <= 0) return B200OT_E_INVALID;
+  if (!C && !(X && Y && d > 0)) return B200OT_E_INVALID;
+  if (n > 128 || m > 128 || m < 2) return B200OT_E_UNSUPPORTED;
+  if (!(prm->eps > 0.f)) return B200OT_E_INVALID;
+  BatchedArgs p;
+  p.C = C;
+  p.X = X;
+  p.Y = Y;
+  p.batch = batch;
+  p.n = n;
+  p.m = m;
+  p.d = d;
+  p.a = a;
+  p.b = b;
+  p.reg = (double)prm->eps;
+  p.max_iter = prm->max_iter;
+  p.check_every = prm->check_every > 0 ? prm->check_every : 1;
+  p.check_phase = prm->check_phase;
+  p.err_norm = prm->err_norm;
+  p.stop_inclusive = prm->stop_inclusive;
+  p.tol = (double)prm->tol;
+  p.P = P;
+  p.u = u;
+  p.v = v;
+  p.n_iter = n_iter;
+  p.err = err;
+  const int ldk = m | 1;
+  const size_t smem = ((size_t)n * ldk + 2 * (size_t)n + 3 * (size_t)m + BT) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200OT_CUDA_OK(cudaFuncSetAttribute(sinkhorn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        200 * 1024));
+    attr_set = true;
+  }
+  if (smem > 200 * 1024) return B200OT_E_UNSUPPORTED;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+  int grid = sm_count() * per_sm;
+  if (grid > batch) grid = batch;
+  sinkhorn_batched_kernel<<<grid, BT, smem, static_cast<cudaStream_t>(stream)>>>(p);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1124 @@
+// Log-domain Sinkhorn on a materialised fp32 cost matrix (streaming path).
+//
+// Replaces the reference's ot.sinkhorn / sinkhorn_scaling / ott linear.solve calls
+// (MRI_PET_OT_nojax.py:143, perturbot/perturbot/match/utils.py:6-115,
+// perturbot/perturbot/match/fot.py:129-134).  One reference iteration is
+//     g <- eps log b - eps LSE_i((f_i - C_ij)/eps)      (POT: v = b / K^T u)
+//     f <- eps log a - eps LSE_j((g_j - C_ij)/eps)      (POT: u = a / K v)
+// followed every check_every iterations by the column-marginal error of
+// exp((f+g-C)/eps).  Internally potentials are kept scaled, fs = f*log2(e)/eps, so the
+// plan entry is 2^(fs_i + gs_j - C_ij*k), k = log2(e)/eps.
+//
+// FUSED path (one HBM read of C per iteration).  For sweep k the kernel holds a group of
+// R rows on chip: t_ij = 2^(fs_i^{k-1} + gs_j^k - k C_ij) is evaluated once per element
+// and kept in registers, the row sums r_i = sum_j t_ij are reduced warp -> CTA -> cluster
+// (DSMEM), w_i = a_i / r_i gives fs_i^k = fs_i^{k-1} + log2 w_i, and the same registers
+// are folded into per-thread column accumulators s_j += t_ij w_i.  s is exactly the column
+// marginal of the plan after iteration k, i.e. both the convergence check and the input of
+// the next g update, gs_j^{k+1} = gs_j^k + log2 b_j - log2 s_j.  Every t_ij <= b_j <= 1
+// because the preceding g update normalised the columns, so no running max is needed; a
+// row or column sum that vanishes (extreme eps in the first iterations) raises the `bad`
+// flag and the host replays the chunk on the ROBUST path.
+//
+// ROBUST path: row pass and column pass as separate sweeps with running-max logsumexp.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace b200ot {
+
+constexpr int kErrHistCap = 4096;
+constexpr int kNpCap = 160;  // max partial slabs (>= clusters of the fused sweep, row splits of the robust one)
+constexpr int kFinalizeThreads = 256;
+
+struct State {
+  int it, done, converged, cur;
+  int bad, n_err, ticket, initialised;
+  float err, kscale, eps, tol;
+  int max_iter, check_every, check_phase, err_norm;
+  int stop_inclusive, path, snap_it, snap_cur;
+  int snap_n_err, pad0, pad1, pad2;
+  float snap_err, pad3, pad4, pad5;
+};
+static_assert(sizeof(State) <= 256, "state block");
+
+struct WsLayout {
+  size_t state, err_hist, errpart, fs, gs0, gs1, a, b, log2b, snap_fs, snap_gs, part_sum, part_max,
+      total;
+  size_t m_pad, n_pad;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static WsLayout ws_layout(int n, int m) {
+  WsLayout L;
+  L.m_pad = align_up((size_t)m, 64);
+  L.n_pad = align_up((size_t)n, 64);
+  size_t off = 0;
+  L.state = off;
+  off += 256;
+  L.err_hist = off;
+  off += kErrHistCap * sizeof(float);
+  L.errpart = off;
+  off += 4096 * sizeof(double);
+  auto vec = [&](size_t elems) {
+    size_t o = off;
+    off += align_up(elems * sizeof(float), 256);
+    return o;
+  };
+  L.fs = vec(L.n_pad);
+  L.gs0 = vec(L.m_pad);
+  L.gs1 = vec(L.m_pad);
+  L.a = vec(L.n_pad);
+  L.b = vec(L.m_pad);
+  L.log2b = vec(L.m_pad);
+  L.snap_fs = vec(L.n_pad);
+  L.snap_gs = vec(L.m_pad);
+  L.part_sum = vec((size_t)kNpCap * L.m_pad);
+  L.part_max = vec((size_t)kNpCap * L.m_pad);
+  L.total = off;
+  return L;
+}
+
+struct WsPtrs {
+  State* st;
+  float* err_hist;
+  double* errpart;
+  float *fs, *gs0, *gs1, *a, *b, *log2b, *snap_fs, *snap_gs, *part_sum, *part_max;
+  size_t m_pad;
+};
+static WsPtrs ws_ptrs(void* ws, const WsLayout& L) {
+  char* p = static_cast<char*>(ws);
+  WsPtrs w;
+  w.st = reinterpret_cast<State*>(p + L.state);
+  w.err_hist = reinterpret_cast<float*>(p + L.err_hist);
+  w.errpart = reinterpret_cast<double*>(p + L.errpart);
+  w.fs = reinterpret_cast<float*>(p + L.fs);
+  w.gs0 = reinterpret_cast<float*>(p + L.gs0);
+  w.gs1 = reinterpret_cast<float*>(p + L.gs1);
+  w.a = reinterpret_cast<float*>(p + L.a);
+  w.b = reinterpret_cast<float*>(p + L.b);
+  w.log2b = reinterpret_cast<float*>(p + L.log2b);
+  w.snap_fs = reinterpret_cast<float*>(p + L.snap_fs);
+  w.snap_gs = reinterpret_cast<float*>(p + L.snap_gs);
+  w.part_sum = reinterpret_cast<float*>(p + L.part_sum);
+  w.part_max = reinterpret_cast<float*>(p + L.part_max);
+  w.m_pad = L.m_pad;
+  return w;
+}
+
+// =============================================================================
+// state / vector initialisation
+// =============================================================================
+__global__ void init_kernel(State* st, b200ot_params prm, int n, int m, const float* __restrict__ a,
+                            const float* __restrict__ b, const float* __restrict__ f0,
+                            const float* __restrict__ g0, float* fs, float* gs0, float* gs1, float* wa,
+                            float* wb, float* log2b) {
+  const float k = kLog2e / prm.eps;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    State s;
+    memset(&s, 0, sizeof(s));
+    s.kscale = k;
+    s.eps = prm.eps;
+    s.tol = prm.tol;
+    s.max_iter = prm.max_iter;
+    s.check_every = prm.check_every > 0 ? prm.check_every : 1;
+    s.check_phase = prm.check_phase;
+    s.err_norm = prm.err_norm;
+    s.stop_inclusive = prm.stop_inclusive;
+    s.path = prm.path;
+    s.err = INFINITY;
+    s.initialised = 1;
+    s.done = prm.max_iter <= 0 ? 1 : 0;
+    *st = s;
+  }
+  if (i < n) {
+    fs[i] = f0 ? f0[i] * k : 0.f;
+    wa[i] = a[i];
+  }
+  if (i < m) {
+    const float g = g0 ? g0[i] * k : 0.f;
+    gs0[i] = g;
+    gs1[i] = g;
+    wb[i] = b[i];
+    log2b[i] = log2f(b[i]);
+  }
+}
+
+// =============================================================================
+// finalize: column sums -> marginal error -> stopping rule -> next g
+// =============================================================================
+// part_sum[p][j] (and optional part_max[p][j]: the sums are relative to 2^max) for p < np.
+// Writes gs_next = gs_cur + log2 b - log2 s and lets the LAST block (ticket) fold the
+// per-block error partials in fixed order and advance the state machine.
+__global__ void __launch_bounds__(kFinalizeThreads)
+    finalize_kernel(State* st, const float* __restrict__ part_sum, const float* __restrict__ part_max,
+                    int np, size_t stride, int m, const float* __restrict__ b,
+                    const float* __restrict__ log2b, float* gs0, float* gs1, double* errpart,
+                    float* err_hist, int is_prologue) {
+  if (st->done) return;
+  const int cur = st->cur;
+  const float* gcur = cur ? gs1 : gs0;
+  float* gnext = cur ? gs0 : gs1;
+  const int norm = st->err_norm;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0;
+  int bad = 0;
+  if (j < m) {
+    float s, l2s;
+    if (part_max) {
+      float M = -INFINITY;
+      for (int p = 0; p < np; ++p) M = fmaxf(M, part_max[(size_t)p * stride + j]);
+      float acc = 0.f;
+      for (int p = 0; p < np; ++p) {
+        const float pm = part_max[(size_t)p * stride + j];
+        if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm - M);
+      }
+      l2s = M + log2f(acc);
+      s = exp2f(l2s);
+    } else {
+      float acc = 0.f;
+      for (int p = 0; p < np; ++p) acc += part_sum[(size_t)p * stride + j];
+      s = acc;
+      l2s = log2f(acc);
+    }
+    const float bj = b[j];
+    const double d = (double)s - (double)bj;
+    e = (norm == B200OT_NORM_L1) ? fabs(d) : d * d;
+    const float gn = gcur[j] + (log2b[j] - l2s);
+    gnext[j] = gn;
+    if (bj > 0.f && !(fabsf(gn) < INFINITY)) bad = 1;
+  }
+  // block reduce (fixed tree)
+  __shared__ double sh[kFinalizeThreads / 32];
+  __shared__ int shbad;
+  if (threadIdx.x == 0) shbad = 0;
+  __syncthreads();
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = e;
+  if (bad) shbad = 1;
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < kFinalizeThreads / 32; ++w) tot += sh[w];
+    errpart[blockIdx.x] = tot;
+    if (shbad) atomicExch(&st->bad, 1);
+    __threadfence();
+    const int t = atomicAdd(&st->ticket, 1);
+    is_last = (t == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  double tot = 0.0;
+  for (unsigned i = 0; i < gridDim.x; ++i) tot += ((volatile double*)errpart)[i];
+  float err = (norm == B200OT_NORM_L2) ? (float)sqrt(tot) : (float)tot;
+  st->ticket = 0;
+  const int isbad = ((volatile int*)&st->bad)[0];
+  if (isbad) {  // fast path lost a sum: stop here, the host rewinds and replays robustly
+    st->done = 1;
+    return;
+  }
+  if (is_prologue) {
+    st->cur = cur ^ 1;
+    return;
+  }
+  const int it = st->it + 1;
+  st->it = it;
+  const int ce = st->check_every;
+  const bool check = (it % ce) == (st->check_phase % ce);
+  bool stop = false;
+  if (check) {
+    st->err = err;
+    const int ne = st->n_err;
+    if (ne < kErrHistCap) err_hist[ne] = err;
+    st->n_err = ne + 1;
+    stop = st->stop_inclusive ? (err <= st->tol) : (err < st->tol);
+  }
+  if (stop) {
+    st->converged = 1;
+    st->done = 1;
+  } else if (it >= st->max_iter) {
+    if (!check) st->err = err;
+    st->done = 1;
+  } else {
+    st->cur = cur ^ 1;
+  }
+}
+
+// =============================================================================
+// FUSED single-sweep kernel
+// =============================================================================
+struct SweepArgs {
+  const float* C;
+  long long ldc;
+  int n, m;
+  State* st;
+  float* fs;
+  const float* gs0;
+  const float* gs1;
+  const float* a;
+  float* part;  // [nclusters][stride]
+  size_t stride;
+  int ng;          // ring depth in row groups
+  int evict_first; // stream C through L2 with an evict-first policy
+};
+
+constexpr int kSweepThreads = 512;
+constexpr int kSweepWarps = kSweepThreads / 32;
+constexpr int kMaxCluster = 8;
+
+template <int CPT, int R>
+__global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const SweepArgs p) {
+  constexpr int NCH = CPT / 4;
+  constexpr int W = kSweepThreads * CPT;  // columns owned by one CTA
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  State* st = p.st;
+  if (st->done) return;  // grid-uniform: every CTA of every cluster leaves together
+  const int cur = st->cur;
+  const float k = st->kscale;
+  const float* __restrict__ gs = cur ? p.gs1 : p.gs0;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = (int)cluster_ctarank();
+  const int Q = (int)cluster_nctarank();
+  const int cid = (int)cluster_id_x();
+  const int NC = (int)cluster_nid_x();
+  const int NG = p.ng;
+
+  const long long col0 = (long long)q * W;
+  int mvalid = p.m - (int)col0;
+  mvalid = mvalid < 0 ? 0 : (mvalid > W ? W : mvalid);
+
+  float* stage = reinterpret_cast<float*>(smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NG * R * W * sizeof(float));
+  float* red = reinterpret_cast<float*>(full + 8);   // [2][kSweepWarps][R]
+  float* xch = red + 2 * kSweepWarps * R;            // [2][R][kMaxCluster]
+
+  float gsv[CPT], acc[CPT];
+  bool cvalid[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * (kSweepThreads * 4) + tid * 4;
+    cvalid[c] = col < mvalid;
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cvalid[c]) g4 = *reinterpret_cast<const float4*>(gs + col0 + col);
+    gsv[c * 4 + 0] = g4.x;
+    gsv[c * 4 + 1] = g4.y;
+    gsv[c * 4 + 2] = g4.z;
+    gsv[c * 4 + 3] = g4.w;
+    acc[c * 4 + 0] = acc[c * 4 + 1] = acc[c * 4 + 2] = acc[c * 4 + 3] = 0.f;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < NG; ++s) mbar_init(smem_u32(full + s), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+
+  const int ngroups = (p.n + R - 1) / R;
+  const int cnt = cid < ngroups ? (ngroups - cid + NC - 1) / NC : 0;
+  const uint64_t pol = p.evict_first ? policy_evict_first() : 0ull;
+
+  auto issue = [&](int i) {
+    const int row0 = (cid + i * NC) * R;
+    int rows = p.n - row0;
+    rows = rows > R ? R : rows;
+    const int s = i % NG;
+    const uint32_t bar = smem_u32(full + s);
+    const uint32_t row_bytes = (uint32_t)mvalid * 4u;
+    mbar_arrive_expect_tx(bar, row_bytes * rows);
+    if (row_bytes) {
+      for (int r = 0; r < rows; ++r) {
+        const float* src = p.C + (long long)(row0 + r) * p.ldc + col0;
+        const uint32_t dst = smem_u32(stage + ((size_t)s * R + r) * W);
+        if (p.evict_first)
+          bulk_g2s_hint(dst, src, row_bytes, bar, pol);
+        else
+          bulk_g2s(dst, src, row_bytes, bar);
+      }
+    }
+  };
+
+  if (tid == 0) {
+    const int pre = cnt < NG ? cnt : NG;
+    for (int i = 0; i < pre; ++i) issue(i);
+  }
+
+  for (int i = 0; i < cnt; ++i) {
+    const int s = i % NG;
+    const uint32_t ph = (uint32_t)((i / NG) & 1);
+    const int par = i & 1;
+    const int row0 = (cid + i * NC) * R;
+    int rows = p.n - row0;
+    rows = rows > R ? R : rows;
+
+    float fsr[R], ar[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      fsr[r] = 0.f;
+      ar[r] = 0.f;
+      if (r < rows) {
+        fsr[r] = p.fs[row0 + r];
+        ar[r] = p.a[row0 + r];
+      }
+    }
+
+    mbar_wait(smem_u32(full + s), ph);
+
+    // pass 1: t = 2^(fs_i + gs_j - k C_ij), row partial sums
+    float t[R][CPT];
+    float ps[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      ps[r] = 0.f;
+      const float* srow = stage + ((size_t)s * R + r) * W + tid * 4;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = cvalid[c] && (r < rows);
+        if (ok) v = *reinterpret_cast<const float4*>(srow + c * (kSweepThreads * 4));
+        const float e0 = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + fsr[r]));
+        const float e1 = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + fsr[r]));
+        const float e2 = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + fsr[r]));
+        const float e3 = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + fsr[r]));
+        t[r][c * 4 + 0] = ok ? e0 : 0.f;
+        t[r][c * 4 + 1] = ok ? e1 : 0.f;
+        t[r][c * 4 + 2] = ok ? e2 : 0.f;
+        t[r][c * 4 + 3] = ok ? e3 : 0.f;
+        ps[r] += (t[r][c * 4 + 0] + t[r][c * 4 + 1]) + (t[r][c * 4 + 2] + t[r][c * 4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float v = warp_sum(ps[r]);
+      if (lane == 0) red[(par * kSweepWarps + warp) * R + r] = v;
+    }
+    __syncthreads();  // every thread has drained stage s; red[par] is complete
+
+    if (tid == 0 && i + NG < cnt) {
+      fence_proxy_async();
+      issue(i + NG);
+    }
+    if (tid < R * Q) {
+      const int r = tid / Q, qq = tid - r * Q;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSweepWarps; ++w) v += red[(par * kSweepWarps + w) * R + r];
+      st_cluster_f32(map_to_cta(smem_u32(xch + (par * R + r) * kMaxCluster + q), (uint32_t)qq), v);
+    }
+    cluster_arrive();
+    cluster_wait();
+
+    // pass 2: w_i = a_i / r_i, fold the row group into the column accumulators
+    float wr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float rt = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < kMaxCluster; ++qq)
+        if (qq < Q) rt += xch[(par * R + r) * kMaxCluster + qq];
+      const bool live = (r < rows) && (ar[r] > 0.f);
+      wr[r] = live ? __fdividef(ar[r], rt) : 0.f;
+      if (q == 0 && tid == r && r < rows) {
+        const float fnew = live ? fsr[r] + (log2f(ar[r]) - log2f(rt)) : -INFINITY;
+        p.fs[row0 + r] = fnew;
+        if (live && !(fabsf(fnew) < INFINITY)) atomicExch(&st->bad, 1);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[r][c], wr[r], acc[c]);
+    }
+  }
+
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (cvalid[c]) {
+      const int col = c * (kSweepThreads * 4) + tid * 4;
+      *reinterpret_cast<float4*>(p.part + (size_t)cid * p.stride + col0 + col) =
+          make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
+    }
+  }
+}
+
+// fold the per-cluster column partials of this rank into one vector (row-sharded mode)
+__global__ void reduce_parts_kernel(const State* st, const float* __restrict__ part_sum,
+                                    const float* __restrict__ part_max, int np, size_t stride, int m,
+                                    float* __restrict__ s_out) {
+  if (st->done) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  float acc = 0.f;
+  if (part_max) {
+    for (int p = 0; p < np; ++p) {
+      const float pm = part_max[(size_t)p * stride + j];
+      if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm);
+    }
+  } else {
+    for (int p = 0; p < np; ++p) acc += part_sum[(size_t)p * stride + j];
+  }
+  s_out[j] = acc;
+}
+
+// =============================================================================
+// ROBUST kernels (running-max logsumexp, any shape / alignment)
+// =============================================================================
+struct OnlineLse {
+  float mx, s;
+  __device__ __forceinline__ void init() {
+    mx = -INFINITY;
+    s = 0.f;
+  }
+  __device__ __forceinline__ void add(float x) {
+    if (x > mx) {
+      s = s * ex2_approx(mx - x) + 1.f;  // mx = -inf: s = 0 * 0 + 1
+      mx = x;
+    } else if (x > -INFINITY) {
+      s += ex2_approx(x - mx);
+    }
+  }
+  __device__ __forceinline__ void merge(float omx, float os) {
+    if (omx == -INFINITY) return;
+    if (mx == -INFINITY) {
+      mx = omx;
+      s = os;
+      return;
+    }
+    const float M = fmaxf(mx, omx);
+    s = s * ex2_approx(mx - M) + os * ex2_approx(omx - M);
+    mx = M;
+  }
+};
+
+// fs_i = log2 a_i - LSE2_j(gs_j - k C_ij); one CTA per row (grid-stride)
+template <bool VEC>
+__global__ void __launch_bounds__(256) rowpass_lse_kernel(const float* __restrict__ C, long long ldc,
+                                                          int n, int m, State* st, float* fs,
+                                                          const float* gs0, const float* gs1,
+                                                          const float* __restrict__ a) {
+  if (st->done) return;
+  const float k = st->kscale;
+  const float* __restrict__ gs = st->cur ? gs1 : gs0;
+  __shared__ float shm[8], shs[8];
+  for (int row = blockIdx.x; row < n; row += gridDim.x) {
+    const float* crow = C + (long long)row * ldc;
+    OnlineLse o;
+    o.init();
+    if (VEC) {
+      for (int j = threadIdx.x * 4; j < m; j += 256 * 4) {
+        const float4 c4 = *reinterpret_cast<const float4*>(crow + j);
+        const float4 g4 = *reinterpret_cast<const float4*>(gs + j);
+        o.add(fmaf(c4.x, -k, g4.x));
+        o.add(fmaf(c4.y, -k, g4.y));
+        o.add(fmaf(c4.z, -k, g4.z));
+        o.add(fmaf(c4.w, -k, g4.w));
+      }
+    } else {
+      for (int j = threadIdx.x; j < m; j += 256) o.add(fmaf(crow[j], -k, gs[j]));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float omx = __shfl_xor_sync(0xffffffffu, o.mx, off);
+      const float os = __shfl_xor_sync(0xffffffffu, o.s, off);
+      o.merge(omx, os);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      shm[threadIdx.x >> 5] = o.mx;
+      shs[threadIdx.x >> 5] = o.s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      OnlineLse t;
+      t.init();
+      for (int w = 0; w < 8; ++w) t.merge(shm[w], shs[w]);
+      const float ai = a[row];
+      float fnew = -INFINITY;
+      if (ai > 0.f) {
+        fnew = log2f(ai) - (t.mx + log2f(t.s));
+        if (!(fabsf(fnew) < INFINITY)) atomicExch(&st->bad, 1);
+      }
+      fs[row] = fnew;
+    }
+    __syncthreads();
+  }
+}
+
+// per-column running-max sums of 2^(fs_i + gs_j - k C_ij) over a row range; (max,sum) partial per
+// row split.  Threads own columns (4 consecutive in the VEC form) so loads are coalesced.
+template <bool VEC>
+__global__ void __launch_bounds__(256) colpass_lse_kernel(const float* __restrict__ C, long long ldc,
+                                                          int n, int m, const State* st,
+                                                          const float* __restrict__ fs,
+                                                          const float* gs0, const float* gs1,
+                                                          float* __restrict__ part_sum,
+                                                          float* __restrict__ part_max, size_t stride,
+                                                          int rows_per_split) {
+  if (st->done) return;
+  const float k = st->kscale;
+  const float* __restrict__ gs = st->cur ? gs1 : gs0;
+  const int split = blockIdx.y;
+  const int r0 = split * rows_per_split;
+  int r1 = r0 + rows_per_split;
+  r1 = r1 > n ? n : r1;
+  if (VEC) {
+    const int j = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (j >= m) return;
+    const float4 g4 = *reinterpret_cast<const float4*>(gs + j);
+    OnlineLse o0, o1, o2, o3;
+    o0.init();
+    o1.init();
+    o2.init();
+    o3.init();
+    for (int i = r0; i < r1; ++i) {
+      const float fi = fs[i];
+      const float4 c4 = *reinterpret_cast<const float4*>(C + (long long)i * ldc + j);
+      o0.add(fmaf(c4.x, -k, g4.x + fi));
+      o1.add(fmaf(c4.y, -k, g4.y + fi));
+      o2.add(fmaf(c4.z, -k, g4.z + fi));
+      o3.add(fmaf(c4.w, -k, g4.w + fi));
+    }
+    const size_t o = (size_t)split * stride + j;
+    *reinterpret_cast<float4*>(part_sum + o) = make_float4(o0.s, o1.s, o2.s, o3.s);
+    *reinterpret_cast<float4*>(part_max + o) = make_float4(o0.mx, o1.mx, o2.mx, o3.mx);
+  } else {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= m) return;
+    const float gj = gs[j];
+    OnlineLse o;
+    o.init();
+    for (int i = r0; i < r1; ++i) o.add(fmaf(C[(long long)i * ldc + j], -k, gj + fs[i]));
+    part_sum[(size_t)split * stride + j] = o.s;
+    part_max[(size_t)split * stride + j] = o.mx;
+  }
+}
+
+// =============================================================================
+// snapshot / rewind / export
+// =============================================================================
+__global__ void snapshot_kernel(State* st, int n, int m, const float* fs, const float* gs0,
+                                const float* gs1, float* snap_fs, float* snap_gs) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* gs = st->cur ? gs1 : gs0;
+  if (i < n) snap_fs[i] = fs[i];
+  if (i < m) snap_gs[i] = gs[i];
+  if (i == 0) {
+    st->snap_it = st->it;
+    st->snap_cur = st->cur;
+    st->snap_n_err = st->n_err;
+    st->snap_err = st->err;
+  }
+}
+
+__global__ void rewind_kernel(State* st, int n, int m, float* fs, float* gs0, float* gs1,
+                              const float* snap_fs, const float* snap_gs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float* gs = st->snap_cur ? gs1 : gs0;
+  if (i < n) fs[i] = snap_fs[i];
+  if (i < m) gs[i] = snap_gs[i];
+  __syncthreads();
+  if (i == 0) {
+    st->it = st->snap_it;
+    st->cur = st->snap_cur;
+    st->n_err = st->snap_n_err;
+    st->err = st->snap_err;
+    st->done = 0;
+    st->converged = 0;
+    st->bad = 0;
+    st->ticket = 0;
+  }
+}
+
+__global__ void export_kernel(const State* st, int n, int m, const float* fs, const float* gs0,
+                              const float* gs1, float* f, float* g, b200ot_result* res,
+                              const float* err_hist, float* err_out, int err_cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float inv = 1.f / st->kscale;
+  const float* gs = st->cur ? gs1 : gs0;
+  if (f && i < n) f[i] = fs[i] * inv;
+  if (g && i < m) g[i] = gs[i] * inv;
+  if (err_out && i < err_cap && i < st->n_err && i < kErrHistCap) err_out[i] = err_hist[i];
+  if (i == 0 && res) {
+    res->n_iter = st->it;
+    res->converged = st->converged;
+    res->status = st->bad ? B200OT_E_NUMERIC : 0;
+    res->n_err = st->n_err;
+    res->err = st->err;
+    res->reserved[0] = res->reserved[1] = res->reserved[2] = 0.f;
+  }
+}
+
+// =============================================================================
+// host side
+// =============================================================================
+struct FusedCfg {
+  int Q, CPT, R, NG, NC;
+  size_t smem;
+  bool ok;
+};
+
+template <int CPT, int R>
+static cudaError_t launch_fused(const SweepArgs& a, int Q, int NC, size_t smem, cudaStream_t s) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(NC * Q));
+  cfg.blockDim = dim3(kSweepThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)Q;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, sweep_fused_kernel<CPT, R>, a);
+}
+
+template <int CPT, int R>
+static int query_fused(int Q, size_t smem, int* nc_out) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sweep_fused_kernel<CPT, R>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e, "cudaFuncSetAttribute(sweep_fused)");
+      return B200OT_E_LAUNCH;
+    }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(Q * 148));
+  cfg.blockDim = dim3(kSweepThreads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)Q;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nc = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, sweep_fused_kernel<CPT, R>, &cfg);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "cudaOccupancyMaxActiveClusters");
+    return B200OT_E_LAUNCH;
+  }
+  *nc_out = nc;
+  return 0;
+}
+
+static int rows_for_cpt(int cpt) { return cpt == 4 ? 4 : cpt == 8 ? 4 : cpt == 16 ? 2 : 1; }
+
+// pick cluster size / columns per thread for a width m; env overrides for tuning runs
+static int pick_fused(int n, int m, FusedCfg* out) {
+  static int cache_nc[4][4];  // [log2 Q][log2(CPT/4)]
+  static bool cache_ok[4][4];
+  int Q = 0, CPT = 0;
+  const char* eq = getenv("B200OT_FUSED_Q");
+  const char* ec = getenv("B200OT_FUSED_CPT");
+  if (eq && ec) {
+    Q = atoi(eq);
+    CPT = atoi(ec);
+    if (!((Q == 1 || Q == 2 || Q == 4 || Q == 8) && (CPT == 4 || CPT == 8 || CPT == 16 || CPT == 32)) ||
+        (long long)Q * kSweepThreads * CPT < m)
+      Q = CPT = 0;
+  }
+  if (!Q) {
+    // smallest cluster that covers a row with <= 32 columns per thread, then the narrowest CPT;
+    // wide rows prefer 16 columns per thread (two rows per group) when the cluster can be doubled
+    for (int q = 1; q <= 8 && !Q; q *= 2)
+      for (int c = 4; c <= 32; c *= 2)
+        if ((long long)q * kSweepThreads * c >= m) {
+          Q = q;
+          CPT = c;
+          break;
+        }
+    if (!Q) return B200OT_E_UNSUPPORTED;
+    if (CPT == 32 && Q < 8) {
+      Q *= 2;
+      CPT = 16;
+    }
+  }
+  const int R = rows_for_cpt(CPT);
+  const size_t stage = (size_t)R * kSweepThreads * CPT * 4;
+  const size_t fixed = 8 * 8 + (2 * kSweepWarps * R + 2 * R * kMaxCluster) * 4 + 128;
+  int NG = (int)((232448 - 1024 - fixed) / stage);
+  NG = NG > 8 ? 8 : NG;
+  if (NG < 2) return B200OT_E_UNSUPPORTED;
+  const char* eg = getenv("B200OT_FUSED_NG");
+  if (eg && atoi(eg) >= 1 && atoi(eg) <= NG) NG = atoi(eg);
+  const size_t smem = (size_t)NG * stage + fixed;
+  const int qi = Q == 1 ? 0 : Q == 2 ? 1 : Q == 4 ? 2 : 3;
+  const int ci = CPT == 4 ? 0 : CPT == 8 ? 1 : CPT == 16 ? 2 : 3;
+  if (!cache_ok[qi][ci] || eg) {
+    int nc = 0, rc;
+    const size_t smem_max = 232448 - 1024;
+    (void)smem_max;
+    switch (CPT) {
+      case 4: rc = query_fused<4, 4>(Q, smem, &nc); break;
+      case 8: rc = query_fused<8, 4>(Q, smem, &nc); break;
+      case 16: rc = query_fused<16, 2>(Q, smem, &nc); break;
+      default: rc = query_fused<32, 1>(Q, smem, &nc); break;
+    }
+    if (rc) return rc;
+    if (nc < 1) return B200OT_E_UNSUPPORTED;
+    cache_nc[qi][ci] = nc;
+    cache_ok[qi][ci] = true;
+  }
+  int NC = cache_nc[qi][ci];
+  const int ngroups = (n + R - 1) / R;
+  if (NC > ngroups) NC = ngroups;
+  if (NC > kNpCap) NC = kNpCap;
+  if (NC < 1) NC = 1;
+  out->Q = Q;
+  out->CPT = CPT;
+  out->R = R;
+  out->NG = NG;
+  out->NC = NC;
+  out->smem = smem;
+  out->ok = true;
+  return 0;
+}
+
+static bool fused_eligible(const float* C, int ldc, int n, int m) {
+  return (ldc % 4 == 0) && (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && m >= 4 &&
+         n >= 1 && (long long)m <= 8ll * kSweepThreads * 32;
+}
+static bool vec_eligible(const float* C, int ldc, int m) {
+  return (ldc % 4 == 0) && (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+}
+
+static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtrs& w, int* np_out,
+                              cudaStream_t s) {
+  FusedCfg cfg;
+  int rc = pick_fused(n, m, &cfg);
+  if (rc) return rc;
+  SweepArgs a;
+  a.C = C;
+  a.ldc = ldc;
+  a.n = n;
+  a.m = m;
+  a.st = w.st;
+  a.fs = w.fs;
+  a.gs0 = w.gs0;
+  a.gs1 = w.gs1;
+  a.a = w.a;
+  a.part = w.part_sum;
+  a.stride = w.m_pad;
+  a.ng = cfg.NG;
+  a.evict_first = ((double)n * (double)m * 4.0 > 100e6) ? 1 : 0;
+  const char* ev = getenv("B200OT_FUSED_EVICT");
+  if (ev) a.evict_first = atoi(ev);
+  cudaError_t e;
+  switch (cfg.CPT) {
+    case 4: e = launch_fused<4, 4>(a, cfg.Q, cfg.NC, cfg.smem, s); break;
+    case 8: e = launch_fused<8, 4>(a, cfg.Q, cfg.NC, cfg.smem, s); break;
+    case 16: e = launch_fused<16, 2>(a, cfg.Q, cfg.NC, cfg.smem, s); break;
+    default: e = launch_fused<32, 1>(a, cfg.Q, cfg.NC, cfg.smem, s); break;
+  }
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "sweep_fused launch");
+    return B200OT_E_LAUNCH;
+  }
+  *np_out = cfg.NC;
+  return 0;
+}
+
+static int launch_rowpass(const float* C, int ldc, int n, int m, const WsPtrs& w, cudaStream_t s) {
+  int grid = n < 148 * 8 ? n : 148 * 8;
+  if (vec_eligible(C, ldc, m))
+    rowpass_lse_kernel<true><<<grid, 256, 0, s>>>(C, ldc, n, m, w.st, w.fs, w.gs0, w.gs1, w.a);
+  else
+    rowpass_lse_kernel<false><<<grid, 256, 0, s>>>(C, ldc, n, m, w.st, w.fs, w.gs0, w.gs1, w.a);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+static int launch_colpass(const float* C, int ldc, int n, int m, const WsPtrs& w, int* np_out,
+                          cudaStream_t s) {
+  const bool vec = vec_eligible(C, ldc, m);
+  const int cols_per_block = vec ? 1024 : 256;
+  const int bx = (m + cols_per_block - 1) / cols_per_block;
+  int splits = (148 * 4 + bx - 1) / bx;
+  if (splits > kNpCap) splits = kNpCap;
+  int rows_per = (n + splits - 1) / splits;
+  if (rows_per < 8) rows_per = n < 8 ? n : 8;
+  splits = (n + rows_per - 1) / rows_per;
+  dim3 grid((unsigned)bx, (unsigned)splits);
+  if (vec)
+    colpass_lse_kernel<true><<<grid, 256, 0, s>>>(C, ldc, n, m, w.st, w.fs, w.gs0, w.gs1, w.part_sum,
+                                                  w.part_max, w.m_pad, rows_per);
+  else
+    colpass_lse_kernel<false><<<grid, 256, 0, s>>>(C, ldc, n, m, w.st, w.fs, w.gs0, w.gs1, w.part_sum,
+                                                   w.part_max, w.m_pad, rows_per);
+  B200OT_LAUNCH_OK();
+  *np_out = splits;
+  return 0;
+}
+
+static int launch_finalize(int m, const WsPtrs& w, const float* psum, const float* pmax, int np,
+                           size_t stride, int is_prologue, cudaStream_t s) {
+  const int grid = (m + kFinalizeThreads - 1) / kFinalizeThreads;
+  if (grid > 4096) return B200OT_E_UNSUPPORTED;
+  finalize_kernel<<<grid, kFinalizeThreads, 0, s>>>(w.st, psum, pmax, np, stride, m, w.b, w.log2b, w.gs0,
+                                                    w.gs1, w.errpart, w.err_hist, is_prologue);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+static int resolve_path(int path, const float* C, int ldc, int n, int m) {
+  if (path == B200OT_PATH_ROBUST) return B200OT_PATH_ROBUST;
+  if (!fused_eligible(C, ldc, n, m)) return B200OT_PATH_ROBUST;
+  return B200OT_PATH_FUSED;
+}
+
+static int check_problem(const float* C, int ldc, int n, int m, void* ws) {
+  if (!C || !ws || n <= 0 || m <= 0 || ldc < m) return B200OT_E_INVALID;
+  if ((long long)m > 4096ll * kFinalizeThreads) return B200OT_E_UNSUPPORTED;
+  return 0;
+}
+
+}  // namespace b200ot
+
+using namespace b200ot;
+
+extern "C" {
+
+size_t b200ot_sinkhorn_workspace_bytes(int n, int m) {
+  if (n <= 0 || m <= 0) return 0;
+  return ws_layout(n, m).total;
+}
+
+int b200ot_sinkhorn_setup(int n, int m, const float* a, const float* b, const float* f0,
+                          const float* g0, const b200ot_params* prm, void* ws, size_t ws_bytes,
+                          void* stream) {
+  if (!ws || n <= 0 || m <= 0) return B200OT_E_INVALID;
+  if ((long long)m > 4096ll * kFinalizeThreads) return B200OT_E_UNSUPPORTED;
+  if (!a || !b || !prm || !(prm->eps > 0.f)) return B200OT_E_INVALID;
+  const WsLayout L = ws_layout(n, m);
+  if (ws_bytes < L.total) return B200OT_E_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, L);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int mx = n > m ? n : m;
+  init_kernel<<<(mx + 255) / 256, 256, 0, s>>>(w.st, *prm, n, m, a, b, f0, g0, w.fs, w.gs0, w.gs1, w.a,
+                                               w.b, w.log2b);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_init(const float* C, int ldc, int n, int m, const float* a, const float* b,
+                         const float* f0, const float* g0, const b200ot_params* prm, void* ws,
+                         size_t ws_bytes, void* stream) {
+  int rc = check_problem(C, ldc, n, m, ws);
+  if (rc) return rc;
+  rc = b200ot_sinkhorn_setup(n, m, a, b, f0, g0, prm, ws, ws_bytes, stream);
+  if (rc) return rc;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n, m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // first g update from the start potentials (running-max form: safe for any eps)
+  int np = 0;
+  rc = launch_colpass(C, ldc, n, m, w, &np, s);
+  if (rc) return rc;
+  return launch_finalize(m, w, w.part_sum, w.part_max, np, w.m_pad, 1, s);
+}
+
+int b200ot_sinkhorn_snapshot(int n, int m, void* ws, void* stream) {
+  if (!ws || n <= 0 || m <= 0) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n, m));
+  const int mx = n > m ? n : m;
+  snapshot_kernel<<<(mx + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w.st, n, m, w.fs, w.gs0, w.gs1, w.snap_fs, w.snap_gs);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_rewind(int n, int m, void* ws, void* stream) {
+  if (!ws || n <= 0 || m <= 0) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n, m));
+  const int mx = n > m ? n : m;
+  // one block per 256 entries; the state reset is done by thread 0 of block 0 after its own
+  // copies, the other blocks only copy, and the next kernel on the stream sees everything
+  rewind_kernel<<<(mx + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w.st, n, m, w.fs, w.gs0, w.gs1, w.snap_fs, w.snap_gs);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_enqueue(const float* C, int ldc, int n, int m, int iters, int path, void* ws,
+                            void* stream) {
+  int rc = check_problem(C, ldc, n, m, ws);
+  if (rc) return rc;
+  if (iters < 0) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n, m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  path = resolve_path(path, C, ldc, n, m);
+  rc = b200ot_sinkhorn_snapshot(n, m, ws, stream);
+  if (rc) return rc;
+  for (int i = 0; i < iters; ++i) {
+    int np = 0;
+    if (path == B200OT_PATH_FUSED) {
+      rc = launch_sweep_fused(C, ldc, n, m, w, &np, s);
+      if (rc) return rc;
+      rc = launch_finalize(m, w, w.part_sum, nullptr, np, w.m_pad, 0, s);
+    } else {
+      rc = launch_rowpass(C, ldc, n, m, w, s);
+      if (rc) return rc;
+      rc = launch_colpass(C, ldc, n, m, w, &np, s);
+      if (rc) return rc;
+      rc = launch_finalize(m, w, w.part_sum, w.part_max, np, w.m_pad, 0, s);
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int b200ot_sinkhorn_finish(int n, int m, void* ws, float* f, float* g, b200ot_result* result,
+                           float* err_hist, int err_hist_cap, void* stream) {
+  if (!ws || n <= 0 || m <= 0) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n, m));
+  int mx = n > m ? n : m;
+  if (err_hist && err_hist_cap > mx) mx = err_hist_cap;
+  export_kernel<<<(mx + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w.st, n, m, w.fs, w.gs0, w.gs1, f, g, result, w.err_hist, err_hist, err_hist ? err_hist_cap : 0);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_peek(void* ws, int* flags8, void* stream) {
+  if (!ws || !flags8) return B200OT_E_INVALID;
+  B200OT_CUDA_OK(cudaMemcpyAsync(flags8, ws, 8 * sizeof(int), cudaMemcpyDefault,
+                                 static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int b200ot_sinkhorn_solve(const float* C, int ldc, int n, int m, const float* a, const float* b,
+                          const float* f0, const float* g0, const b200ot_params* prm, void* ws,
+                          size_t ws_bytes, float* f, float* g, b200ot_result* result_host,
+                          float* err_hist, int err_hist_cap, void* stream) {
+  if (!prm) return B200OT_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = b200ot_sinkhorn_init(C, ldc, n, m, a, b, f0, g0, prm, ws, ws_bytes, stream);
+  if (rc) return rc;
+  static thread_local int* pinned = nullptr;  // 2 slots x 8 ints + result block
+  static thread_local cudaEvent_t ev[2];
+  if (!pinned) {
+    B200OT_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&pinned), 64 * sizeof(int), cudaHostAllocDefault));
+    B200OT_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    B200OT_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  }
+  int path = resolve_path(prm->path, C, ldc, n, m);
+  const int ce = prm->check_every > 0 ? prm->check_every : 1;
+  const int phase = ((prm->check_phase % ce) + ce) % ce;
+  // Chunks end on check iterations.  Chunk c is queued before chunk c-1's flags are read, so the
+  // host never starves the stream; kernels of a chunk queued after the rule fired are no-ops.
+  int it_enq = 0;
+  int c = 0;
+  bool have_prev = false;
+  for (;;) {
+    int len = 0;
+    if (it_enq < prm->max_iter) {
+      len = (((phase - it_enq - 1) % ce) + ce) % ce + 1;
+      if (len > prm->max_iter - it_enq) len = prm->max_iter - it_enq;
+      rc = b200ot_sinkhorn_enqueue(C, ldc, n, m, len, path, ws, stream);
+      if (rc) return rc;
+      it_enq += len;
+      B200OT_CUDA_OK(cudaMemcpyAsync(pinned + (c & 1) * 8, ws, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      B200OT_CUDA_OK(cudaEventRecord(ev[c & 1], s));
+    }
+    if (have_prev) {
+      B200OT_CUDA_OK(cudaEventSynchronize(ev[(c - 1) & 1]));
+      const int* fl = pinned + ((c - 1) & 1) * 8;
+      const int done = fl[1], bad = fl[4];
+      if (bad) {
+        if (path == B200OT_PATH_ROBUST) break;  // nothing more robust to try; status says so
+        // ws holds the snapshot taken at the start of the chunk that lost a sum
+        rc = b200ot_sinkhorn_rewind(n, m, ws, stream);
+        if (rc) return rc;
+        B200OT_CUDA_OK(cudaMemcpyAsync(pinned + 16, ws, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+        B200OT_CUDA_OK(cudaStreamSynchronize(s));
+        it_enq = pinned[16];
+        path = B200OT_PATH_ROBUST;
+        have_prev = false;
+        c = 0;
+        continue;
+      }
+      if (done) break;
+    }
+    if (len == 0) break;
+    have_prev = true;
+    ++c;
+  }
+  b200ot_result* dres = reinterpret_cast<b200ot_result*>(static_cast<char*>(ws) + ws_layout(n, m).errpart);
+  // reuse the (now idle) error-partial area as the device-side result block
+  rc = b200ot_sinkhorn_finish(n, m, ws, f, g, dres, err_hist, err_hist_cap, stream);
+  if (rc) return rc;
+  if (result_host) {
+    B200OT_CUDA_OK(cudaMemcpyAsync(pinned + 32, dres, sizeof(b200ot_result), cudaMemcpyDeviceToHost, s));
+    B200OT_CUDA_OK(cudaStreamSynchronize(s));
+    memcpy(result_host, pinned + 32, sizeof(b200ot_result));
+  }
+  return 0;
+}
+
+// ---- row-sharded entry points ------------------------------------------------
+int b200ot_sinkhorn_shard_prologue(const float* C, int ldc, int n_local, int m, void* ws,
+                                   float* s_local, void* stream) {
+  int rc = check_problem(C, ldc, n_local, m, ws);
+  if (rc) return rc;
+  if (!s_local) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int np = 0;
+  rc = launch_colpass(C, ldc, n_local, m, w, &np, s);
+  if (rc) return rc;
+  reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, w.part_max, np, w.m_pad, m, s_local);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_shard_sweep(const float* C, int ldc, int n_local, int m, int path, void* ws,
+                                float* s_local, void* stream) {
+  int rc = check_problem(C, ldc, n_local, m, ws);
+  if (rc) return rc;
+  if (!s_local) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  path = resolve_path(path, C, ldc, n_local, m);
+  int np = 0;
+  if (path == B200OT_PATH_FUSED) {
+    rc = launch_sweep_fused(C, ldc, n_local, m, w, &np, s);
+    if (rc) return rc;
+    reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, nullptr, np, w.m_pad, m, s_local);
+  } else {
+    rc = launch_rowpass(C, ldc, n_local, m, w, s);
+    if (rc) return rc;
+    rc = launch_colpass(C, ldc, n_local, m, w, &np, s);
+    if (rc) return rc;
+    reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, w.part_max, np, w.m_pad, m, s_local);
+  }
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_shard_finalize(int n_local, int m, void* ws, const float* s_total,
+                                   int is_prologue, void* stream) {
+  if (!ws || !s_total || n_local <= 0 || m <= 0) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
+  return launch_finalize(m, w, s_total, nullptr, 1, 0, is_prologue, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

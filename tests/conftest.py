@@ -4,8 +4,10 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if ROOT not in sys.path:
-    sys.path.insert(0, ROOT)
+PKG = os.path.join(ROOT, "ot-based-heterogeneous-multi-modal-fusion-embedding-for-ad-analysis-_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -19,7 +21,16 @@ def golden_dir():
     return GOLDEN
 
 
-def pytest_collection_modifyitems(config, items):
-    # GPU tests are only ever *selected* with -m gpu; when they are, a missing
-    # device or a missing native library is a hard failure, not a skip.
-    pass
+@pytest.fixture(scope="session")
+def native_lib():
+    """Path of libb200ot.so, building it with nvcc if the tree has no fresh copy.
+    A missing library is a hard failure, never a skip: there is no fallback path."""
+    from b200ot import build as b200ot_build
+    return b200ot_build.build()
+
+
+@pytest.fixture(scope="session")
+def cuda_dev(native_lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests were selected (-m gpu) but no CUDA device is visible"
+    return torch.device("cuda", 0)

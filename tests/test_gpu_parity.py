@@ -1,0 +1,349 @@
+"""GPU parity: the CUDA path (through the C ABI) against the float64 oracle and the golden
+vectors produced by the reference's own code.  Run with ``-m gpu`` on a B200.
+
+Tolerances (north star): plan / loss / fused embeddings within 1e-4 relative in fp32;
+iteration counts exactly equal.  "Relative" for the plan is measured against the largest
+entry of the reference plan (entries far below it carry no transport mass).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ot_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _rel(P, Pref):
+    P = np.asarray(P, dtype=np.float64)
+    return float(np.abs(P - Pref).max() / np.abs(Pref).max())
+
+
+def _dev(x, dev, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device=dev, dtype=dtype)
+
+
+# ---------------------------------------------------------------------------
+# cost construction
+# ---------------------------------------------------------------------------
+def test_cost_sqeuclid_golden(cuda_dev, golden_dir):
+    from b200ot import ops
+    g = _load(golden_dir, "c1_sample_64.npz")
+    C = ops.cost_matrix(_dev(g["X"], cuda_dev), _dev(g["Y"], cuda_dev)).cpu().numpy()
+    np.testing.assert_allclose(C, g["C"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 7, 3), (130, 257, 65), (300, 129, 512)])
+def test_cost_ragged_shapes(cuda_dev, n, m, d):
+    from b200ot import ops
+    rng = np.random.default_rng(n * 1000 + m)
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Y = rng.standard_normal((m, d)).astype(np.float32)
+    C = ops.cost_matrix(_dev(X, cuda_dev), _dev(Y, cuda_dev)).cpu().numpy()
+    ref = orc.sqeuclid_cost(X, Y)
+    np.testing.assert_allclose(C, ref, rtol=0, atol=1e-5 * max(1.0, np.abs(ref).max()))
+    Cc = ops.cost_matrix(_dev(X, cuda_dev), _dev(Y, cuda_dev), kind="cosine").cpu().numpy()
+    np.testing.assert_allclose(Cc, orc.cosine_cost(X, Y), rtol=0, atol=2e-6)
+
+
+def test_fot_cost_matches_reference_construction(cuda_dev, golden_dir):
+    from b200ot import ops
+    g = _load(golden_dir, "c1_sample_64.npz")
+    Ts = np.eye(64) / 64
+    M = ops.fot_cost(_dev(g["X"], cuda_dev), _dev(g["Y"], cuda_dev), _dev(Ts, cuda_dev),
+                     _dev(Ts.sum(1), cuda_dev), _dev(Ts.sum(0), cuda_dev)).cpu().numpy()
+    ref = orc.fot_cost_pot(g["X"], g["Y"], Ts)
+    np.testing.assert_allclose(M, ref, rtol=0, atol=1e-7)
+    h = _load(golden_dir, "helpers.npz")  # init_matrix_np of the reference, rectangular
+    T = np.random.default_rng(3).random((6, 5))
+    Mg = ops.fot_cost(_dev(h["X1"].T, cuda_dev), _dev(h["X2"].T, cuda_dev), _dev(T, cuda_dev),
+                      _dev(h["v1"], cuda_dev), _dev(h["v2"], cuda_dev)).cpu().numpy()
+    np.testing.assert_allclose(Mg, h["constC"] - h["hC1"] @ T @ h["hC2"].T, rtol=0, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------
+# Sinkhorn: golden vectors from the reference's own sinkhorn_scaling
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["fused", "robust"])
+def test_c1_200_iterations_match_reference(cuda_dev, golden_dir, path):
+    import b200ot
+    g = _load(golden_dir, "c1_sample_64.npz")
+    a = np.ones(64) / 64
+    P, lg = b200ot.sinkhorn(a, a, g["C"], float(g["eps"]), numItermax=200, stopThr=0.0, log=True,
+                            err_norm="l2sq", path=path, warn=False)
+    assert lg["n_iter"] == 200
+    assert _rel(P, g["P200"]) < RTOL
+    np.testing.assert_allclose(lg["log_u"], np.log(g["u200"]), rtol=0, atol=2e-4)
+    np.testing.assert_allclose(lg["log_v"], np.log(g["v200"]), rtol=0, atol=2e-4)
+    assert len(lg["err"]) == len(g["err200"])
+    np.testing.assert_allclose(lg["err"][:3], g["err200"][:3], rtol=2e-3)
+
+
+def test_c1_mirror_rule_same_iteration_count(cuda_dev, golden_dir):
+    import b200ot
+    g = _load(golden_dir, "c1_sample_64.npz")
+    a = np.ones(64) / 64
+    K = np.exp(-g["C"] / float(g["eps"]))
+    P, lg = b200ot.sinkhorn_scaling(a, a, K, numItermax=2000, stopThr=1e-9, log=True)
+    assert lg["n_iter"] == 11 == 10 * (len(g["errconv"]) - 1) + 1
+    assert len(lg["err"]) == len(g["errconv"])
+    assert _rel(P, g["Pconv"]) < RTOL
+
+
+def test_c3_cohort_4096_matches_reference(cuda_dev, golden_dir):
+    from b200ot import ops
+    g = _load(golden_dir, "c3_cohort_4096_summary.npz")
+    X, Y = orc.synthetic_embeddings(4096, 4096, 512, config_index=2)
+    xd, yd = _dev(X, cuda_dev), _dev(Y, cuda_dev)
+    C = ops.cost_matrix(xd, yd)
+    a = torch.full((4096,), 1.0 / 4096, device=cuda_dev)
+    eps = float(g["eps"])
+    f0 = torch.full((4096,), eps * np.log(1.0 / 4096), device=cuda_dev)
+    f, gg, info = ops.sinkhorn_potentials(C, a, a, eps, max_iter=200, tol=0.0, err_norm="l2sq", f0=f0)
+    assert info["n_iter"] == 200
+    np.testing.assert_allclose(f.cpu().numpy() / eps, np.log(g["u200"]), rtol=0, atol=3e-4)
+    np.testing.assert_allclose(gg.cpu().numpy() / eps, np.log(g["v200"]), rtol=0, atol=3e-4)
+    P = ops.plan(C, f, gg, eps).cpu().numpy()
+    assert _rel(P[::512], g["rows200"]) < RTOL
+    cost = float(ops.ot_cost(C, f, gg, eps).item())
+    assert abs(cost - float(g["cost200"])) < RTOL * abs(float(g["cost200"]))
+    bary = ops.apply_plan(C, f, gg, eps, yd, normalise=True).cpu().numpy()
+    np.testing.assert_allclose(bary[::512], g["bary_rows"], rtol=0, atol=RTOL * np.abs(g["bary_rows"]).max())
+    errs = info["errs"].cpu().numpy()
+    assert len(errs) == len(g["err200"])
+    np.testing.assert_allclose(errs[:2], g["err200"][:2], rtol=5e-3)
+    # convergence run, mirror rule: same number of checks and iterations as the reference
+    f, gg, info = ops.sinkhorn_potentials(C, a, a, eps, max_iter=2000, tol=1e-9, err_norm="l2sq",
+                                          stop_inclusive=True, f0=f0)
+    assert info["converged"]
+    assert info["n_err"] == len(g["errconv"])
+    assert info["n_iter"] == 10 * (len(g["errconv"]) - 1) + 1
+
+
+# ---------------------------------------------------------------------------
+# Sinkhorn: oracle on seeded inputs, both paths, ragged shapes, non-uniform marginals
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n,m", [(64, 64), (200, 2048), (37, 4100), (1000, 8192), (513, 12288)])
+@pytest.mark.parametrize("path", ["fused", "robust"])
+def test_paths_match_oracle(cuda_dev, n, m, path):
+    from b200ot import ops
+    rng = np.random.default_rng(n + m)
+    X, Y = orc.synthetic_embeddings(n, m, 32, config_index=n % 7)
+    C = orc.sqeuclid_cost(X, Y)
+    a = rng.random(n) + 0.5
+    a /= a.sum()
+    b = rng.random(m) + 0.5
+    b /= b.sum()
+    eps = 0.1
+    Pref, lg = orc.sinkhorn_log(C, a, b, eps, max_iter=25, tol=0.0, err_norm="l1", check_every=5,
+                                check_phase=0, log=True)
+    Cd = ops.aligned_copy(_dev(C, cuda_dev))
+    f, g, info = ops.sinkhorn_potentials(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), eps, max_iter=25, tol=0.0,
+                                         check_every=5, check_phase=0, err_norm="l1", path=path)
+    assert info["n_iter"] == 25 and info["status"] == 0
+    P = ops.plan(Cd, f, g, eps).cpu().numpy()
+    assert _rel(P, Pref) < RTOL
+    np.testing.assert_allclose(info["errs"].cpu().numpy(), lg["err"], rtol=2e-2, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,m", [(5, 3), (33, 31), (2, 1001)])
+def test_unaligned_shapes_use_generic_kernels(cuda_dev, n, m):
+    from b200ot import ops
+    rng = np.random.default_rng(11)
+    C = rng.random((n, m))
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    Pref = orc.sinkhorn_log(C, a, b, 0.2, max_iter=30, tol=0.0)
+    f, g, info = ops.sinkhorn_potentials(_dev(C, cuda_dev), _dev(a, cuda_dev), _dev(b, cuda_dev), 0.2,
+                                         max_iter=30, tol=0.0)
+    P = ops.plan(_dev(C, cuda_dev), f, g, 0.2).cpu().numpy()
+    assert _rel(P, Pref) < RTOL
+
+
+def test_ott_rule_iteration_count(cuda_dev, golden_dir):
+    """ott flavour (perturbot/match/fot.py:129-134): max-scaled cost, L1 rule, threshold 1e-3."""
+    import b200ot
+    g = _load(golden_dir, "fot_ott_512.npz")
+    M, _ = orc.fot_cost_ott(g["X"], g["Y"], np.eye(64) / 64)
+    Pref, lg = orc.sinkhorn_log_ott(M, float(g["eps"]), log=True)
+    out = b200ot.linear_solve(b200ot.Geometry(cost_matrix=M, epsilon=float(g["eps"]), scale_cost="max_cost"),
+                              max_iterations=2000)
+    assert out.n_iters == lg["n_iter"] and out.converged
+    assert _rel(out.matrix, Pref) < RTOL
+    Tv, log = b200ot.get_coupling_fot(({0: g["X"]}, {0: g["Y"]}), {0: np.eye(64) / 64}, eps=float(g["eps"]))
+    assert _rel(Tv, g["Tv"]) < RTOL
+    assert abs(log["cost"][-1] - float(g["cost"])) < RTOL * abs(float(g["cost"]))
+
+
+def test_feature_coupling_pot_golden(cuda_dev, golden_dir):
+    import b200ot
+    g = _load(golden_dir, "fot_pot_512.npz")
+    Tv, lg = b200ot.get_feature_coupling_pot(({0: g["X"]}, {0: g["Y"]}), {0: np.eye(64) / 64},
+                                             eps=float(g["eps"]))
+    assert lg == {} and Tv.shape == (512, 512) and Tv.dtype == np.float64
+    assert _rel(Tv, g["Tv"]) < RTOL
+    h = _load(golden_dir, "fot_pot_labels.npz")
+    Xd = {1: h["X1"], 0: h["X0"]}
+    Yd = {1: h["Y1"], 0: h["Y0"]}
+    Tv, _ = b200ot.get_feature_coupling_pot((Xd, Yd), {1: h["Ts1"], 0: h["Ts0"]}, eps=float(h["eps"]))
+    assert _rel(Tv, h["Tv"]) < RTOL
+
+
+def test_small_eps_falls_back_and_stays_finite(cuda_dev):
+    """eps = 1e-3 on a max-scaled cost: exp(-C/eps) underflows in the reference; the engine must
+    return a finite plan with exact row marginals (robust replay of chunks that lose a sum)."""
+    from b200ot import ops
+    X, Y = orc.synthetic_embeddings(256, 2048, 16, config_index=5)
+    C = orc.sqeuclid_cost(X, Y)
+    C = C / C.max()
+    a = np.ones(256) / 256
+    b = np.ones(2048) / 2048
+    eps = 1e-3
+    Pref = orc.sinkhorn_log(C, a, b, eps, max_iter=40, tol=0.0)
+    Cd = ops.aligned_copy(_dev(C, cuda_dev))
+    f, g, info = ops.sinkhorn_potentials(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), eps, max_iter=40, tol=0.0)
+    P = ops.plan(Cd, f, g, eps).cpu().numpy()
+    assert np.isfinite(P).all() and info["n_iter"] == 40
+    np.testing.assert_allclose(P.sum(1), a, rtol=1e-3)
+    assert _rel(P, Pref) < 2e-2  # exponents ~1e3: fp32 resolves the plan to ~1e-3 here
+
+
+def test_warm_start_and_stepper(cuda_dev):
+    from b200ot import ops
+    X, Y = orc.synthetic_embeddings(512, 4096, 64, config_index=1)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(512) / 512
+    b = np.ones(4096) / 4096
+    Pref, lg = orc.sinkhorn_log(C, a, b, 0.05, max_iter=30, tol=0.0, log=True)
+    Cd = ops.aligned_copy(_dev(C, cuda_dev))
+    st = ops.SinkhornStepper(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), 0.05, max_iter=30, tol=0.0)
+    st.enqueue(12)
+    assert st.flags()["it"] == 12
+    st.enqueue(100)  # more than remain: the rule stops it at max_iter
+    fl = st.flags()
+    assert fl["it"] == 30 and fl["done"] == 1
+    f, g, info = st.finish()
+    assert _rel(ops.plan(Cd, f, g, 0.05).cpu().numpy(), Pref) < RTOL
+    # warm start from the solution: one more iteration changes nothing
+    f2, g2, _ = ops.sinkhorn_potentials(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), 0.05, max_iter=1, tol=0.0,
+                                        f0=f, g0=g)
+    Pw = orc.sinkhorn_log(C, a, b, 0.05, max_iter=1, tol=0.0, f0=lg["f"], g0=lg["g"])
+    assert _rel(ops.plan(Cd, f2, g2, 0.05).cpu().numpy(), Pw) < RTOL
+
+
+# ---------------------------------------------------------------------------
+# batched small problems (float64 kernel-domain, POT arithmetic)
+# ---------------------------------------------------------------------------
+def test_batched_matches_reference_loop(cuda_dev, golden_dir):
+    from b200ot import ops
+    g = _load(golden_dir, "c1_sample_64.npz")
+    B = 48
+    Xs, Ys, Cs = [g["X"]], [g["Y"]], [g["C"]]
+    for i in range(1, B):
+        X, Y = orc.synthetic_embeddings(64, 64, 512, config_index=100 + i)
+        Xs.append(X)
+        Ys.append(Y)
+        Cs.append(orc.sqeuclid_cost(X, Y))
+    a = np.ones(64) / 64
+    eps = float(g["eps"])
+    ad = _dev(a, cuda_dev)
+    # from embeddings, POT rule (L2, strict), convergence run
+    P, lg = ops.sinkhorn_batched(ad, ad, eps, X=_dev(np.stack(Xs), cuda_dev), Y=_dev(np.stack(Ys), cuda_dev),
+                                 max_iter=2000, tol=1e-9, err_norm="l2")
+    P = P.cpu().numpy()
+    n_iter = lg["n_iter"].cpu().numpy()
+    for i in range(B):
+        Pref, rl = orc.sinkhorn_knopp(a, a, M=Cs[i], reg=eps, numItermax=2000, stopThr=1e-9, err_norm="l2",
+                                      log=True)
+        assert n_iter[i] == rl["n_iter"], i
+        assert _rel(P[i], Pref) < 1e-6
+    # from a cost tensor, mirror rule, fixed 200 iterations: the reference's own golden plan
+    P, lg = ops.sinkhorn_batched(ad, ad, eps, C3=_dev(np.stack(Cs), cuda_dev), max_iter=200, tol=0.0,
+                                 err_norm="l2sq", stop_inclusive=False)
+    assert int(lg["n_iter"][0]) == 200
+    assert _rel(P[0].cpu().numpy(), g["P200"]) < 1e-6
+    np.testing.assert_allclose(lg["u"][0].cpu().numpy(), g["u200"], rtol=1e-6)
+
+
+def test_batched_numerical_guard(cuda_dev):
+    """Underflowing kernel: POT restores the previous iterate and stops (utils.py:55-79)."""
+    from b200ot import ops
+    rng = np.random.default_rng(5)
+    C = rng.random((4, 32, 32)) * 1000.0
+    a = np.ones(32) / 32
+    P, lg = ops.sinkhorn_batched(_dev(a, cuda_dev), _dev(a, cuda_dev), 1e-3, C3=_dev(C, cuda_dev), max_iter=100,
+                                 tol=1e-9)
+    for i in range(4):
+        Pref, rl = orc.sinkhorn_knopp(a, a, M=C[i].astype(np.float32).astype(np.float64), reg=1e-3,
+                                      numItermax=100, stopThr=1e-9, log=True)
+        assert int(lg["n_iter"][i]) == rl["n_iter"]
+        np.testing.assert_allclose(P[i].cpu().numpy(), Pref, rtol=1e-5, atol=1e-30)
+
+
+# ---------------------------------------------------------------------------
+# epilogues
+# ---------------------------------------------------------------------------
+def test_apply_plan_and_losses(cuda_dev):
+    from b200ot import ops
+    rng = np.random.default_rng(9)
+    n, m, dv = 150, 260, 70
+    C = rng.random((n, m))
+    f = rng.standard_normal(n) * 0.05
+    g = rng.standard_normal(m) * 0.05
+    eps = 0.3
+    P = orc.plan_from_potentials(C, f, g, eps)
+    V = rng.standard_normal((m, dv))
+    U = rng.standard_normal((n, dv))
+    Cd, fd, gd = _dev(C, cuda_dev), _dev(f, cuda_dev), _dev(g, cuda_dev)
+    np.testing.assert_allclose(ops.apply_plan(Cd, fd, gd, eps, _dev(V, cuda_dev)).cpu().numpy(), P @ V,
+                               rtol=0, atol=RTOL * np.abs(P @ V).max())
+    np.testing.assert_allclose(ops.apply_plan(Cd, fd, gd, eps, _dev(V, cuda_dev), normalise=True).cpu().numpy(),
+                               orc.barycentric(P, V), rtol=0, atol=RTOL * np.abs(V).max())
+    np.testing.assert_allclose(ops.apply_plan(Cd, fd, gd, eps, _dev(U, cuda_dev), transpose=True).cpu().numpy(),
+                               P.T @ U, rtol=0, atol=RTOL * np.abs(P.T @ U).max())
+    assert abs(float(ops.ot_cost(Cd, fd, gd, eps).item()) - orc.ot_cost(P, C)) < RTOL * orc.ot_cost(P, C)
+    A = rng.standard_normal((33, 512))
+    B = rng.standard_normal((33, 512))
+    assert abs(float(ops.cosine_loss(_dev(A, cuda_dev), _dev(B, cuda_dev)).item()) - orc.cosine_loss(A, B)) < 1e-5
+
+
+# ---------------------------------------------------------------------------
+# BASELINE full size: size-independent properties
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_full_size_marginal_properties(cuda_dev, n):
+    """At sizes the oracle cannot reach: after an f update the row marginals are exact, the reported
+    error equals the column-marginal violation of the returned plan, and the error decreases."""
+    from b200ot import ops
+    m, d = n, 512
+    gen = torch.Generator(device="cpu").manual_seed(20251118 + 3)
+    X = torch.randn(n, d, generator=gen)
+    Y = torch.randn(m, d, generator=gen) + 0.5 * torch.randn(1, d, generator=gen)
+    X = (X / X.norm(dim=1, keepdim=True)).to(cuda_dev)
+    Y = (Y / Y.norm(dim=1, keepdim=True)).to(cuda_dev)
+    C = ops.cost_matrix(X, Y)
+    a = torch.full((n,), 1.0 / n, device=cuda_dev)
+    eps = 0.05
+    f, g, info = ops.sinkhorn_potentials(C, a, a, eps, max_iter=21, tol=0.0, check_every=10, check_phase=1,
+                                         err_norm="l1")
+    assert info["n_iter"] == 21 and info["status"] == 0 and info["n_err"] == 3
+    errs = info["errs"].cpu().numpy()
+    assert errs[2] < errs[1] < errs[0]
+    ones = torch.ones((m, 1), device=cuda_dev)
+    rows = ops.apply_plan(C, f, g, eps, ones).reshape(-1)
+    assert float((rows * n - 1).abs().max()) < 5e-4
+    cols = ops.apply_plan(C, f, g, eps, torch.ones((n, 1), device=cuda_dev), transpose=True).reshape(-1)
+    l1 = float((cols - 1.0 / m).abs().sum())
+    assert abs(l1 - errs[2]) < 0.02 * errs[2] + 1e-6
+    # fused single-sweep and two-sweep robust paths agree
+    f2, g2, _ = ops.sinkhorn_potentials(C, a, a, eps, max_iter=3, tol=0.0, path="robust")
+    f3, g3, _ = ops.sinkhorn_potentials(C, a, a, eps, max_iter=3, tol=0.0, path="fused")
+    assert float((f2 - f3).abs().max()) / eps < 2e-4 and float((g2 - g3).abs().max()) / eps < 2e-4
