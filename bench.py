@@ -44,6 +44,7 @@ class ClockSampler:
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q_OLD = Q.replace("clocks_event_reasons", "clocks_throttle_reasons")
 
     def __init__(self, index):
         self.index = index
@@ -52,8 +53,13 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            q = self.Q
+            probe = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20)
+            if probe.returncode != 0 or not probe.stdout.strip()[:1].isdigit():
+                q = self.Q_OLD
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()

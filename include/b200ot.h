@@ -87,7 +87,15 @@ const char* b200ot_last_cuda_error(void);
  * Replaces ot.dist(X, Y) (MRI_PET_OT_nojax.py:70-71) and is the T = I case of the
  * feature cost M = t1 (+) t2 - 2 X^T Ts Y (MRI_PET_OT_nojax.py:121-136,
  * perturbot/perturbot/match/utils.py:125-184).  X is n x d (ldx), Y is m x d (ldy).
+ * b200ot_cost runs the contraction on tcgen05 (bf16 tensor cores, fp32 accumulators in TMEM)
+ * with an fp32-accurate split over bf16 parts x = x1 + x2 + x3: terms = 6 evaluates
+ * x1.y3 + x3.y1 + x2.y2 + x1.y2 + x2.y1 + x1.y1 (fp32-grade, the default of the Python host),
+ * terms = 3 drops the first three (error ~2^-17 per product), terms = 1 is the plain bf16 product.
+ * `ws` (1024-byte aligned) needs b200ot_cost_workspace_bytes(n, m, d) bytes.
  * cost_simt is the fp32 FMA version; `norms` is scratch for n + m floats.          */
+size_t b200ot_cost_workspace_bytes(int n, int m, int d);
+int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, int d, int kind,
+                float* C, int ldc, void* ws, size_t ws_bytes, int terms, void* stream);
 int b200ot_cost_simt(const float* X, int ldx, const float* Y, int ldy, int n, int m, int d,
                      int kind, float* C, int ldc, float* norms, void* stream);
 

@@ -46,6 +46,8 @@ SIGNATURES = {
     "b200ot_version": (_i, []),
     "b200ot_strerror": (C.c_char_p, [_i]),
     "b200ot_last_cuda_error": (C.c_char_p, []),
+    "b200ot_cost_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200ot_cost": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _i, _p]),
     "b200ot_cost_simt": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
     "b200ot_fot_cost": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p]),
     "b200ot_matrix_max": (_i, [_p, _i, _i, _i, _p, _p]),

@@ -75,8 +75,8 @@ def _uniform(n, device):
 # POT surface
 # ---------------------------------------------------------------------------
 def sinkhorn(a, b, M, reg, method="sinkhorn", numItermax=1000, stopThr=1e-9, verbose=False,
-             log=False, warn=True, warmstart=None, *, check_every=10, err_norm="l2", path="auto",
-             device=None, **kwargs):
+             log=False, warn=True, warmstart=None, *, check_every=10, err_norm="l2", stop_inclusive=False,
+             path="auto", device=None, **kwargs):
     """Drop-in for ``ot.sinkhorn`` as called at MRI_PET_OT_nojax.py:143.
 
     Same stopping rule as POT 0.9.6 ``sinkhorn_knopp`` (L2 norm of the column-marginal
@@ -99,7 +99,8 @@ def sinkhorn(a, b, M, reg, method="sinkhorn", numItermax=1000, stopThr=1e-9, ver
         g0 = torch.full((m,), float(reg) * math.log(1.0 / m), dtype=torch.float32, device=cv.device)
     f, g, info = ops.sinkhorn_potentials(Md, ad, bd, float(reg), max_iter=int(numItermax),
                                          tol=float(stopThr), check_every=check_every, check_phase=1,
-                                         err_norm=err_norm, stop_inclusive=False, path=path, f0=f0, g0=g0)
+                                         err_norm=err_norm, stop_inclusive=stop_inclusive, path=path, f0=f0,
+                                         g0=g0)
     if warn and not info["converged"] and stopThr > 0:
         warnings.warn("Sinkhorn did not converge. You might want to increase the number of "
                       "iterations `numItermax` or the regularization parameter `reg`.")
@@ -232,12 +233,13 @@ def _concat(d, keys):
     return np.concatenate([np.asarray(v) for v in vals])
 
 
-def get_feature_coupling_pot(data, Ts, eps=5e-3, *, numItermax=2000, stopThr=1e-9, path="auto",
-                             device=None):
+def get_feature_coupling_pot(data, Ts, eps=5e-3, *, numItermax=2000, stopThr=1e-9, err_norm="l2",
+                             stop_inclusive=False, path="auto", device=None):
     """Drop-in for ``get_feature_coupling_pot`` (MRI_PET_OT_nojax.py:91-145): sorted-label concat,
     block-diagonal ``Ts``, feature cost ``M = t1 (+) t2 - 2 X^T Ts Y`` with ``w1 = Ts.sum(1)``,
     ``w2 = Ts.sum(0)``, uniform feature marginals, ``ot.sinkhorn(a, b, M, reg=eps,
-    numItermax=2000)``.  Returns ``(Tv, {})``."""
+    numItermax=2000)``.  Returns ``(Tv, {})``.  ``err_norm="l2"`` is POT 0.9.6's rule; the in-tree mirror
+    of that loop (perturbot/perturbot/match/utils.py:88-89) uses ``err_norm="l2sq", stop_inclusive=True``."""
     X_dict, Y_dict = data
     keys = sorted(X_dict.keys())
     X = _concat(X_dict, keys)
@@ -253,7 +255,7 @@ def get_feature_coupling_pot(data, Ts, eps=5e-3, *, numItermax=2000, stopThr=1e-
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         Tv = sinkhorn(_uniform(d1, cv.device), _uniform(d2, cv.device), M, eps, numItermax=numItermax,
-                      stopThr=stopThr, path=path)
+                      stopThr=stopThr, err_norm=err_norm, stop_inclusive=stop_inclusive, path=path)
     return cv.back(Tv), {}
 
 

@@ -72,8 +72,11 @@ def aligned_copy(Cm: torch.Tensor) -> torch.Tensor:
 # cost construction
 # ---------------------------------------------------------------------------
 def cost_matrix(x: torch.Tensor, y: torch.Tensor, kind: str = "sqeuclidean",
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """C_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  or  1 - cos(x_i, y_j) (include/b200ot.h: b200ot_cost_simt)."""
+                out: Optional[torch.Tensor] = None, impl: str = "auto", terms: int = 6) -> torch.Tensor:
+    """C_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  or  1 - cos(x_i, y_j).
+
+    impl="tc": tcgen05 split-bf16 GEMM (b200ot_cost); impl="simt": fp32 FMA kernel
+    (b200ot_cost_simt); "auto" picks the tensor-core kernel once the problem fills the GPU."""
     lib = _lib.load()
     x, ldx = _matrix(x, "x")
     y, ldy = _matrix(y, "y")
@@ -84,9 +87,20 @@ def cost_matrix(x: torch.Tensor, y: torch.Tensor, kind: str = "sqeuclidean",
     if out is None:
         out = empty_matrix(n, m, x.device)
     out, ldc = _matrix(out, "out")
-    norms = torch.empty(n + m, dtype=torch.float32, device=x.device)
-    check(lib.b200ot_cost_simt(_ptr(x), ldx, _ptr(y), ldy, n, m, d, _lib.COSTS[kind], _ptr(out), ldc,
-                               _ptr(norms), _stream()), "b200ot_cost_simt")
+    if impl == "auto":
+        impl = "tc" if (n >= 512 and m >= 512 and d >= 64) else "simt"
+    if impl == "tc":
+        need = lib.b200ot_cost_workspace_bytes(n, m, d)
+        ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+        wsp = C.c_void_p((ws.data_ptr() + 1023) // 1024 * 1024)
+        check(lib.b200ot_cost(_ptr(x), ldx, _ptr(y), ldy, n, m, d, _lib.COSTS[kind], _ptr(out), ldc, wsp,
+                              need, int(terms), _stream()), "b200ot_cost")
+    elif impl == "simt":
+        norms = torch.empty(n + m, dtype=torch.float32, device=x.device)
+        check(lib.b200ot_cost_simt(_ptr(x), ldx, _ptr(y), ldy, n, m, d, _lib.COSTS[kind], _ptr(out), ldc,
+                                   _ptr(norms), _stream()), "b200ot_cost_simt")
+    else:
+        raise B200OTError(f"unknown cost impl {impl!r}")
     return out
 
 

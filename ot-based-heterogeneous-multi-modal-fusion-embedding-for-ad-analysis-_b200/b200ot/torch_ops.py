@@ -1,0 +1,160 @@
+"""``torch.library`` custom ops and autograd functions over the C ABI.
+
+The ops (``torch.ops.b200ot.*``) make the engine visible to PyTorch's dispatcher (fake
+tensors / graph capture see shapes without running CUDA); the autograd functions put the OT
+solve inside a training graph:
+
+  * ``OTLoss``       embeddings -> entropic OT value, gradient by the envelope theorem
+                     (dL/dx_i = sum_j P_ij dC_ij/dx_i with P held at the optimum).  The
+                     reference never differentiates through OT (features are detached at
+                     MRI_PET_OT_nojax.py:683-684); this is the north star's new capability.
+  * ``ApplyPlan``    Z = [diag(1/P1)] P V with the plan constant and the gradient flowing
+                     to V only -- exactly how the reference's ``pet_feat @ T.t()`` re-enters
+                     autograd (MRI_PET_OT_OT_per_epoch_attn.py:728).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+
+_NORM_NAMES = {v: k for k, v in _lib.NORMS.items()}
+_PATH_NAMES = {v: k for k, v in _lib.PATHS.items()}
+
+
+@torch.library.custom_op("b200ot::cost", mutates_args=())
+def cost_op(x: Tensor, y: Tensor, kind: int) -> Tensor:
+    return ops.cost_matrix(x, y, kind="cosine" if kind == _lib.COST_COSINE else "sqeuclidean").contiguous()
+
+
+@cost_op.register_fake
+def _(x, y, kind):
+    return x.new_empty((x.shape[0], y.shape[0]))
+
+
+@torch.library.custom_op("b200ot::sinkhorn_fwd", mutates_args=())
+def sinkhorn_fwd(C: Tensor, a: Tensor, b: Tensor, eps: float, max_iter: int, tol: float, check_every: int,
+                 check_phase: int, err_norm: int, stop_inclusive: bool, path: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """(f, g, stats) with stats = [n_iter, converged, err, status] as fp32."""
+    f, g, info = ops.sinkhorn_potentials(ops.aligned_copy(C), a, b, eps, max_iter=max_iter, tol=tol,
+                                         check_every=check_every, check_phase=check_phase,
+                                         err_norm=_NORM_NAMES[err_norm], stop_inclusive=stop_inclusive,
+                                         path=_PATH_NAMES[path])
+    stats = torch.tensor([info["n_iter"], float(info["converged"]), info["err"], info["status"]],
+                         dtype=torch.float32, device=C.device)
+    return f, g, stats
+
+
+@sinkhorn_fwd.register_fake
+def _(C, a, b, eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive, path):
+    return C.new_empty((C.shape[0],)), C.new_empty((C.shape[1],)), C.new_empty((4,))
+
+
+@torch.library.custom_op("b200ot::plan", mutates_args=())
+def plan_op(C: Tensor, f: Tensor, g: Tensor, eps: float) -> Tensor:
+    return ops.plan(C, f, g, eps)
+
+
+@plan_op.register_fake
+def _(C, f, g, eps):
+    return C.new_empty(C.shape)
+
+
+@torch.library.custom_op("b200ot::apply_plan", mutates_args=())
+def apply_plan_op(C: Tensor, f: Tensor, g: Tensor, eps: float, V: Tensor, normalise: bool, transpose: bool) -> Tensor:
+    return ops.apply_plan(C, f, g, eps, V, normalise=normalise, transpose=transpose)
+
+
+@apply_plan_op.register_fake
+def _(C, f, g, eps, V, normalise, transpose):
+    return V.new_empty((C.shape[1] if transpose else C.shape[0], V.shape[1]))
+
+
+@torch.library.custom_op("b200ot::sinkhorn_bwd_envelope", mutates_args=())
+def sinkhorn_bwd_envelope(C: Tensor, f: Tensor, g: Tensor, eps: float, x: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
+    """Envelope gradients of <P, C(x, y)> for the squared-Euclidean cost at fixed P:
+    dx = 2 (diag(P1) x - P y), dy = 2 (diag(P^T 1) y - P^T x).  The row / column sums come out of the
+    same plan-free kernel by appending a column of ones to the right-hand side."""
+    n, m = C.shape
+    ones_m = torch.ones((m, 1), dtype=torch.float32, device=C.device)
+    ones_n = torch.ones((n, 1), dtype=torch.float32, device=C.device)
+    Py = ops.apply_plan(C, f, g, eps, torch.cat([y, ones_m], dim=1))
+    Ptx = ops.apply_plan(C, f, g, eps, torch.cat([x, ones_n], dim=1), transpose=True)
+    dx = 2.0 * (Py[:, -1:] * x - Py[:, :-1])
+    dy = 2.0 * (Ptx[:, -1:] * y - Ptx[:, :-1])
+    return dx, dy
+
+
+@sinkhorn_bwd_envelope.register_fake
+def _(C, f, g, eps, x, y):
+    return torch.empty_like(x), torch.empty_like(y)
+
+
+class OTLoss(torch.autograd.Function):
+    """Entropic OT value between two embedding clouds (squared-Euclidean cost).
+
+    forward:  C = cost(x, y);  (f, g) = Sinkhorn(C, a, b, eps);
+              value = <P, C>                      (``value="primal"``, fot.py:137's cost)
+                    | <a, f> + <b, g>             (``value="dual"``, the regularised OT value up to a constant)
+    backward: envelope theorem -- P is held fixed, d value / dx = 2 (diag(P1) x - P y) and the same for y.
+    """
+
+    @staticmethod
+    def forward(ctx, x, y, a, b, eps, max_iter, tol, value):
+        xd, yd = x.detach().float().contiguous(), y.detach().float().contiguous()
+        C = ops.cost_matrix(xd, yd)
+        f, g, info = ops.sinkhorn_potentials(C, a, b, eps, max_iter=max_iter, tol=tol)
+        ctx.save_for_backward(C, f, g, xd, yd)
+        ctx.eps = eps
+        ctx.info = info
+        if value == "dual":
+            out = (a * f).sum() + (b * g).sum()
+        else:
+            out = ops.ot_cost(C, f, g, eps).to(torch.float32).reshape(())
+        return out.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        C, f, g, xd, yd = ctx.saved_tensors
+        dx, dy = torch.ops.b200ot.sinkhorn_bwd_envelope(C, f, g, ctx.eps, xd, yd)
+        return grad_out * dx, grad_out * dy, None, None, None, None, None, None
+
+
+def ot_loss(x: Tensor, y: Tensor, a: Tensor = None, b: Tensor = None, eps: float = 0.05, max_iter: int = 1000,
+            tol: float = 1e-6, value: str = "primal") -> Tensor:
+    n, m = x.shape[0], y.shape[0]
+    if a is None:
+        a = torch.full((n,), 1.0 / n, dtype=torch.float32, device=x.device)
+    if b is None:
+        b = torch.full((m,), 1.0 / m, dtype=torch.float32, device=x.device)
+    return OTLoss.apply(x, y, a, b, float(eps), int(max_iter), float(tol), value)
+
+
+class ApplyPlan(torch.autograd.Function):
+    """Z = [diag(1/P1)] P V, plan from (C, f, g) treated as a constant; gradient flows to V."""
+
+    @staticmethod
+    def forward(ctx, C, f, g, eps, V, normalise):
+        Vd = V.detach().float().contiguous()
+        Z = ops.apply_plan(C, f, g, eps, Vd, normalise=normalise)
+        ctx.save_for_backward(C, f, g)
+        ctx.eps, ctx.normalise = eps, normalise
+        return Z.to(V.dtype)
+
+    @staticmethod
+    def backward(ctx, dZ):
+        C, f, g = ctx.saved_tensors
+        dZ = dZ.float().contiguous()
+        if ctx.normalise:
+            ones = torch.ones((C.shape[1], 1), dtype=torch.float32, device=C.device)
+            rs = ops.apply_plan(C, f, g, ctx.eps, ones)
+            dZ = dZ / torch.where(rs == 0, torch.full_like(rs, 1e-30), rs)
+        dV = ops.apply_plan(C, f, g, ctx.eps, dZ, transpose=True)
+        return None, None, None, None, dV, None
+
+
+def apply_plan(C, f, g, eps, V, normalise=False):
+    return ApplyPlan.apply(C, f, g, float(eps), V, bool(normalise))

@@ -151,6 +151,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// DSMEM store that completes 4 bytes of a transaction on the destination CTA's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t addr, float v, uint32_t mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr),
+               "r"(__float_as_uint(v)), "r"(mbar)
+               : "memory");
+}
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }

@@ -1,0 +1,408 @@
+// Cost construction on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate.
+//
+//   C_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j      or      1 - cos(x_i, y_j)
+//
+// is the one dense contraction of the OT path (ot.dist at MRI_PET_OT_nojax.py:70-71; the T = I
+// case of the feature cost at :121-136).  A plan entry is exp((f+g-C)/eps), so an absolute
+// error d in C is a relative error d/eps in the plan: bf16 or tf32 inputs (d ~ 1e-3) are
+// unusable.  The contraction is therefore run as a 3-term split product on bf16 tensor cores,
+//     x = x1 + x2 + x3 (bf16 parts),
+//     terms = 3:  x.y ~= x1.y2 + x2.y1 + x1.y1                          (error ~2^-17 per product)
+//     terms = 6:  ... + x1.y3 + x3.y1 + x2.y2                           (error ~2^-24: fp32 grade)
+// which is an ordinary bf16 GEMM with K' = terms * K over concatenated parts.
+// A pre-pass splits the fp32 embeddings and writes the parts *pre-tiled*: every
+// (ROWS x 64) operand tile is one contiguous block already in the canonical no-swizzle K-major
+// UMMA shared-memory layout (8 x 16-byte core matrices), so the GEMM feeds shared memory with
+// plain 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) and needs no tensor map.
+//
+// GEMM kernel: persistent, one CTA per SM, warp-specialised:
+//   warp 0  TMA producer     (one lane): ring of 4 stages x (A 128x64 + B 256x64) bf16
+//   warp 1  MMA issuer       (one lane): tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16,
+//                                        fp32 accumulators in TMEM, two accumulator stages
+//   warps 2-5 epilogue       tcgen05.ld -> |x|^2 + |y|^2 - 2 acc -> smem transpose -> coalesced stores
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200ot {
+
+constexpr int TC_BM = 128;   // tile rows (UMMA M)
+constexpr int TC_BN = 256;   // tile cols (UMMA N)
+constexpr int TC_BK = 64;    // K elements per stage (bf16: 128 B per row)
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
+constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KiB
+constexpr int TC_GROUP_N = 16;  // n-blocks per raster group (keeps a 12 MiB slab of B' hot in L2)
+
+// ---- tcgen05 wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = byte step between the two K chunks of
+// one MMA, SBO = byte step between 8-row groups (both in 16-byte units in the descriptor).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+  return d;                // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- pre-pass: fp32 rows -> two bf16 parts in tiled UMMA layout + row norms ---------------------
+// One warp per (padded) row.  x = p1 + p2 + p3 (bf16 parts, 8 + 8 + 8 significand bits).
+// Tile (rb, part, kblk) of `tile_rows` x 64 bf16 starts at
+// ((rb * nparts + part) * kblocks + kblk) * tile_rows * 128 bytes; inside it the core matrix
+// (row group rg, k chunk kc) sits at (kc * tile_rows/8 + rg) * 128 and row r%8 at r%8 * 16.
+__global__ void __launch_bounds__(256) split_tiles_kernel(const float* __restrict__ X, long long ldx, int rows,
+                                                          int d, int tile_rows, int kblocks, int rows_pad,
+                                                          int cosine, int nparts, uint8_t* __restrict__ out,
+                                                          float* __restrict__ norms) {
+  const int row = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows_pad) return;
+  const bool live = row < rows;
+  const float* x = X + (long long)row * ldx;
+  float ss = 0.f;
+  if (live)
+    for (int k = lane; k < d; k += 32) ss = fmaf(x[k], x[k], ss);
+  ss = warp_sum(ss);
+  if (live && lane == 0) norms[row] = cosine ? 1.f : ss;
+  const float scale = cosine ? (ss > 0.f ? rsqrtf(ss) : 0.f) : 1.f;
+  const int rb = row / tile_rows, rin = row % tile_rows;
+  const size_t tile_bytes = (size_t)tile_rows * 128;
+  const int nchunks = kblocks * 8;
+  for (int c = lane; c < nchunks; c += 32) {
+    const int kblk = c >> 3, kc = c & 7;
+    __nv_bfloat16 p1[8], p2[8], p3[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = c * 8 + e;
+      const float v = (live && k < d) ? x[k] * scale : 0.f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(h);  // exact in fp32
+      const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
+      p1[e] = h;
+      p2[e] = h2;
+      p3[e] = __float2bfloat16_rn(r1 - __bfloat162float(h2));
+    }
+    const size_t inner = ((size_t)kc * (tile_rows / 8) + (rin >> 3)) * 128 + (size_t)(rin & 7) * 16;
+    const size_t tb = (size_t)rb * nparts * kblocks + kblk;
+    *reinterpret_cast<uint4*>(out + tb * tile_bytes + inner) = *reinterpret_cast<const uint4*>(p1);
+    if (nparts > 1)
+      *reinterpret_cast<uint4*>(out + (tb + kblocks) * tile_bytes + inner) = *reinterpret_cast<const uint4*>(p2);
+    if (nparts > 2)
+      *reinterpret_cast<uint4*>(out + (tb + 2 * (size_t)kblocks) * tile_bytes + inner) =
+          *reinterpret_cast<const uint4*>(p3);
+  }
+}
+
+// ---- the GEMM -----------------------------------------------------------------------------------
+struct CostTcArgs {
+  const uint8_t* A;   // tiled parts of X  (tile_rows = TC_BM)
+  const uint8_t* B;   // tiled parts of Y  (tile_rows = TC_BN)
+  const float* xn;    // |x_i|^2 (or 1)
+  const float* yn;
+  float* C;
+  long long ldc;
+  int n, m, kblocks, nseg, nparts, cosine;
+  int tiles_m, tiles_n;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) cost_tc_kernel(const CostTcArgs p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint8_t* sA = smem;                                    // TC_STAGES x 16 KiB
+  uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;           // TC_STAGES x 32 KiB
+  float* sEpi = reinterpret_cast<float*>(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES));  // 4 x 32 x 33 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * 32 * 33);
+  uint64_t* full = bars;                 // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;    // [TC_STAGES]
+  uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]
+  uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total_tiles = (long long)p.tiles_m * p.tiles_n;
+  const int ksteps = p.kblocks * p.nseg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(tfull + a), 1);
+      mbar_init(smem_u32(tempty + a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_coords = [&](long long t, int& mb, int& nb) {
+    const long long per_group = (long long)p.tiles_m * TC_GROUP_N;
+    const int g = (int)(t / per_group);
+    const long long idx = t - (long long)g * per_group;
+    int gw = p.tiles_n - g * TC_GROUP_N;
+    gw = gw > TC_GROUP_N ? TC_GROUP_N : gw;
+    mb = (int)(idx / gw);
+    nb = g * TC_GROUP_N + (int)(idx - (long long)mb * gw);
+  };
+  // the last raster group may be narrower than TC_GROUP_N; per_group above assumes full width, so
+  // tiles are enumerated group by group with the true width:
+  auto tile_coords_exact = [&](long long t, int& mb, int& nb) {
+    const long long full_groups = p.tiles_n / TC_GROUP_N;
+    const long long per_group = (long long)p.tiles_m * TC_GROUP_N;
+    if (t < full_groups * per_group) {
+      tile_coords(t, mb, nb);
+    } else {
+      const long long idx = t - full_groups * per_group;
+      const int gw = p.tiles_n - (int)full_groups * TC_GROUP_N;
+      mb = (int)(idx / gw);
+      nb = (int)full_groups * TC_GROUP_N + (int)(idx - (long long)mb * gw);
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t a_tile = TC_A_BYTES, b_tile = TC_B_BYTES;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mb, nb;
+        tile_coords_exact(t, mb, nb);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int seg = ks / p.kblocks, kblk = ks - seg * p.kblocks;
+          // segment -> (part of X, part of Y): smallest cross terms first, the x1.y1 term last
+          int pa = 0, pb = 0;
+          if (p.nseg == 3) {
+            pa = seg == 1 ? 1 : 0;
+            pb = seg == 0 ? 1 : 0;
+          } else if (p.nseg == 6) {
+            // x1.y3, x3.y1, x2.y2, x1.y2, x2.y1, x1.y1
+            pa = seg == 1 ? 2 : ((seg == 2 || seg == 4) ? 1 : 0);
+            pb = seg == 0 ? 2 : ((seg == 2 || seg == 3) ? 1 : 0);
+          }
+          mbar_wait(smem_u32(empty + stage), phase ^ 1);
+          const uint32_t bar = smem_u32(full + stage);
+          mbar_arrive_expect_tx(bar, TC_A_BYTES + TC_B_BYTES);
+          const uint8_t* srcA = p.A + ((size_t)(mb * p.nparts + pa) * p.kblocks + kblk) * a_tile;
+          const uint8_t* srcB = p.B + ((size_t)(nb * p.nparts + pb) * p.kblocks + kblk) * b_tile;
+          bulk_g2s(smem_u32(sA + (size_t)stage * TC_A_BYTES), srcA, TC_A_BYTES, bar);
+          bulk_g2s(smem_u32(sB + (size_t)stage * TC_B_BYTES), srcB, TC_B_BYTES, bar);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                             ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(smem_u32(tempty + as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * TC_BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(smem_u32(full + stage), phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + (size_t)stage * TC_A_BYTES);
+          const uint32_t b0 = smem_u32(sB + (size_t)stage * TC_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // one MMA consumes two 8-element K chunks: chunk stride = tile_rows * 16 bytes
+            const uint64_t ad = make_smem_desc(a0 + (uint32_t)k * 2u * (TC_BM * 16u), TC_BM * 16u, 128u);
+            const uint64_t bd = make_smem_desc(b0 + (uint32_t)k * 2u * (TC_BN * 16u), TC_BN * 16u, 128u);
+            tc_mma_bf16(tmem_d, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(empty + stage));  // frees the smem stage once these MMAs have read it
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(smem_u32(tfull + as));  // accumulator complete
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    float* sm = sEpi + (warp - 2) * (32 * 33);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mb, nb;
+      tile_coords_exact(t, mb, nb);
+      mbar_wait(smem_u32(tfull + as), aphase);
+      tc_fence_after();
+      const int row0 = mb * TC_BM + q * 32;
+      const float xn_l = (row0 + lane < p.n) ? p.xn[row0 + lane] : 0.f;
+#pragma unroll 1
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * TC_BN + (uint32_t)c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sm[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = nb * TC_BN + c * 32 + lane;
+        const bool cok = col < p.m;
+        const float yn_c = cok ? p.yn[col] : 0.f;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const float acc = sm[r * 33 + lane];
+          const float xr = __shfl_sync(0xffffffffu, xn_l, r);
+          const int row = row0 + r;
+          if (cok && row < p.n) {
+            const float out = p.cosine ? (1.f - acc) : ((xr + yn_c) - 2.f * acc);
+            p.C[(long long)row * p.ldc + col] = out;
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(smem_u32(tempty + as));
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+constexpr size_t TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 4 * 32 * 33 * 4 + (2 * TC_STAGES + 4) * 8 + 16;
+
+struct CostWs {
+  size_t a_off, b_off, norm_off, total;
+  int kblocks, n_pad, m_pad;
+};
+static CostWs cost_ws(int n, int m, int d) {
+  CostWs w;
+  w.kblocks = (d + TC_BK - 1) / TC_BK;
+  w.n_pad = (n + TC_BM - 1) / TC_BM * TC_BM;
+  w.m_pad = (m + TC_BN - 1) / TC_BN * TC_BN;
+  const size_t a_bytes = (size_t)w.n_pad * w.kblocks * TC_BK * 2 * 3;  // up to three bf16 parts
+  const size_t b_bytes = (size_t)w.m_pad * w.kblocks * TC_BK * 2 * 3;
+  w.a_off = 0;
+  w.b_off = (a_bytes + 1023) / 1024 * 1024;
+  w.norm_off = w.b_off + (b_bytes + 1023) / 1024 * 1024;
+  w.total = w.norm_off + ((size_t)(n + m) * 4 + 1023) / 1024 * 1024;
+  return w;
+}
+
+}  // namespace b200ot
+
+using namespace b200ot;
+
+extern "C" {
+
+size_t b200ot_cost_workspace_bytes(int n, int m, int d) {
+  if (n <= 0 || m <= 0 || d <= 0) return 0;
+  return cost_ws(n, m, d).total;
+}
+
+int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, int d, int kind,
+                float* C, int ldc, void* ws, size_t ws_bytes, int terms, void* stream) {
+  if (!X || !Y || !C || !ws || n <= 0 || m <= 0 || d <= 0 || ldx < d || ldy < d || ldc < m)
+    return B200OT_E_INVALID;
+  if (kind != B200OT_COST_SQEUCLIDEAN && kind != B200OT_COST_COSINE) return B200OT_E_INVALID;
+  if (terms != 1 && terms != 3 && terms != 6) return B200OT_E_INVALID;
+  const int nparts = terms == 1 ? 1 : terms == 3 ? 2 : 3;
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return B200OT_E_INVALID;
+  const CostWs w = cost_ws(n, m, d);
+  if (ws_bytes < w.total) return B200OT_E_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  uint8_t* Ap = base + w.a_off;
+  uint8_t* Bp = base + w.b_off;
+  float* xn = reinterpret_cast<float*>(base + w.norm_off);
+  float* yn = xn + n;
+  const int cosine = kind == B200OT_COST_COSINE ? 1 : 0;
+  split_tiles_kernel<<<(w.n_pad * 32 + 255) / 256, 256, 0, s>>>(X, ldx, n, d, TC_BM, w.kblocks, w.n_pad, cosine, nparts, Ap, xn);
+  B200OT_LAUNCH_OK();
+  split_tiles_kernel<<<(w.m_pad * 32 + 255) / 256, 256, 0, s>>>(Y, ldy, m, d, TC_BN, w.kblocks, w.m_pad, cosine, nparts, Bp, yn);
+  B200OT_LAUNCH_OK();
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200OT_CUDA_OK(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    attr_set = true;
+  }
+  CostTcArgs a;
+  a.A = Ap;
+  a.B = Bp;
+  a.xn = xn;
+  a.yn = yn;
+  a.C = C;
+  a.ldc = ldc;
+  a.n = n;
+  a.m = m;
+  a.kblocks = w.kblocks;
+  a.nseg = terms;
+  a.nparts = nparts;
+  a.cosine = cosine;
+  a.tiles_m = w.n_pad / TC_BM;
+  a.tiles_n = w.m_pad / TC_BN;
+  const long long tiles = (long long)a.tiles_m * a.tiles_n;
+  int grid = sm_count();
+  if (grid > tiles) grid = (int)tiles;
+  cost_tc_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(a);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

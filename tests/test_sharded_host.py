@@ -1,0 +1,127 @@
+"""Host-side logic of the row-sharded solver (b200ot/sharded.py) on CPU with gloo, world_size 2.
+
+The CUDA kernels cannot run here, so the per-rank kernel interface is filled by a float64 NumPy
+emulation of what the C-ABI kernels compute (test infrastructure); what is under test is the
+orchestration: the row partition, the one all-reduce per iteration, the replicated stopping rule
+(every rank must stop at the same iteration), and that the sharded result equals the unsharded oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ot_oracle as orc
+
+
+def test_row_range_partitions_everything():
+    from b200ot.sharded import row_range
+    for n in (1, 3, 4, 7, 64, 65, 1000, 65536):
+        for world in (1, 2, 3, 4, 8):
+            spans = [row_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(spans, spans[1:]):
+                assert hi == lo2 and lo <= hi
+            for lo, hi in spans:
+                assert hi == lo or lo % 4 == 0  # non-empty shards start on a group-of-4 row boundary
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 4 or n < 4 * world
+
+
+class NumpyShardKernels:
+    """float64 emulation of the per-rank kernels (setup / prologue / sweep / finalize / flags / finish)."""
+
+    def __init__(self, C_local, a_local, b, eps, max_iter, tol, check_every, check_phase):
+        self.C, self.a, self.b, self.eps = C_local, a_local, b, eps
+        self.max_iter, self.tol, self.ce, self.cp = max_iter, tol, check_every, check_phase
+
+    def setup(self):
+        self.f = np.zeros(len(self.a))
+        self.g = np.zeros(len(self.b))
+        self.it, self.done, self.converged, self.errs = 0, 0, 0, []
+
+    def prologue(self):
+        return torch.from_numpy(np.exp((self.f[:, None] + self.g[None, :] - self.C) / self.eps).sum(0))
+
+    def sweep(self):
+        if self.done:
+            return torch.zeros(len(self.b), dtype=torch.float64)
+        t = np.exp((self.f[:, None] + self.g[None, :] - self.C) / self.eps)
+        w = self.a / t.sum(1)
+        self.f = self.f + self.eps * np.log(w)
+        return torch.from_numpy((t * w[:, None]).sum(0))
+
+    def finalize(self, s_total, is_prologue):
+        if self.done:
+            return
+        s = s_total.numpy()
+        g_next = self.g + self.eps * (np.log(self.b) - np.log(s))
+        if is_prologue:
+            self.g = g_next
+            return
+        self.it += 1
+        if self.it % self.ce == self.cp % self.ce:
+            err = float(np.abs(s - self.b).sum())
+            self.errs.append(err)
+            if err < self.tol:
+                self.converged = self.done = 1
+                return
+        if self.it >= self.max_iter:
+            self.done = 1
+            return
+        self.g = g_next
+
+    def flags(self):
+        return {"it": self.it, "done": self.done, "converged": self.converged, "bad": 0, "n_err": len(self.errs)}
+
+    def finish(self):
+        return self.f, self.g, {"n_iter": self.it, "converged": bool(self.converged), "errs": self.errs}
+
+
+def _worker(rank, world, port, n, m, tol, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "ot-based-heterogeneous-multi-modal-fusion-embedding-for-ad-analysis-_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from b200ot.sharded import ShardedSinkhorn, row_range
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, Y = orc.synthetic_embeddings(n, m, 16, config_index=4)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    lo, hi = row_range(n, world, rank)
+    k = NumpyShardKernels(C[lo:hi], a[lo:hi], b, 0.1, 200, tol, 10, 0)
+    drv = ShardedSinkhorn(k)
+    f, g, info = drv.solve(200, check_every=10, check_phase=0)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), f=f, g=g, lo=lo, hi=hi, n_iter=info["n_iter"],
+             converged=info["converged"], allreduces=drv.allreduces, errs=np.array(info["errs"]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tol", [1e-3, 0.0])
+def test_two_rank_gloo_solve_matches_unsharded_oracle(tmp_path, tol):
+    n, m, world = 50, 36, 2
+    port = 29500 + (os.getpid() % 500) + (0 if tol else 1)
+    mp.spawn(_worker, args=(world, port, n, m, tol, str(tmp_path)), nprocs=world, join=True)
+    X, Y = orc.synthetic_embeddings(n, m, 16, config_index=4)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    Pref, lg = orc.sinkhorn_log(C, a, b, 0.1, max_iter=200, tol=tol, err_norm="l1", check_every=10, check_phase=0,
+                                log=True)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    # every rank took the same decisions
+    assert len({int(p["n_iter"]) for p in parts}) == 1
+    assert int(parts[0]["n_iter"]) == lg["n_iter"]
+    assert bool(parts[0]["converged"]) == lg["converged"]
+    # one all-reduce for the first g update + one per iteration actually queued
+    assert int(parts[0]["allreduces"]) >= 1 + lg["n_iter"]
+    f = np.concatenate([p["f"] for p in parts])
+    np.testing.assert_allclose(parts[0]["g"], parts[1]["g"], rtol=0, atol=0)  # replicated, bit-identical
+    P = orc.plan_from_potentials(C, f, parts[0]["g"], 0.1)
+    np.testing.assert_allclose(P, Pref, rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(parts[0]["errs"], lg["err"], rtol=1e-8)
