@@ -28,7 +28,7 @@ def test_row_range_partitions_everything():
             for lo, hi in spans:
                 assert hi == lo or lo % 4 == 0  # non-empty shards start on a group-of-4 row boundary
             sizes = [hi - lo for lo, hi in spans]
-            assert max(sizes) - min(sizes) <= 4 or n < 4 * world
+            assert max(sizes) - min(sizes) <= 7 or n < 4 * world  # one group of 4 plus a ragged tail
 
 
 class NumpyShardKernels:
