@@ -74,6 +74,23 @@ def _uniform(n, device):
 # ---------------------------------------------------------------------------
 # POT surface
 # ---------------------------------------------------------------------------
+def unif(n, type_as=None):
+    """``ot.unif(n)`` (MRI_PET_OT_nojax.py:72-73): uniform histogram."""
+    if isinstance(type_as, torch.Tensor):
+        return torch.full((n,), 1.0 / n, dtype=type_as.dtype, device=type_as.device)
+    return np.ones((n,)) / n
+
+
+def dist(x1, x2=None, metric="sqeuclidean", *, device=None):
+    """``ot.dist(x1, x2)`` (MRI_PET_OT_nojax.py:70-71): pairwise squared-Euclidean (default) or
+    cosine cost, built on the GPU (tcgen05 split-bf16 GEMM for large problems)."""
+    if metric not in ("sqeuclidean", "cosine"):
+        raise B200OTError(f"metric {metric!r} is not used on the reference's OT path")
+    x2 = x1 if x2 is None else x2
+    cv = _Conv(x1, device)
+    return cv.back(ops.cost_matrix(cv.to_dev(x1), cv.to_dev(x2), kind=metric))
+
+
 def sinkhorn(a, b, M, reg, method="sinkhorn", numItermax=1000, stopThr=1e-9, verbose=False,
              log=False, warn=True, warmstart=None, *, check_every=10, err_norm="l2", stop_inclusive=False,
              path="auto", device=None, **kwargs):

@@ -19,6 +19,7 @@ void set_last_cuda_error(cudaError_t e, const char* where);
     cudaError_t _e = (expr);                            \
     if (_e != cudaSuccess) {                            \
       ::b200ot::set_last_cuda_error(_e, #expr);         \
+      (void)cudaGetLastError();                         \
       return B200OT_E_LAUNCH;                           \
     }                                                   \
   } while (0)

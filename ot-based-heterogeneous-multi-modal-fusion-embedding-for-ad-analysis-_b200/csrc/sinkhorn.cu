@@ -698,15 +698,28 @@ __global__ void export_kernel(const State* st, int n, int m, const float* fs, co
 // =============================================================================
 // host side
 // =============================================================================
+constexpr size_t kSweepSmemMax = 232448 - 1024;
+
 struct FusedCfg {
   int Q, NCH, R, NG, NC;
   size_t smem;
 };
 
-constexpr size_t kSweepSmemMax = 232448 - 1024;
+
+template <int NCH, int R>
+static cudaError_t fused_set_attr() {
+  static bool attr_set = false;  // one flag per instantiation
+  if (attr_set) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(sweep_fused_kernel<NCH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(232448 - 1024));
+  if (e == cudaSuccess) attr_set = true;
+  return e;
+}
 
 template <int NCH, int R>
 static cudaError_t launch_fused(const SweepArgs& a, int Q, int NC, size_t smem, cudaStream_t s) {
+  cudaError_t e = fused_set_attr<NCH, R>();
+  if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(NC * Q));
@@ -725,15 +738,13 @@ static cudaError_t launch_fused(const SweepArgs& a, int Q, int NC, size_t smem, 
 
 template <int NCH, int R>
 static int query_fused(int Q, size_t smem, int* nc_out) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sweep_fused_kernel<NCH, R>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSweepSmemMax);
+  {
+    cudaError_t e = fused_set_attr<NCH, R>();
     if (e != cudaSuccess) {
       set_last_cuda_error(e, "cudaFuncSetAttribute(sweep_fused)");
+      (void)cudaGetLastError();
       return B200OT_E_LAUNCH;
     }
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -881,6 +892,7 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
 #undef B200OT_L
   if (e != cudaSuccess) {
     set_last_cuda_error(e, "sweep_fused launch");
+    (void)cudaGetLastError();  // do not leave a stale error for the next launch check
     return B200OT_E_LAUNCH;
   }
   *np_out = cfg.NC;
