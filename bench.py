@@ -228,7 +228,8 @@ def run_b200(args):
         _, _, info = stepper.finish()
     else:
         _, _, info = kern.finish()
-    assert info["n_iter"] == iters and info["status"] == 0, info
+    if not os.environ.get("B200OT_FUSED_MODE"):  # diagnostic modes do not run the real arithmetic
+        assert info["n_iter"] == iters and info["status"] == 0, info
     ms_per_step = ms / args.steps
     value = iters / (ms_per_step * 1e-3)
 

@@ -203,6 +203,19 @@ int b200ot_apply_plan_t(const float* C, int ldc, int n, int m, const float* f, c
 int b200ot_cosine_loss(const float* A, int lda, const float* B, int ldb, int rows, int d,
                        float* out, void* stream);
 
+/* ---- attention fusion core ----------------------------------------------------
+ * softmax(Q K^T / sqrt(dh)) V for the S <= 4 fusion tokens of the reference's SelfAttentionBlock
+ * (MRI_PET_OT_OT_per_epoch_attn.py:523-549, tokens built at :731-738; one token in
+ * MRI_PET_OT_nojax.py:664-669).  qkv is (S, B, 3E) as produced by nn.MultiheadAttention's
+ * in_proj (batch_first=False), out is (S, B, E), probs (B, H, S, S) keeps the softmax for the
+ * backward pass.  keep_mask (B, H, S, S; may be NULL) with keep_scale = 1/(1-p) is the attention
+ * dropout of training mode.  One warp per (sample, head), forward and backward.          */
+int b200ot_token_attention_fwd(const float* qkv, int S, int B, int E, int H, const float* keep_mask,
+                               float keep_scale, float* out, float* probs, void* stream);
+int b200ot_token_attention_bwd(const float* qkv, const float* probs, const float* keep_mask,
+                               float keep_scale, const float* dout, int S, int B, int E, int H,
+                               float* dqkv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

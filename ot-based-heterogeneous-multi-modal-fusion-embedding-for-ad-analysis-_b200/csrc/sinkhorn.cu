@@ -26,6 +26,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200ot {
@@ -42,7 +44,29 @@ struct State {
   int stop_inclusive, path, snap_it, snap_cur;
   int snap_n_err, pad0, pad1, pad2;
   float snap_err, pad3, pad4, pad5;
+  // range of the scaled row potentials fs; slot [it & 1] is valid when `it` iterations are complete,
+  // the sweep of iteration it+1 fills slot [(it+1) & 1].  lo > hi means "unknown".
+  float fs_lo[2], fs_hi[2];
 };
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *a;
+  while (__int_as_float(old) > v) {
+    const int prev = atomicCAS(a, old, __float_as_int(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  int* a = reinterpret_cast<int*>(addr);
+  int old = *a;
+  while (__int_as_float(old) < v) {
+    const int prev = atomicCAS(a, old, __float_as_int(v));
+    if (prev == old) break;
+    old = prev;
+  }
+}
 static_assert(sizeof(State) <= 256, "state block");
 
 struct WsLayout {
@@ -113,32 +137,41 @@ static WsPtrs ws_ptrs(void* ws, const WsLayout& L) {
 // =============================================================================
 // state / vector initialisation
 // =============================================================================
-__global__ void init_kernel(State* st, b200ot_params prm, int n, int m, const float* __restrict__ a,
-                            const float* __restrict__ b, const float* __restrict__ f0,
-                            const float* __restrict__ g0, float* fs, float* gs0, float* gs1, float* wa,
-                            float* wb, float* log2b) {
-  const float k = kLog2e / prm.eps;
+__global__ void init_state_kernel(State* st, b200ot_params prm) {
+  State s;
+  memset(&s, 0, sizeof(s));
+  s.kscale = kLog2e / prm.eps;
+  s.eps = prm.eps;
+  s.tol = prm.tol;
+  s.max_iter = prm.max_iter;
+  s.check_every = prm.check_every > 0 ? prm.check_every : 1;
+  s.check_phase = prm.check_phase;
+  s.err_norm = prm.err_norm;
+  s.stop_inclusive = prm.stop_inclusive;
+  s.path = prm.path;
+  s.err = INFINITY;
+  s.initialised = 1;
+  s.done = prm.max_iter <= 0 ? 1 : 0;
+  s.fs_lo[0] = INFINITY;
+  s.fs_hi[0] = -INFINITY;
+  s.fs_lo[1] = INFINITY;
+  s.fs_hi[1] = -INFINITY;
+  *st = s;
+}
+
+__global__ void __launch_bounds__(256) init_kernel(State* st, float eps, int n, int m,
+                                                   const float* __restrict__ a, const float* __restrict__ b,
+                                                   const float* __restrict__ f0, const float* __restrict__ g0,
+                                                   float* fs, float* gs0, float* gs1, float* wa, float* wb,
+                                                   float* log2b) {
+  const float k = kLog2e / eps;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) {
-    State s;
-    memset(&s, 0, sizeof(s));
-    s.kscale = k;
-    s.eps = prm.eps;
-    s.tol = prm.tol;
-    s.max_iter = prm.max_iter;
-    s.check_every = prm.check_every > 0 ? prm.check_every : 1;
-    s.check_phase = prm.check_phase;
-    s.err_norm = prm.err_norm;
-    s.stop_inclusive = prm.stop_inclusive;
-    s.path = prm.path;
-    s.err = INFINITY;
-    s.initialised = 1;
-    s.done = prm.max_iter <= 0 ? 1 : 0;
-    *st = s;
-  }
+  float lo = INFINITY, hi = -INFINITY;
   if (i < n) {
-    fs[i] = f0 ? f0[i] * k : 0.f;
+    const float v = f0 ? f0[i] * k : 0.f;
+    fs[i] = v;
     wa[i] = a[i];
+    if (fabsf(v) < INFINITY) lo = hi = v;
   }
   if (i < m) {
     const float g = g0 ? g0[i] * k : 0.f;
@@ -146,6 +179,15 @@ __global__ void init_kernel(State* st, b200ot_params prm, int n, int m, const fl
     gs1[i] = g;
     wb[i] = b[i];
     log2b[i] = log2f(b[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomic_min_float(&st->fs_lo[0], lo);
+    atomic_max_float(&st->fs_hi[0], hi);
   }
 }
 
@@ -230,6 +272,14 @@ __global__ void __launch_bounds__(kFinalizeThreads)
   }
   const int it = st->it + 1;
   st->it = it;
+  // fs range bookkeeping: the sweep that just ran filled slot [it & 1] (the two-sweep path does not
+  // track it: mark unknown); open the other slot for the next sweep
+  if (part_max) {
+    st->fs_lo[it & 1] = INFINITY;
+    st->fs_hi[it & 1] = -INFINITY;
+  }
+  st->fs_lo[(it + 1) & 1] = INFINITY;
+  st->fs_hi[(it + 1) & 1] = -INFINITY;
   const int ce = st->check_every;
   const bool check = (it % ce) == (st->check_phase % ce);
   bool stop = false;
@@ -267,6 +317,8 @@ struct SweepArgs {
   size_t stride;
   int ng;          // ring depth in row groups
   int evict_first; // stream C through L2 with an evict-first policy
+  int wq;          // columns per CTA (multiple of 4, <= 2048*NCH): an even split of m over the cluster
+  int mode;        // 0 = normal; 1 = stream only (diagnostic: TMA ring without the arithmetic)
 };
 
 constexpr int kSweepThreads = 512;
@@ -306,9 +358,18 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
   const int NC = (int)cluster_nid_x();
   const int NG = p.ng;
 
-  const long long col0 = (long long)q * W;
+  const long long col0 = (long long)q * p.wq;
   int mvalid = p.m - (int)col0;
-  mvalid = mvalid < 0 ? 0 : (mvalid > W ? W : mvalid);
+  mvalid = mvalid < 0 ? 0 : (mvalid > p.wq ? p.wq : mvalid);
+
+  // Shift of the exponent.  t_ij = 2^(shift + gs_j - k C_ij) must stay in fp32 range; the exact choice
+  // cancels in w_i = a_i / r_i.  If the row potentials of the previous iteration span less than 2^48 a
+  // single shift (mid-range) is folded into gs once per sweep and saves one FADD per element;
+  // otherwise each row uses its own previous potential.
+  const int it0 = st->it;
+  const float flo = st->fs_lo[it0 & 1], fhi = st->fs_hi[it0 & 1];
+  const bool uniform = (fhi - flo) < 48.f;  // false when the range is unknown (lo > hi) or infinite
+  const float sigma = uniform ? 0.5f * (flo + fhi) : 0.f;
 
   float* stage = reinterpret_cast<float*>(smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NG * R * W * sizeof(float));  // [8]
@@ -324,10 +385,10 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
     cvalid[c] = col < mvalid;
     float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cvalid[c]) g4 = *reinterpret_cast<const float4*>(gs + col0 + col);
-    gsv[c * 4 + 0] = g4.x;
-    gsv[c * 4 + 1] = g4.y;
-    gsv[c * 4 + 2] = g4.z;
-    gsv[c * 4 + 3] = g4.w;
+    gsv[c * 4 + 0] = g4.x + sigma;
+    gsv[c * 4 + 1] = g4.y + sigma;
+    gsv[c * 4 + 2] = g4.z + sigma;
+    gsv[c * 4 + 3] = g4.w + sigma;
     acc[c * 4 + 0] = acc[c * 4 + 1] = acc[c * 4 + 2] = acc[c * 4 + 3] = 0.f;
   }
 
@@ -346,15 +407,15 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
 
   auto issue = [&](int i) {
     const int row0 = (cid + i * NC) * R;
-    int rows = p.n - row0;
-    rows = rows > R ? R : rows;
     const int s = i % NG;
     const uint32_t bar = smem_u32(full + s);
     const uint32_t row_bytes = (uint32_t)mvalid * 4u;
-    mbar_arrive_expect_tx(bar, row_bytes * rows);
+    mbar_arrive_expect_tx(bar, row_bytes * R);
     if (row_bytes) {
-      for (int r = 0; r < rows; ++r) {
-        const float* src = p.C + (long long)(row0 + r) * p.ldc + col0;
+      for (int r = 0; r < R; ++r) {
+        int row = row0 + r;
+        row = row < p.n ? row : p.n - 1;  // ragged last group: re-read the last row, its weight is zero
+        const float* src = p.C + (long long)row * p.ldc + col0;
         const uint32_t dst = smem_u32(stage + ((size_t)s * R + r) * W);
         if (p.evict_first)
           bulk_g2s_hint(dst, src, row_bytes, bar, pol);
@@ -370,12 +431,21 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
   }
 
   struct Ctx {
-    float fsr[R], ar[R];
+    float sh[R], ar[R];  // sh: exponent shift of the row (sigma or its previous potential)
     int row0, rows;
   };
+  float f_lo = INFINITY, f_hi = -INFINITY;  // range of the potentials this thread writes
 
-  // P1 + SEND of group i
-  auto front = [&](int i, float (&t)[R][CPT], Ctx& cx) {
+  // Column validity: the host guarantees mvalid > 2048*(NCH-1) for every CTA, so quads 0..NCH-2 are
+  // valid for all threads; only the last quad is masked (warp-uniform skip where a whole warp is out).
+  const bool last_ok = cvalid[NCH - 1];
+  const bool last_any = __any_sync(0xffffffffu, last_ok);
+  const bool stream_only = (p.mode & 1) != 0;  // diagnostic: skip the arithmetic
+  const bool no_exchange = (p.mode & 2) != 0;  // diagnostic: skip the DSMEM exchange (wrong row sums)
+
+  // P1 + SEND of group i.  Rows beyond n are loaded as copies of row n-1 (finite data) and get w = 0.
+  auto front = [&](int i, float (&t)[R][CPT], Ctx& cx, auto uni_tag) {
+    constexpr bool UNI = decltype(uni_tag)::value;
     const int s = i % NG;
     const uint32_t ph = (uint32_t)((i / NG) & 1);
     cx.row0 = (cid + i * NC) * R;
@@ -383,34 +453,65 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
     cx.rows = cx.rows > R ? R : cx.rows;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      cx.fsr[r] = 0.f;
+      cx.sh[r] = sigma;
       cx.ar[r] = 0.f;
       if (r < cx.rows) {
-        cx.fsr[r] = p.fs[cx.row0 + r];
+        if (!UNI) cx.sh[r] = p.fs[cx.row0 + r];
         cx.ar[r] = p.a[cx.row0 + r];
       }
     }
     mbar_wait(smem_u32(full + s), ph);
     float ps[R];
+    auto quad = [&](int r, int c, const float* srow) {
+      const float4 v = *reinterpret_cast<const float4*>(srow + c * (kSweepThreads * 4));
+      float e0, e1, e2, e3;
+      if (UNI) {
+        e0 = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0]));
+        e1 = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1]));
+        e2 = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2]));
+        e3 = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3]));
+      } else {
+        e0 = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + cx.sh[r]));
+        e1 = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + cx.sh[r]));
+        e2 = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + cx.sh[r]));
+        e3 = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + cx.sh[r]));
+      }
+      t[r][c * 4 + 0] = e0;
+      t[r][c * 4 + 1] = e1;
+      t[r][c * 4 + 2] = e2;
+      t[r][c * 4 + 3] = e3;
+    };
+    if (!stream_only) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float* srow = stage + ((size_t)s * R + r) * W + tid * 4;
+#pragma unroll
+        for (int c = 0; c < NCH - 1; ++c) quad(r, c, srow);  // straight-line: loads batch ahead of the math
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float* srow = stage + ((size_t)s * R + r) * W + tid * 4;
+        if (last_any) {
+          quad(r, NCH - 1, srow);  // smem beyond mvalid holds stale but finite-or-masked data
+          if (!last_ok) t[r][CPT - 4] = t[r][CPT - 3] = t[r][CPT - 2] = t[r][CPT - 1] = 0.f;
+        } else {
+          t[r][CPT - 4] = t[r][CPT - 3] = t[r][CPT - 2] = t[r][CPT - 1] = 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          t[r][c * 4 + 0] = t[r][c * 4 + 1] = t[r][c * 4 + 2] = t[r][c * 4 + 3] = cvalid[c] ? 1.f : 0.f;
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      ps[r] = 0.f;
-      const float* srow = stage + ((size_t)s * R + r) * W + tid * 4;
+      float acc4 = 0.f;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool ok = cvalid[c] && (r < cx.rows);
-        if (ok) v = *reinterpret_cast<const float4*>(srow + c * (kSweepThreads * 4));
-        const float e0 = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + cx.fsr[r]));
-        const float e1 = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + cx.fsr[r]));
-        const float e2 = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + cx.fsr[r]));
-        const float e3 = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + cx.fsr[r]));
-        t[r][c * 4 + 0] = ok ? e0 : 0.f;
-        t[r][c * 4 + 1] = ok ? e1 : 0.f;
-        t[r][c * 4 + 2] = ok ? e2 : 0.f;
-        t[r][c * 4 + 3] = ok ? e3 : 0.f;
-        ps[r] += (t[r][c * 4 + 0] + t[r][c * 4 + 1]) + (t[r][c * 4 + 2] + t[r][c * 4 + 3]);
-      }
+      for (int c = 0; c < NCH; ++c)
+        acc4 += (t[r][c * 4 + 0] + t[r][c * 4 + 1]) + (t[r][c * 4 + 2] + t[r][c * 4 + 3]);
+      ps[r] = acc4;
     }
     const int par = i & 1;
 #pragma unroll
@@ -425,9 +526,9 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
         fence_proxy_async();
         issue(i + NG);
       }
-      mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * R * 4));
+      if (!no_exchange) mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * R * 4));
     }
-    if (tid < R * Q) {
+    if (tid < R * Q && !no_exchange) {
       const int r = tid / Q, qq = tid - r * Q;
       float v = 0.f;
 #pragma unroll
@@ -441,20 +542,31 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
   // P2 of group i
   auto back = [&](int i, float (&t)[R][CPT], const Ctx& cx) {
     const int xb = i % kXBuf;
-    mbar_wait(smem_u32(xbar + xb), (uint32_t)((i / kXBuf) & 1));
+    if (!no_exchange) mbar_wait(smem_u32(xbar + xb), (uint32_t)((i / kXBuf) & 1));
     float wr[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       float rt = 0.f;
+      if (no_exchange) {
+        rt = red[((i & 1) * kSweepWarps) * R + r] * (float)(Q * kSweepWarps);
+      } else {
 #pragma unroll
-      for (int qq = 0; qq < kMaxCluster; ++qq)
-        if (qq < Q) rt += xch[(xb * R + r) * kMaxCluster + qq];
+        for (int qq = 0; qq < kMaxCluster; ++qq)
+          if (qq < Q) rt += xch[(xb * R + r) * kMaxCluster + qq];
+      }
       const bool live = (r < cx.rows) && (cx.ar[r] > 0.f);
       wr[r] = live ? __fdividef(cx.ar[r], rt) : 0.f;
-      if (q == 0 && tid == r && r < cx.rows) {
-        const float fnew = live ? cx.fsr[r] + (log2f(cx.ar[r]) - log2f(rt)) : -INFINITY;
+      if (q == 0 && tid == r && r < cx.rows && !stream_only) {
+        const float fnew = live ? cx.sh[r] + (log2f(cx.ar[r]) - log2f(rt)) : -INFINITY;
         p.fs[cx.row0 + r] = fnew;
-        if (live && !(fabsf(fnew) < INFINITY)) atomicExch(&st->bad, 1);
+        if (live) {
+          if (fabsf(fnew) < INFINITY) {
+            f_lo = fminf(f_lo, fnew);
+            f_hi = fmaxf(f_hi, fnew);
+          } else {
+            atomicExch(&st->bad, 1);
+          }
+        }
       }
     }
 #pragma unroll
@@ -466,14 +578,23 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
 
   float tA[R][CPT], tB[R][CPT];
   Ctx cA, cB;
-  if (cnt > 0) front(0, tA, cA);
-  for (int i = 0; i < cnt; i += 2) {
-    if (i + 1 < cnt) front(i + 1, tB, cB);
-    back(i, tA, cA);
-    if (i + 1 < cnt) {
-      if (i + 2 < cnt) front(i + 2, tA, cA);
-      back(i + 1, tB, cB);
+  // F0 F1 B0 F2 B1 F3 B2 ... : even groups use register set A, odd groups set B
+  auto run = [&](auto uni_tag) {
+    for (int i = -1; i < cnt; i += 2) {
+      if (i + 1 < cnt) front(i + 1, tA, cA, uni_tag);
+      if (i >= 0) back(i, tB, cB);
+      if (i + 2 < cnt) front(i + 2, tB, cB, uni_tag);
+      if (i + 1 < cnt) back(i + 1, tA, cA);
     }
+  };
+  if (uniform)
+    run(std::true_type{});
+  else
+    run(std::false_type{});
+
+  if (q == 0 && tid < R && f_lo <= f_hi) {
+    atomic_min_float(&st->fs_lo[(it0 + 1) & 1], f_lo);
+    atomic_max_float(&st->fs_hi[(it0 + 1) & 1], f_hi);
   }
 
 #pragma unroll
@@ -673,6 +794,8 @@ __global__ void rewind_kernel(State* st, int n, int m, float* fs, float* gs0, fl
     st->converged = 0;
     st->bad = 0;
     st->ticket = 0;
+    st->fs_lo[0] = st->fs_lo[1] = INFINITY;  // range unknown after a rewind: per-row shift
+    st->fs_hi[0] = st->fs_hi[1] = -INFINITY;
   }
 }
 
@@ -701,7 +824,7 @@ __global__ void export_kernel(const State* st, int n, int m, const float* fs, co
 constexpr size_t kSweepSmemMax = 232448 - 1024;
 
 struct FusedCfg {
-  int Q, NCH, R, NG, NC;
+  int Q, NCH, R, NG, NC, wq;
   size_t smem;
 };
 
@@ -772,6 +895,10 @@ static int query_fused(int Q, size_t smem, int* nc_out) {
 static int rows_for_nch(int nch) { return nch <= 2 ? 4 : nch <= 4 ? 2 : 1; }
 constexpr int kMaxNch = 6;
 
+// columns per CTA: an even split of m over the cluster, rounded up to 128 floats (512 B) so every CTA's
+// slice starts on a cache-line boundary and column validity is warp-uniform; Q = 1 keeps m itself.
+static int fused_wq(int m, int Q) { return Q == 1 ? m : ((m + Q - 1) / Q + 127) / 128 * 128; }
+
 static size_t fused_fixed_smem(int R) {
   return 8 * 8 + kXBuf * 8 + (2 * kSweepWarps * R + kXBuf * R * kMaxCluster) * 4 + 128;
 }
@@ -811,15 +938,18 @@ static int pick_fused(int n, int m, FusedCfg* out) {
   const char* en = getenv("B200OT_FUSED_NCH");
   if (eq && en) {
     const int Q = atoi(eq), N = atoi(en);
-    if (Q >= 1 && Q <= kMaxCluster && N >= 1 && N <= kMaxNch && (long long)Q * N * 2048 >= m) {
+    if (Q >= 1 && Q <= kMaxCluster && N >= 1 && N <= kMaxNch && (long long)Q * N * 2048 >= m &&
+        N == (fused_wq(m, Q) + 2047) / 2048 && m - (Q - 1) * fused_wq(m, Q) > 2048 * (N - 1)) {
       bestQ = Q;
       bestN = N;
     }
   }
   if (!bestQ) {
     for (int Q = 1; Q <= kMaxCluster; ++Q) {
-      const int N = (int)((m + (long long)Q * 2048 - 1) / ((long long)Q * 2048));
+      const int wq = fused_wq(m, Q);
+      const int N = (wq + 2047) / 2048;
       if (N > kMaxNch) continue;
+      if (m - (Q - 1) * wq <= 2048 * (N - 1)) continue;  // last CTA must reach into the last quad
       int nc = 0;
       const int rc = clusters_for(Q, N, &nc);
       if (rc) return rc;
@@ -854,6 +984,7 @@ static int pick_fused(int n, int m, FusedCfg* out) {
   out->NG = NG;
   out->NC = NC;
   out->smem = (size_t)NG * stage + fixed;
+  out->wq = fused_wq(m, bestQ);
   return 0;
 }
 
@@ -886,6 +1017,9 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
   a.evict_first = ((double)n * (double)m * 4.0 > 100e6) ? 1 : 0;
   const char* ev = getenv("B200OT_FUSED_EVICT");
   if (ev) a.evict_first = atoi(ev);
+  a.wq = cfg.wq;
+  const char* em = getenv("B200OT_FUSED_MODE");
+  a.mode = em ? atoi(em) : 0;
   cudaError_t e = cudaSuccess;
 #define B200OT_L(NCH_, R_) e = launch_fused<NCH_, R_>(a, cfg.Q, cfg.NC, cfg.smem, s)
   B200OT_DISPATCH_NCH(cfg.NCH, B200OT_L)
@@ -976,7 +1110,9 @@ int b200ot_sinkhorn_setup(int n, int m, const float* a, const float* b, const fl
   const WsPtrs w = ws_ptrs(ws, L);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int mx = n > m ? n : m;
-  init_kernel<<<(mx + 255) / 256, 256, 0, s>>>(w.st, *prm, n, m, a, b, f0, g0, w.fs, w.gs0, w.gs1, w.a,
+  init_state_kernel<<<1, 1, 0, s>>>(w.st, *prm);
+  B200OT_LAUNCH_OK();
+  init_kernel<<<(mx + 255) / 256, 256, 0, s>>>(w.st, prm->eps, n, m, a, b, f0, g0, w.fs, w.gs0, w.gs1, w.a,
                                                w.b, w.log2b);
   B200OT_LAUNCH_OK();
   return 0;
