@@ -285,7 +285,7 @@ def run_b200(args):
         "config": {"workload": f"log-domain Sinkhorn n=m={n} d={D} eps={EPS}, {iters} iterations per solve "
                                f"(BASELINE configs[3]; single-sweep fused kernel, C resident in HBM)",
                    "n": n, "m": m, "d": D, "eps": EPS, "iterations_per_step": iters, "path": args.path,
-                   "rows_per_gpu": n_loc, "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                   "rows_per_gpu": n_loc, "kernel": ops.describe_kernel(n_loc, m), "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                    "l2": "cost matrix (%.1f GiB per GPU) is far larger than L2, no flush needed" % (alg_bytes / 2**30)},
         "hbm_gbs": achieved * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

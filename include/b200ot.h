@@ -141,6 +141,8 @@ int b200ot_sinkhorn_enqueue(const float* C, int ldc, int n, int m, int iters, in
 int b200ot_sinkhorn_snapshot(int n, int m, void* ws, void* stream);
 int b200ot_sinkhorn_rewind(int n, int m, void* ws, void* stream);
 int b200ot_sinkhorn_peek(void* ws, int* flags8, void* stream);
+/* human-readable description of the kernel configuration chosen for an n x m problem (host buffer) */
+int b200ot_sinkhorn_describe(int n, int m, char* buf_host, int buf_len);
 int b200ot_sinkhorn_finish(int n, int m, void* ws, float* f, float* g, b200ot_result* result,
                            float* err_hist, int err_hist_cap, void* stream);
 /* blocking convenience driver: init, chunks ending on check iterations with the flags of

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200ot.so")
+# B200OT_LIB lets a tuning run A/B two builds of the same ABI in one process launch each
+LIB_PATH = os.environ.get("B200OT_LIB") or os.path.join(HERE, "libb200ot.so")
 
 # status codes / enums (include/b200ot.h)
 OK, E_INVALID, E_WORKSPACE, E_LAUNCH, E_UNSUPPORTED, E_NUMERIC = 0, -1, -2, -3, -4, -5
@@ -59,6 +60,7 @@ SIGNATURES = {
     "b200ot_sinkhorn_snapshot": (_i, [_i, _i, _p, _p]),
     "b200ot_sinkhorn_rewind": (_i, [_i, _i, _p, _p]),
     "b200ot_sinkhorn_peek": (_i, [_p, _p, _p]),
+    "b200ot_sinkhorn_describe": (_i, [_i, _i, C.c_char_p, _i]),
     "b200ot_sinkhorn_finish": (_i, [_i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "b200ot_sinkhorn_solve": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, C.POINTER(Params), _p, _sz, _p, _p,
                                    C.POINTER(Result), _p, _i, _p]),

@@ -166,6 +166,14 @@ def _ws_ptr(ws: torch.Tensor):
     return C.c_void_p((base + 255) // 256 * 256)
 
 
+def describe_kernel(n: int, m: int) -> str:
+    """Which Sinkhorn kernel configuration the library picks for an n x m problem (needs a GPU)."""
+    lib = _lib.load()
+    buf = C.create_string_buffer(512)
+    check(lib.b200ot_sinkhorn_describe(int(n), int(m), buf, 512), "b200ot_sinkhorn_describe")
+    return buf.value.decode()
+
+
 def make_params(eps, max_iter, tol, check_every=10, check_phase=1, err_norm="l2",
                 stop_inclusive=False, path="auto") -> Params:
     return Params(float(eps), int(max_iter), float(tol), int(check_every), int(check_phase),

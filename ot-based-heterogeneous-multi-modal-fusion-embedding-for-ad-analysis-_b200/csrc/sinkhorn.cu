@@ -442,6 +442,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
   const bool last_any = __any_sync(0xffffffffu, last_ok);
   const bool stream_only = (p.mode & 1) != 0;  // diagnostic: skip the arithmetic
   const bool no_exchange = (p.mode & 2) != 0;  // diagnostic: skip the DSMEM exchange (wrong row sums)
+  const bool no_exp = (p.mode & 4) != 0;       // diagnostic: replace ex2 by a multiply (wrong values)
 
   // P1 + SEND of group i.  Rows beyond n are loaded as copies of row n-1 (finite data) and get w = 0.
   auto front = [&](int i, float (&t)[R][CPT], Ctx& cx, auto uni_tag) {
@@ -465,16 +466,26 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
     auto quad = [&](int r, int c, const float* srow) {
       const float4 v = *reinterpret_cast<const float4*>(srow + c * (kSweepThreads * 4));
       float e0, e1, e2, e3;
-      if (UNI) {
-        e0 = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0]));
-        e1 = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1]));
-        e2 = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2]));
-        e3 = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3]));
+      const float2 mk2 = make_float2(-k, -k);
+      float2 g0 = make_float2(gsv[c * 4 + 0], gsv[c * 4 + 1]);
+      float2 g1 = make_float2(gsv[c * 4 + 2], gsv[c * 4 + 3]);
+      if (!UNI) {
+        const float2 sh2 = make_float2(cx.sh[r], cx.sh[r]);
+        g0 = __fadd2_rn(g0, sh2);
+        g1 = __fadd2_rn(g1, sh2);
+      }
+      const float2 x0 = __ffma2_rn(make_float2(v.x, v.y), mk2, g0);
+      const float2 x1 = __ffma2_rn(make_float2(v.z, v.w), mk2, g1);
+      if (no_exp) {
+        e0 = x0.x * 1e-3f;
+        e1 = x0.y * 1e-3f;
+        e2 = x1.x * 1e-3f;
+        e3 = x1.y * 1e-3f;
       } else {
-        e0 = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + cx.sh[r]));
-        e1 = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + cx.sh[r]));
-        e2 = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + cx.sh[r]));
-        e3 = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + cx.sh[r]));
+        e0 = ex2_approx(x0.x);
+        e1 = ex2_approx(x0.y);
+        e2 = ex2_approx(x1.x);
+        e3 = ex2_approx(x1.y);
       }
       t[r][c * 4 + 0] = e0;
       t[r][c * 4 + 1] = e1;
@@ -507,11 +518,10 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float acc4 = 0.f;
+      float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c)
-        acc4 += (t[r][c * 4 + 0] + t[r][c * 4 + 1]) + (t[r][c * 4 + 2] + t[r][c * 4 + 3]);
-      ps[r] = acc4;
+      for (int c = 0; c < CPT / 2; ++c) s2 = __fadd2_rn(s2, make_float2(t[r][2 * c], t[r][2 * c + 1]));
+      ps[r] = s2.x + s2.y;
     }
     const int par = i & 1;
 #pragma unroll
@@ -571,8 +581,13 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
+      const float2 w2 = make_float2(wr[r], wr[r]);
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[r][c], wr[r], acc[c]);
+      for (int c = 0; c < CPT / 2; ++c) {
+        const float2 a2 = __ffma2_rn(make_float2(t[r][2 * c], t[r][2 * c + 1]), w2, make_float2(acc[2 * c], acc[2 * c + 1]));
+        acc[2 * c] = a2.x;
+        acc[2 * c + 1] = a2.y;
+      }
     }
   };
 
@@ -606,6 +621,199 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
     }
   }
   cluster_arrive();  // no CTA retires while a peer may still address its shared memory
+  cluster_wait();
+}
+
+// =============================================================================
+// FUSED single-sweep kernel, "lite" form: 256-thread CTAs, two per SM
+// =============================================================================
+// Same mathematics and data path as sweep_fused_kernel, but latency is hidden by occupancy instead of by
+// software pipelining: each CTA keeps ONE register set of exponentials (32 per thread), so two CTAs of
+// different clusters share an SM and one computes while the other sits in its reduction / DSMEM exchange.
+constexpr int kLiteThreads = 256;
+constexpr int kLiteWarps = kLiteThreads / 32;
+constexpr size_t kLiteSmemMax = 113 * 1024;
+
+template <int NCH>
+__global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const SweepArgs p) {
+  constexpr int CPT = 4 * NCH;
+  constexpr int W = kLiteThreads * CPT;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  State* st = p.st;
+  if (st->done) return;
+  const int cur = st->cur;
+  const float k = st->kscale;
+  const float* __restrict__ gs = cur ? p.gs1 : p.gs0;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = (int)cluster_ctarank();
+  const int Q = (int)cluster_nctarank();
+  const int cid = (int)cluster_id_x();
+  const int NC = (int)cluster_nid_x();
+  const int NG = p.ng;
+
+  const long long col0 = (long long)q * p.wq;
+  int mvalid = p.m - (int)col0;
+  mvalid = mvalid < 0 ? 0 : (mvalid > p.wq ? p.wq : mvalid);
+
+  const int it0 = st->it;
+  const float flo = st->fs_lo[it0 & 1], fhi = st->fs_hi[it0 & 1];
+  const bool uniform = (fhi - flo) < 48.f;
+  const float sigma = uniform ? 0.5f * (flo + fhi) : 0.f;
+
+  float* stage = reinterpret_cast<float*>(smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NG * W * sizeof(float));  // [8]
+  uint64_t* xbar = full + 8;                                                            // [kXBuf]
+  float* red = reinterpret_cast<float*>(xbar + kXBuf);  // [2][kLiteWarps]
+  float* xch = red + 2 * kLiteWarps;                     // [kXBuf][kMaxCluster]
+
+  float gsv[CPT], acc[CPT];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * (kLiteThreads * 4) + tid * 4;
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < mvalid) g4 = *reinterpret_cast<const float4*>(gs + col0 + col);
+    gsv[c * 4 + 0] = g4.x + sigma;
+    gsv[c * 4 + 1] = g4.y + sigma;
+    gsv[c * 4 + 2] = g4.z + sigma;
+    gsv[c * 4 + 3] = g4.w + sigma;
+    acc[c * 4 + 0] = acc[c * 4 + 1] = acc[c * 4 + 2] = acc[c * 4 + 3] = 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NG; ++s) mbar_init(smem_u32(full + s), 1);
+    for (int s = 0; s < kXBuf; ++s) mbar_init(smem_u32(xbar + s), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+
+  const int cnt = cid < p.n ? (p.n - cid + NC - 1) / NC : 0;  // rows cid, cid + NC, ...
+  const uint64_t pol = p.evict_first ? policy_evict_first() : 0ull;
+  const uint32_t row_bytes = (uint32_t)mvalid * 4u;
+  auto issue = [&](int i) {
+    const int s = i % NG;
+    const uint32_t bar = smem_u32(full + s);
+    mbar_arrive_expect_tx(bar, row_bytes);
+    if (row_bytes) {
+      const float* src = p.C + (long long)(cid + i * NC) * p.ldc + col0;
+      const uint32_t dst = smem_u32(stage + (size_t)s * W);
+      if (p.evict_first)
+        bulk_g2s_hint(dst, src, row_bytes, bar, pol);
+      else
+        bulk_g2s(dst, src, row_bytes, bar);
+    }
+  };
+  if (tid == 0) {
+    const int pre = cnt < NG ? cnt : NG;
+    for (int i = 0; i < pre; ++i) issue(i);
+  }
+
+  const bool last_ok = (NCH - 1) * (kLiteThreads * 4) + tid * 4 < mvalid;
+  const bool last_any = __any_sync(0xffffffffu, last_ok);
+  float f_lo = INFINITY, f_hi = -INFINITY;
+
+  auto row_loop = [&](auto uni_tag) {
+    constexpr bool UNI = decltype(uni_tag)::value;
+    float a_next = cnt > 0 ? p.a[cid] : 0.f;
+    float sh_next = (!UNI && cnt > 0) ? p.fs[cid] : sigma;
+    for (int i = 0; i < cnt; ++i) {
+      const int row = cid + i * NC;
+      const int s = i % NG;
+      const float ar = a_next, sh = sh_next;
+      if (i + 1 < cnt) {  // prefetch the next row's scalars so their latency is off the critical path
+        a_next = p.a[row + NC];
+        if (!UNI) sh_next = p.fs[row + NC];
+      }
+      mbar_wait(smem_u32(full + s), (uint32_t)((i / NG) & 1));
+      float t[CPT];
+      const float* srow = stage + (size_t)s * W + tid * 4;
+      auto quad = [&](int c) {
+        const float4 v = *reinterpret_cast<const float4*>(srow + c * (kLiteThreads * 4));
+        if (UNI) {
+          t[c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0]));
+          t[c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1]));
+          t[c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2]));
+          t[c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3]));
+        } else {
+          t[c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + sh));
+          t[c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + sh));
+          t[c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + sh));
+          t[c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + sh));
+        }
+      };
+#pragma unroll
+      for (int c = 0; c < NCH - 1; ++c) quad(c);
+      if (last_any) {
+        quad(NCH - 1);
+        if (!last_ok) t[CPT - 4] = t[CPT - 3] = t[CPT - 2] = t[CPT - 1] = 0.f;
+      } else {
+        t[CPT - 4] = t[CPT - 3] = t[CPT - 2] = t[CPT - 1] = 0.f;
+      }
+      float ps = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) ps += (t[c * 4 + 0] + t[c * 4 + 1]) + (t[c * 4 + 2] + t[c * 4 + 3]);
+      ps = warp_sum(ps);
+      const int par = i & 1;
+      if (lane == 0) red[par * kLiteWarps + warp] = ps;
+      __syncthreads();  // ring stage drained by every warp; red[par] complete
+      const int xb = i % kXBuf;
+      if (tid == 0) {
+        if (i + NG < cnt) {
+          fence_proxy_async();
+          issue(i + NG);
+        }
+        mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
+      }
+      if (tid < Q) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLiteWarps; ++w) v += red[par * kLiteWarps + w];
+        st_async_f32(map_to_cta(smem_u32(xch + xb * kMaxCluster + q), (uint32_t)tid), v,
+                     map_to_cta(smem_u32(xbar + xb), (uint32_t)tid));
+      }
+      mbar_wait(smem_u32(xbar + xb), (uint32_t)((i / kXBuf) & 1));
+      float rt = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < kMaxCluster; ++qq)
+        if (qq < Q) rt += xch[xb * kMaxCluster + qq];
+      const bool live = ar > 0.f;
+      const float w = live ? __fdividef(ar, rt) : 0.f;
+      if (q == 0 && tid == 0) {
+        const float fnew = live ? sh + (log2f(ar) - log2f(rt)) : -INFINITY;
+        p.fs[row] = fnew;
+        if (live) {
+          if (fabsf(fnew) < INFINITY) {
+            f_lo = fminf(f_lo, fnew);
+            f_hi = fmaxf(f_hi, fnew);
+          } else {
+            atomicExch(&st->bad, 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[c], w, acc[c]);
+    }
+  };
+  if (uniform)
+    row_loop(std::true_type{});
+  else
+    row_loop(std::false_type{});
+
+  if (q == 0 && tid == 0 && f_lo <= f_hi) {
+    atomic_min_float(&st->fs_lo[(it0 + 1) & 1], f_lo);
+    atomic_max_float(&st->fs_hi[(it0 + 1) & 1], f_hi);
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * (kLiteThreads * 4) + tid * 4;
+    if (col < mvalid)
+      *reinterpret_cast<float4*>(p.part + (size_t)cid * p.stride + col0 + col) =
+          make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
+  }
+  cluster_arrive();
   cluster_wait();
 }
 
@@ -988,6 +1196,105 @@ static int pick_fused(int n, int m, FusedCfg* out) {
   return 0;
 }
 
+// ---- lite variant host side ---------------------------------------------------------------------
+constexpr int kLiteMaxNch = 8;
+
+template <int NCH>
+static cudaError_t lite_set_attr() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(sweep_lite_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kLiteSmemMax);
+  if (e == cudaSuccess) done = true;
+  return e;
+}
+
+template <int NCH>
+static cudaError_t lite_launch_or_query(const SweepArgs* a, int Q, int NC, size_t smem, cudaStream_t s, int* nc_out) {
+  cudaError_t e = lite_set_attr<NCH>();
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((a ? NC : 2 * 148) * Q));
+  cfg.blockDim = dim3(kLiteThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)Q;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (!a) return cudaOccupancyMaxActiveClusters(nc_out, sweep_lite_kernel<NCH>, &cfg);
+  return cudaLaunchKernelEx(&cfg, sweep_lite_kernel<NCH>, *a);
+}
+
+static cudaError_t lite_dispatch(int nch, const SweepArgs* a, int Q, int NC, size_t smem, cudaStream_t s, int* nc_out) {
+  switch (nch) {
+    case 1: return lite_launch_or_query<1>(a, Q, NC, smem, s, nc_out);
+    case 2: return lite_launch_or_query<2>(a, Q, NC, smem, s, nc_out);
+    case 3: return lite_launch_or_query<3>(a, Q, NC, smem, s, nc_out);
+    case 4: return lite_launch_or_query<4>(a, Q, NC, smem, s, nc_out);
+    case 5: return lite_launch_or_query<5>(a, Q, NC, smem, s, nc_out);
+    case 6: return lite_launch_or_query<6>(a, Q, NC, smem, s, nc_out);
+    case 7: return lite_launch_or_query<7>(a, Q, NC, smem, s, nc_out);
+    default: return lite_launch_or_query<8>(a, Q, NC, smem, s, nc_out);
+  }
+}
+
+// (Q, NCH) for the lite kernel: most co-resident CTAs first, then the smaller cluster
+static int pick_lite(int n, int m, FusedCfg* out) {
+  static int cache_nc[kMaxCluster + 1][kLiteMaxNch + 1];
+  const size_t fixed = 8 * 8 + kXBuf * 8 + (2 * kLiteWarps + kXBuf * kMaxCluster) * 4 + 128;
+  int bestQ = 0, bestN = 0, bestCtas = -1, bestNC = 0;
+  const char* eq = getenv("B200OT_FUSED_Q");
+  const int forceQ = eq ? atoi(eq) : 0;
+  for (int Q = 1; Q <= kMaxCluster; ++Q) {
+    if (forceQ && Q != forceQ) continue;
+    const int wq = fused_wq(m, Q);
+    const int N = (wq + 1023) / 1024;
+    if (N > kLiteMaxNch) continue;
+    if (m - (Q - 1) * wq <= 1024 * (N - 1)) continue;
+    if (cache_nc[Q][N] == 0) {
+      int v = 0;
+      cudaError_t e = lite_dispatch(N, nullptr, Q, 0, kLiteSmemMax, nullptr, &v);
+      if (e != cudaSuccess) {
+        set_last_cuda_error(e, "lite occupancy query");
+        (void)cudaGetLastError();
+        return B200OT_E_LAUNCH;
+      }
+      cache_nc[Q][N] = v > 0 ? v : -1;
+    }
+    const int nc = cache_nc[Q][N];
+    if (nc < 1) continue;
+    if (nc * Q > bestCtas) {
+      bestCtas = nc * Q;
+      bestQ = Q;
+      bestN = N;
+      bestNC = nc;
+    }
+  }
+  if (!bestQ) return B200OT_E_UNSUPPORTED;
+  const size_t stage = (size_t)kLiteThreads * 4 * bestN * 4;
+  int NG = (int)((kLiteSmemMax - fixed) / stage);
+  NG = NG > 8 ? 8 : NG;
+  if (NG < 2) return B200OT_E_UNSUPPORTED;
+  const char* eg = getenv("B200OT_FUSED_NG");
+  if (eg && atoi(eg) >= 2 && atoi(eg) <= NG) NG = atoi(eg);
+  int NC = bestNC;
+  if (NC > n) NC = n;
+  if (NC > kNpCap) NC = kNpCap;
+  out->Q = bestQ;
+  out->NCH = bestN;
+  out->R = 1;
+  out->NG = NG;
+  out->NC = NC;
+  out->smem = (size_t)NG * stage + fixed;
+  out->wq = fused_wq(m, bestQ);
+  return 0;
+}
+
 static bool fused_eligible(const float* C, int ldc, int n, int m) {
   return (ldc % 4 == 0) && (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && m >= 4 &&
          n >= 1 && (long long)m <= (long long)kMaxCluster * kMaxNch * 2048;
@@ -998,8 +1305,16 @@ static bool vec_eligible(const float* C, int ldc, int m) {
 
 static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtrs& w, int* np_out,
                               cudaStream_t s) {
+  // B200OT_FUSED_VARIANT: "lite" = 256-thread CTAs, two per SM; "pipe" = 512-thread software-pipelined
+  static int variant = -1;
+  if (variant < 0) {
+    const char* ev = getenv("B200OT_FUSED_VARIANT");
+    variant = (ev && !strcmp(ev, "pipe")) ? 0 : 1;  // default: lite (measured 1.5x faster at 65536^2)
+  }
+  const bool lite = variant == 1;
   FusedCfg cfg;
-  int rc = pick_fused(n, m, &cfg);
+  int rc = lite ? pick_lite(n, m, &cfg) : pick_fused(n, m, &cfg);
+  if (rc == B200OT_E_UNSUPPORTED && lite) rc = pick_fused(n, m, &cfg);
   if (rc) return rc;
   SweepArgs a;
   a.C = C;
@@ -1021,9 +1336,13 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
   const char* em = getenv("B200OT_FUSED_MODE");
   a.mode = em ? atoi(em) : 0;
   cudaError_t e = cudaSuccess;
+  if (lite && cfg.R == 1 && cfg.smem <= kLiteSmemMax && cfg.NCH <= kLiteMaxNch && cfg.wq <= 1024 * cfg.NCH) {
+    e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
+  } else {
 #define B200OT_L(NCH_, R_) e = launch_fused<NCH_, R_>(a, cfg.Q, cfg.NC, cfg.smem, s)
-  B200OT_DISPATCH_NCH(cfg.NCH, B200OT_L)
+    B200OT_DISPATCH_NCH(cfg.NCH, B200OT_L)
 #undef B200OT_L
+  }
   if (e != cudaSuccess) {
     set_last_cuda_error(e, "sweep_fused launch");
     (void)cudaGetLastError();  // do not leave a stale error for the next launch check
@@ -1193,6 +1512,30 @@ int b200ot_sinkhorn_finish(int n, int m, void* ws, float* f, float* g, b200ot_re
   export_kernel<<<(mx + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w.st, n, m, w.fs, w.gs0, w.gs1, f, g, result, w.err_hist, err_hist, err_hist ? err_hist_cap : 0);
   B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_describe(int n, int m, char* buf, int buf_len) {
+  if (!buf || buf_len < 8 || n <= 0 || m <= 0) return B200OT_E_INVALID;
+  if (m % 4 != 0 || (long long)m > (long long)kMaxCluster * kMaxNch * 2048) {
+    snprintf(buf, buf_len, "robust two-sweep kernels (m=%d is not eligible for the single-sweep kernel)", m);
+    return 0;
+  }
+  FusedCfg cfg;
+  const char* ev = getenv("B200OT_FUSED_VARIANT");
+  bool lite = !(ev && !strcmp(ev, "pipe"));
+  int rc = lite ? pick_lite(n, m, &cfg) : pick_fused(n, m, &cfg);
+  if (rc == B200OT_E_UNSUPPORTED && lite) {
+    lite = false;
+    rc = pick_fused(n, m, &cfg);
+  }
+  if (rc) return rc;
+  snprintf(buf, buf_len,
+           "%s: cluster=%d CTAs x %d threads, %d clusters (%d CTAs), %d cols/CTA, %d cols/thread, "
+           "%d row(s)/group, TMA ring %d x %zu B, smem %zu B/CTA",
+           lite ? "sweep_lite_kernel (2 CTAs/SM)" : "sweep_fused_kernel (pipelined, 1 CTA/SM)", cfg.Q,
+           lite ? kLiteThreads : kSweepThreads, cfg.NC, cfg.NC * cfg.Q, cfg.wq, 4 * cfg.NCH, cfg.R, cfg.NG,
+           (size_t)cfg.R * (lite ? kLiteThreads : kSweepThreads) * 4 * cfg.NCH * 4, cfg.smem);
   return 0;
 }
 

@@ -16,6 +16,8 @@ from oracle import ot_oracle as orc
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT_DIR, "ot-based-heterogeneous-multi-modal-fusion-embedding-for-ad-analysis-_b200")
 
 
 def _load(golden_dir, name):
@@ -155,6 +157,7 @@ def test_c3_cohort_4096_matches_reference(cuda_dev, golden_dir):
 @pytest.mark.parametrize("n,m", [(64, 64), (200, 2048), (37, 4100), (1000, 8192), (513, 12288)])
 @pytest.mark.parametrize("path", ["fused", "robust"])
 def test_paths_match_oracle(cuda_dev, n, m, path):
+    """Both single-sweep kernels (256-thread two-per-SM form by default) and the robust kernels."""
     from b200ot import ops
     rng = np.random.default_rng(n + m)
     X, Y = orc.synthetic_embeddings(n, m, 32, config_index=n % 7)
@@ -360,7 +363,7 @@ def test_full_size_marginal_properties(cuda_dev, n):
                                          err_norm="l1")
     assert info["n_iter"] == 21 and info["status"] == 0 and info["n_err"] == 3
     errs = info["errs"].cpu().numpy()
-    assert errs[1] < errs[0] and errs[2] < 1.05 * errs[1]  # the third check may sit on the fp32 floor
+    assert errs[1] < errs[0] and errs[2] < max(1.05 * errs[1], 5e-6)  # later checks sit on the fp32 floor
     ones = torch.ones((m, 1), device=cuda_dev)
     rows = ops.apply_plan(C, f, g, eps, ones).reshape(-1)
     assert float((rows * n - 1).abs().max()) < 5e-4
@@ -372,3 +375,31 @@ def test_full_size_marginal_properties(cuda_dev, n):
     f2, g2, _ = ops.sinkhorn_potentials(C, a, a, eps, max_iter=3, tol=0.0, path="robust")
     f3, g3, _ = ops.sinkhorn_potentials(C, a, a, eps, max_iter=3, tol=0.0, path="fused")
     assert float((f2 - f3).abs().max()) / eps < 2e-4 and float((g2 - g3).abs().max()) / eps < 2e-4
+
+
+def test_pipelined_variant_in_subprocess(cuda_dev):
+    """The 512-thread software-pipelined single-sweep kernel (fallback for rows wider than 65536 columns)
+    is selected per process with B200OT_FUSED_VARIANT=pipe: run it in a child and compare with the oracle."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path[:0] = [%r, %r]
+from oracle import ot_oracle as orc
+from b200ot import ops
+assert "pipelined" in ops.describe_kernel(300, 12288)
+X, Y = orc.synthetic_embeddings(300, 12288, 32, config_index=3)
+C = orc.sqeuclid_cost(X, Y); a = np.ones(300) / 300; b = np.ones(12288) / 12288
+Pref = orc.sinkhorn_log(C, a, b, 0.1, max_iter=20, tol=0.0)
+dev = torch.device("cuda", 0)
+Cd = ops.aligned_copy(torch.tensor(C, dtype=torch.float32, device=dev))
+f, g, info = ops.sinkhorn_potentials(Cd, torch.tensor(a, dtype=torch.float32, device=dev),
+                                     torch.tensor(b, dtype=torch.float32, device=dev), 0.1, max_iter=20, tol=0.0, path="fused")
+P = ops.plan(Cd, f, g, 0.1).cpu().numpy()
+rel = np.abs(P - Pref).max() / Pref.max()
+assert info["n_iter"] == 20 and rel < 1e-4, rel
+print("ok", rel)
+''' % (ROOT_DIR, PKG_DIR)
+    env = dict(os.environ, B200OT_FUSED_VARIANT="pipe")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
