@@ -201,30 +201,52 @@ __global__ void __launch_bounds__(kFinalizeThreads)
     finalize_kernel(State* st, const float* __restrict__ part_sum, const float* __restrict__ part_max,
                     int np, size_t stride, int m, const float* __restrict__ b,
                     const float* __restrict__ log2b, float* gs0, float* gs1, double* errpart,
-                    float* err_hist, int is_prologue) {
+                    float* err_hist, int is_prologue, int groups) {
   if (st->done) return;
   const int cur = st->cur;
   const float* gcur = cur ? gs1 : gs0;
   float* gnext = cur ? gs0 : gs1;
   const int norm = st->err_norm;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  // A block covers CB = 256/groups columns; thread (grp, c) folds the partial slabs p = grp, grp+groups, ...
+  // so many slabs over few columns still fill the GPU; the `groups` results are combined in fixed order.
+  const int CB = kFinalizeThreads / groups;
+  const int grp = threadIdx.x / CB, c = threadIdx.x - grp * CB;
+  const int j = blockIdx.x * CB + c;
+  __shared__ float sh_s[kFinalizeThreads], sh_m[kFinalizeThreads];
+  {
+    float acc = 0.f, M = -INFINITY;
+    if (j < m) {
+      if (part_max) {
+        for (int p = grp; p < np; p += groups) M = fmaxf(M, part_max[(size_t)p * stride + j]);
+        for (int p = grp; p < np; p += groups) {
+          const float pm = part_max[(size_t)p * stride + j];
+          if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm - M);
+        }
+      } else {
+        for (int p = grp; p < np; p += groups) acc += part_sum[(size_t)p * stride + j];
+      }
+    }
+    sh_s[threadIdx.x] = acc;
+    sh_m[threadIdx.x] = M;
+  }
+  __syncthreads();
   double e = 0.0;
   int bad = 0;
-  if (j < m) {
+  if (j < m && grp == 0) {
     float s, l2s;
     if (part_max) {
       float M = -INFINITY;
-      for (int p = 0; p < np; ++p) M = fmaxf(M, part_max[(size_t)p * stride + j]);
+      for (int g2 = 0; g2 < groups; ++g2) M = fmaxf(M, sh_m[g2 * CB + c]);
       float acc = 0.f;
-      for (int p = 0; p < np; ++p) {
-        const float pm = part_max[(size_t)p * stride + j];
-        if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm - M);
+      for (int g2 = 0; g2 < groups; ++g2) {
+        const float pm = sh_m[g2 * CB + c];
+        if (pm > -INFINITY) acc += sh_s[g2 * CB + c] * exp2f(pm - M);
       }
       l2s = M + log2f(acc);
       s = exp2f(l2s);
     } else {
       float acc = 0.f;
-      for (int p = 0; p < np; ++p) acc += part_sum[(size_t)p * stride + j];
+      for (int g2 = 0; g2 < groups; ++g2) acc += sh_s[g2 * CB + c];
       s = acc;
       l2s = log2f(acc);
     }
@@ -1386,10 +1408,13 @@ static int launch_colpass(const float* C, int ldc, int n, int m, const WsPtrs& w
 
 static int launch_finalize(int m, const WsPtrs& w, const float* psum, const float* pmax, int np,
                            size_t stride, int is_prologue, cudaStream_t s) {
-  const int grid = (m + kFinalizeThreads - 1) / kFinalizeThreads;
+  int groups = np >= 32 ? 8 : np >= 16 ? 4 : np >= 8 ? 2 : 1;
+  while (groups > 1 && (long long)(m + kFinalizeThreads / groups - 1) / (kFinalizeThreads / groups) > 4096) groups >>= 1;
+  const int cb = kFinalizeThreads / groups;
+  const int grid = (m + cb - 1) / cb;
   if (grid > 4096) return B200OT_E_UNSUPPORTED;
   finalize_kernel<<<grid, kFinalizeThreads, 0, s>>>(w.st, psum, pmax, np, stride, m, w.b, w.log2b, w.gs0,
-                                                    w.gs1, w.errpart, w.err_hist, is_prologue);
+                                                    w.gs1, w.errpart, w.err_hist, is_prologue, groups);
   B200OT_LAUNCH_OK();
   return 0;
 }

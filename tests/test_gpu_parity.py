@@ -403,3 +403,42 @@ print("ok", rel)
     env = dict(os.environ, B200OT_FUSED_VARIANT="pipe")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("n,m,shards", [(301, 2048, 2), (1000, 8192, 4)])
+def test_row_sharded_kernels_emulated_on_one_gpu(cuda_dev, n, m, shards):
+    """The row-sharded C-ABI entry points (setup / shard_prologue / shard_sweep / shard_finalize), with the
+    NCCL all-reduce replaced by a sum over shard objects living on one GPU: same plan as the unsharded oracle,
+    every shard takes the same stopping decision."""
+    from b200ot import ops, sharded
+    X, Y = orc.synthetic_embeddings(n, m, 24, config_index=9)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    eps = 0.1
+    Pref, lg = orc.sinkhorn_log(C, a, b, eps, max_iter=60, tol=1e-4, err_norm="l1", check_every=10, check_phase=0,
+                                log=True)
+    Cd = ops.aligned_copy(_dev(C, cuda_dev))
+    bd = _dev(b, cuda_dev)
+    prm = ops.make_params(eps, 60, 1e-4, 10, 0, "l1", False, "auto")
+    ks = []
+    for r in range(shards):
+        lo, hi = sharded.row_range(n, shards, r)
+        ks.append(sharded.CudaShardKernels(Cd[lo:hi], _dev(a[lo:hi], cuda_dev), bd, prm))
+    for k in ks:
+        k.setup()
+    tot = sum(k.prologue().clone() for k in ks)
+    for k in ks:
+        k.finalize(tot, True)
+    for _ in range(60):
+        tot = sum(k.sweep().clone() for k in ks)
+        for k in ks:
+            k.finalize(tot, False)
+    outs = [k.finish() for k in ks]
+    assert len({o[2]["n_iter"] for o in outs}) == 1 and outs[0][2]["n_iter"] == lg["n_iter"]
+    assert all(o[2]["converged"] == lg["converged"] for o in outs)
+    f = torch.cat([o[0] for o in outs])
+    for o in outs[1:]:
+        assert torch.equal(o[1], outs[0][1])  # g is replicated bit for bit
+    P = ops.plan(Cd, f, outs[0][1], eps).cpu().numpy()
+    assert _rel(P, Pref) < RTOL
