@@ -104,6 +104,7 @@ class ShardedSinkhorn:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.iterations_queued = 0
         self.allreduces = 0
+        self._events = []  # bounds how far the host may run ahead of the GPU (see run())
 
     def _allreduce(self, s: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
@@ -119,8 +120,17 @@ class ShardedSinkhorn:
     def run(self, iters: int):
         """Queue `iters` iterations: local sweep -> all-reduce of m column partials -> finalize.
         Asynchronous: nothing here waits for the GPU."""
-        for _ in range(int(iters)):
+        cuda = torch.cuda.is_available() and self.world > 1
+        for i in range(int(iters)):
             self.k.finalize(self._allreduce(self.k.sweep()), False)
+            # Keep at most ~64 iterations queued: with hundreds of collectives outstanding NCCL's host side
+            # starts to serialise with the device (measured: 2.7 ms instead of 1.45 ms per iteration at N=2).
+            if cuda and (self.iterations_queued + i) % 16 == 15:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._events.append(ev)
+                if len(self._events) > 4:
+                    self._events.pop(0).synchronize()
         self.iterations_queued += int(iters)
 
     def solve(self, max_iter: int, check_every: int = 10, check_phase: int = 1):
