@@ -30,6 +30,19 @@ EPS = 0.05
 D = 512
 
 
+def _traffic(kernel_desc, n_loc, m):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r01_traffic.json), when this run uses the captured configuration."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+            for rec in json.load(fh):
+                if rec["n_local"] == n_loc and rec["m"] == m and rec["kernel"] in kernel_desc:
+                    return rec["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -278,6 +291,7 @@ def run_b200(args):
     per_iter_s = ms_per_step * 1e-3 / iters
     achieved = alg_bytes / per_iter_s / 1e9
     launches_per_step = (3 + 1 + 2 * iters) if world == 1 else (1 + 3 + 3 * iters)
+    kernel_desc = ops.describe_kernel(n_loc, m)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -285,11 +299,11 @@ def run_b200(args):
         "config": {"workload": f"log-domain Sinkhorn n=m={n} d={D} eps={EPS}, {iters} iterations per solve "
                                f"(BASELINE configs[3]; single-sweep fused kernel, C resident in HBM)",
                    "n": n, "m": m, "d": D, "eps": EPS, "iterations_per_step": iters, "path": args.path,
-                   "rows_per_gpu": n_loc, "kernel": ops.describe_kernel(n_loc, m), "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                   "rows_per_gpu": n_loc, "kernel": kernel_desc, "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                    "l2": "cost matrix (%.1f GiB per GPU) is far larger than L2, no flush needed" % (alg_bytes / 2**30)},
         "hbm_gbs": achieved * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": _traffic(kernel_desc, n_loc, m), "peak_source": peak_src,
                      "note": "achieved = 4*n_local*m bytes per iteration / (step time / iterations); the step time "
                              "includes the finalize kernel and, for N>1, the NCCL all-reduce"},
         "cpu_baseline": cpu_baseline,

@@ -277,10 +277,20 @@ __global__ void __launch_bounds__(kFinalizeThreads)
     is_last = (t == (int)gridDim.x - 1);
   }
   __syncthreads();
-  if (!is_last || threadIdx.x != 0) return;
+  if (!is_last) return;
+  // last block: fold the per-block error partials with all threads (fixed assignment + fixed tree)
   __threadfence();
+  {
+    double part = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += kFinalizeThreads) part += ((volatile double*)errpart)[i];
+    part = warp_sum(part);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
   double tot = 0.0;
-  for (unsigned i = 0; i < gridDim.x; ++i) tot += ((volatile double*)errpart)[i];
+  for (int w = 0; w < kFinalizeThreads / 32; ++w) tot += sh[w];
   float err = (norm == B200OT_NORM_L2) ? (float)sqrt(tot) : (float)tot;
   st->ticket = 0;
   const int isbad = ((volatile int*)&st->bad)[0];
