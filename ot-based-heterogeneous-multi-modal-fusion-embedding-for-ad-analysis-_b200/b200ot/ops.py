@@ -245,6 +245,35 @@ class SinkhornStepper:
                                                self.path, _ws_ptr(self.ws), _stream()),
               "b200ot_sinkhorn_enqueue")
 
+    def build_graph(self, iters_per_replay: int = 10):
+        """Capture `iters_per_replay` iterations into a CUDA graph (launch-bound small problems: two kernel
+        launches per iteration become one graph replay per `iters_per_replay`).  Kernels no-op once the
+        stopping rule has fired, so replaying past convergence is harmless."""
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.reset()
+            self.enqueue(2)  # warm-up: kernel attributes and occupancy queries happen outside the capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self.enqueue(int(iters_per_replay))
+        self._graph_iters = int(iters_per_replay)
+        self.reset()
+        return self._graph
+
+    def run(self, iters: int):
+        """enqueue() through the captured graph where whole replays fit, eagerly for the remainder."""
+        g = getattr(self, "_graph", None)
+        iters = int(iters)
+        while g is not None and iters >= self._graph_iters:
+            g.replay()
+            iters -= self._graph_iters
+        if iters > 0:
+            self.enqueue(iters)
+
     def flags(self) -> dict:
         out = torch.empty(8, dtype=torch.int32, device=self.C.device)
         check(self.lib.b200ot_sinkhorn_peek(_ws_ptr(self.ws), _ptr(out), _stream()), "b200ot_sinkhorn_peek")

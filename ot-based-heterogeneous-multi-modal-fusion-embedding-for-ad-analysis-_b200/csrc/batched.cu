@@ -62,8 +62,55 @@ __global__ void __launch_bounds__(BT) sinkhorn_batched_kernel(const BatchedArgs 
         const int i = e / m, j = e - i * m;
         K[i * ldk + j] = exp(-(double)Cp[e] / p.reg);
       }
+    } else if (n <= 64 && m <= 64) {
+      // squared-Euclidean cost from the embeddings in float64, tiled through shared memory:
+      // 16 x 16 threads, each owning a 4 x 4 block (rows ty + 16 r, columns tx + 16 c) of the 64 x 64 cost
+      const float* Xp = p.X + (size_t)prob * n * p.d;
+      const float* Yp = p.Y + (size_t)prob * m * p.d;
+      float* Xs = reinterpret_cast<float*>(scratch + BT);  // [64][33]
+      float* Ys = Xs + 64 * 33;
+      const int tx = tid & 15, ty = tid >> 4;
+      double acc[4][4], xx[4], yy[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        xx[r] = yy[r] = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+      }
+      for (int kc = 0; kc < p.d; kc += 32) {
+        for (int e = tid; e < 64 * 32; e += BT) {
+          const int i = e >> 5, kk = e & 31;
+          const bool kin = kc + kk < p.d;
+          Xs[i * 33 + kk] = (i < n && kin) ? Xp[(size_t)i * p.d + kc + kk] : 0.f;
+          Ys[i * 33 + kk] = (i < m && kin) ? Yp[(size_t)i * p.d + kc + kk] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < 32; ++kk) {
+          double xv[4], yv[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            xv[r] = (double)Xs[(ty + 16 * r) * 33 + kk];
+            yv[r] = (double)Ys[(tx + 16 * r) * 33 + kk];
+            xx[r] = fma(xv[r], xv[r], xx[r]);
+            yy[r] = fma(yv[r], yv[r], yy[r]);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = fma(xv[r], yv[c], acc[r][c]);
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = ty + 16 * r, j = tx + 16 * c;
+          if (i < n && j < m) K[i * ldk + j] = exp(-((xx[r] + yy[c]) - 2.0 * acc[r][c]) / p.reg);
+        }
     } else {
-      // squared-Euclidean cost from the embeddings, accumulated in float64
+      // squared-Euclidean cost from the embeddings, accumulated in float64 (generic sizes)
       const float* Xp = p.X + (size_t)prob * n * p.d;
       const float* Yp = p.Y + (size_t)prob * m * p.d;
       for (int e = tid; e < n * m; e += BT) {
@@ -225,7 +272,8 @@ int b200ot_sinkhorn_batched(const float* C, const float* X, const float* Y, int 
   p.n_iter = n_iter;
   p.err = err;
   const int ldk = m | 1;
-  const size_t smem = ((size_t)n * ldk + 2 * (size_t)n + 3 * (size_t)m + BT) * sizeof(double);
+  const size_t smem = ((size_t)n * ldk + 2 * (size_t)n + 3 * (size_t)m + BT) * sizeof(double) +
+                      ((!C && n <= 64 && m <= 64) ? 2 * 64 * 33 * sizeof(float) : 0);
   static bool attr_set = false;
   if (!attr_set) {
     B200OT_CUDA_OK(cudaFuncSetAttribute(sinkhorn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
