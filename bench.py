@@ -200,13 +200,14 @@ def run_b200(args):
 
     prm = ops.make_params(EPS, iters, 0.0, 10, 1, "l2", False, args.path)
     kern = sharded.CudaShardKernels(Cmat, a_loc, b, prm, path=args.path)
-    solver = sharded.ShardedSinkhorn(kern)
+    comm = sharded.NcclComm() if (world > 1 and args.loop == "c") else None
+    solver = sharded.ShardedSinkhorn(kern, comm=comm)
     stepper = None
     if world == 1:
         stepper = ops.SinkhornStepper(Cmat, a_loc, b, EPS, max_iter=iters, tol=0.0, path=args.path)
         if args.graph:
             stepper.build_graph(args.graph)
-    elif args.graph:
+    elif args.graph and comm is None and args.loop == "graph":
         solver.build_graph(args.graph)
 
     def step_device():
@@ -258,7 +259,7 @@ def run_b200(args):
         xd = Xp.to(dev, non_blocking=True)
         yd = Yp.to(dev, non_blocking=True)
         ops.cost_matrix(xd, yd, out=Cmat)
-        f, g, inf = sharded.solve_sharded(Cmat, a_loc, b, EPS, max_iter=iters, tol=0.0, path=args.path)
+        f, g, inf = sharded.solve_sharded(Cmat, a_loc, b, EPS, max_iter=iters, tol=0.0, path=args.path, comm=comm)
         f.cpu(), g.cpu()
         return inf["err"]
 
@@ -288,7 +289,7 @@ def run_b200(args):
                                   f"({args.cpu_sample}/{n})^2 to the full problem"}
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            _shutdown(dist)
         return
     peak, peak_src = _peaks()
     alg_bytes = 4.0 * n_loc * m  # one fp32 read of this rank's rows of C per iteration
@@ -307,7 +308,8 @@ def run_b200(args):
                                f"(BASELINE configs[3]; single-sweep fused kernel, C resident in HBM)",
                    "n": n, "m": m, "d": D, "eps": EPS, "iterations_per_step": iters, "path": args.path,
                    "rows_per_gpu": n_loc, "kernel": kernel_desc,
-                   "launch": f"CUDA graph, {args.graph} iterations per replay" if args.graph else "eager launches", "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
+                   "launch": (f"CUDA graph, {args.graph} iterations per replay" if args.graph else "eager launches")
+                   if world == 1 else f"loop={args.loop}", "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                    "l2": "cost matrix (%.1f GiB per GPU) is far larger than L2, no flush needed" % (alg_bytes / 2**30)},
         "hbm_gbs": achieved * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -321,9 +323,21 @@ def run_b200(args):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _shutdown(dist)
+
+
+def _shutdown(dist):
+    """Leave without tearing NCCL down rank by rank (a captured graph or a second communicator can make
+    destroy_process_group block); the line is already printed and flushed."""
+    try:
+        import torch
+        torch.cuda.synchronize()
+        dist.barrier()
+    finally:
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
@@ -336,7 +350,10 @@ def main():
     ap.add_argument("--iters", type=int, default=200, help="Sinkhorn iterations per step (one solve)")
     ap.add_argument("--path", default="auto", choices=["auto", "fused", "robust"])
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--graph", type=int, default=10, help="iterations per CUDA-graph replay (0 = eager launches)")
+    ap.add_argument("--graph", type=int, default=10, help="iterations per CUDA-graph replay at N=1 (0 = eager launches)")
+    ap.add_argument("--loop", default="c", choices=["c", "python", "graph"],
+                    help="N>1: who queues the per-iteration loop (c = one C call incl. ncclAllReduce on the compute "
+                         "stream; python = torch.distributed all_reduce per iteration; graph = python loop captured)")
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--cpu-iters", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")

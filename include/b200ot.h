@@ -166,6 +166,20 @@ int b200ot_sinkhorn_shard_sweep(const float* C, int ldc, int n_local, int m, int
 int b200ot_sinkhorn_shard_finalize(int n_local, int m, void* ws, const float* s_total,
                                    int is_prologue, void* stream);
 
+/* Same loop with the all-reduce issued from C on the compute stream (NCCL is bound at run time from the
+ * libnccl.so.2 already loaded in the process; no link-time dependency).  unique_id: rank 0 creates the
+ * 128-byte id, the host broadcasts it, every rank calls nccl_init (collective).  shard_start = first g
+ * update (column sums -> all-reduce -> finalize); shard_run = `iters` x (single-sweep -> fold partials ->
+ * ncclAllReduce of m floats -> finalize), all on `stream`, CUDA-graph capturable.  comm == NULL runs the
+ * loop without the collective.  s_buf: m floats of device scratch.                              */
+int b200ot_nccl_unique_id(unsigned char* id128_host);
+int b200ot_nccl_init(const unsigned char* id128_host, int world, int rank, void** comm_out);
+int b200ot_nccl_destroy(void* comm);
+int b200ot_sinkhorn_shard_start(const float* C, int ldc, int n_local, int m, void* ws, float* s_buf,
+                                void* comm, void* stream);
+int b200ot_sinkhorn_shard_run(const float* C, int ldc, int n_local, int m, int iters, int path, void* ws,
+                              float* s_buf, void* comm, void* stream);
+
 /* ---- batched small problems (one problem per CTA, float64, kernel domain) --
  * BASELINE config 2: per-training-step minibatch OT (MRI_PET_OT_nojax.py:679-715).
  * Runs POT's sinkhorn_knopp arithmetic itself (u = 1/n start, v then u update, error every

@@ -67,6 +67,11 @@ SIGNATURES = {
     "b200ot_sinkhorn_shard_prologue": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "b200ot_sinkhorn_shard_sweep": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "b200ot_sinkhorn_shard_finalize": (_i, [_i, _i, _p, _p, _i, _p]),
+    "b200ot_nccl_unique_id": (_i, [_p]),
+    "b200ot_nccl_init": (_i, [_p, _i, _i, C.POINTER(C.c_void_p)]),
+    "b200ot_nccl_destroy": (_i, [_p]),
+    "b200ot_sinkhorn_shard_start": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
+    "b200ot_sinkhorn_shard_run": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "b200ot_sinkhorn_batched": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, C.POINTER(Params), _p, _p, _p,
                                      _p, _p, _p]),
     "b200ot_plan": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _p]),

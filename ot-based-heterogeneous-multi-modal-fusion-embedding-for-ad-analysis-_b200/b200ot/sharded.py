@@ -34,6 +34,33 @@ def row_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     return min(lo_g * 4, n), min(hi_g * 4, n)
 
 
+class NcclComm:
+    """A communicator owned by libb200ot (ncclCommInitRank through the C ABI): rank 0 creates the unique id,
+    torch.distributed broadcasts it, every rank joins.  Used so the per-iteration all-reduce can be queued
+    from C on the compute stream instead of from Python on PyTorch's NCCL stream."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        self.lib = _lib.load()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_ubyte * 128)()
+            check(self.lib.b200ot_nccl_unique_id(buf), "b200ot_nccl_unique_id")
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        idt = idt.to(dev)
+        dist.broadcast(idt, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(idt.cpu().tolist())
+        self.handle = C.c_void_p()
+        check(self.lib.b200ot_nccl_init(raw, self.world, self.rank, C.byref(self.handle)), "b200ot_nccl_init")
+
+    def close(self):
+        if self.handle:
+            self.lib.b200ot_nccl_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
 class CudaShardKernels:
     """The C-ABI implementation of the per-rank kernels (include/b200ot.h, row-sharded form)."""
 
@@ -75,6 +102,18 @@ class CudaShardKernels:
                                                       int(is_prologue), ops._stream()),
               "b200ot_sinkhorn_shard_finalize")
 
+    # -- C-driven loop: everything, including the all-reduce, is queued by one call on the compute stream
+    def start_c(self, comm: Optional["NcclComm"]):
+        check(self.lib.b200ot_sinkhorn_shard_start(ops._ptr(self.C), self.ldc, self.n, self.m, ops._ws_ptr(self.ws),
+                                                   ops._ptr(self.s), comm.handle if comm else None, ops._stream()),
+              "b200ot_sinkhorn_shard_start")
+
+    def run_c(self, iters: int, comm: Optional["NcclComm"]):
+        check(self.lib.b200ot_sinkhorn_shard_run(ops._ptr(self.C), self.ldc, self.n, self.m, int(iters), self.path,
+                                                 ops._ws_ptr(self.ws), ops._ptr(self.s),
+                                                 comm.handle if comm else None, ops._stream()),
+              "b200ot_sinkhorn_shard_run")
+
     def flags(self) -> dict:
         out = torch.empty(8, dtype=torch.int32, device=self.C.device)
         check(self.lib.b200ot_sinkhorn_peek(ops._ws_ptr(self.ws), ops._ptr(out), ops._stream()),
@@ -99,10 +138,13 @@ class CudaShardKernels:
 class ShardedSinkhorn:
     """Drives one row shard; `kernels` implements the per-rank kernel interface."""
 
-    def __init__(self, kernels, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, kernels, group: Optional[dist.ProcessGroup] = None, comm: Optional[NcclComm] = None):
         self.k = kernels
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # with a libb200ot-owned communicator the loop is driven from C (one call queues everything)
+        self.comm = comm
+        self.c_loop = comm is not None and hasattr(kernels, "run_c")
         self.iterations_queued = 0
         self.allreduces = 0
         self._events = []  # bounds how far the host may run ahead of the GPU (see run())
@@ -119,6 +161,10 @@ class ShardedSinkhorn:
     def start(self):
         """State setup + the first g update (one all-reduce)."""
         self.k.setup()
+        if self.c_loop:
+            self.k.start_c(self.comm)
+            self.allreduces += 1
+            return
         self.k.finalize(self._allreduce(self.k.prologue()), True)
 
     def build_graph(self, iters_per_replay: int = 10):
@@ -151,6 +197,20 @@ class ShardedSinkhorn:
         Asynchronous apart from a bounded run-ahead window."""
         cuda = torch.cuda.is_available() and self.world > 1
         iters = int(iters)
+        if self.c_loop:
+            done = 0
+            while done < iters:  # chunks keep the host at most two windows ahead of the device
+                step = min(self._win, iters - done)
+                self.k.run_c(step, self.comm)
+                done += step
+                ev = torch.cuda.Event()
+                ev.record()
+                self._events.append(ev)
+                if len(self._events) > 2:
+                    self._events.pop(0).synchronize()
+            self.allreduces += iters
+            self.iterations_queued += iters
+            return
         i = 0
         while i < iters:
             if self._graph is not None and iters - i >= self._graph_iters:
@@ -189,8 +249,9 @@ class ShardedSinkhorn:
 
 
 def solve_sharded(C_local, a_local, b, eps, max_iter=1000, tol=1e-9, check_every=10, check_phase=1,
-                  err_norm="l2", stop_inclusive=False, path="auto", f0=None, g0=None, group=None):
-    """One call: row-sharded log-domain Sinkhorn; returns this rank's (f_local, g, info)."""
+                  err_norm="l2", stop_inclusive=False, path="auto", f0=None, g0=None, group=None, comm=None):
+    """One call: row-sharded log-domain Sinkhorn; returns this rank's (f_local, g, info).
+    Pass a `NcclComm` to drive the loop from C (recommended at 4+ GPUs)."""
     prm = ops.make_params(eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive, path)
     k = CudaShardKernels(C_local, a_local, b, prm, path=path, f0=f0, g0=g0)
-    return ShardedSinkhorn(k, group).solve(max_iter, check_every, check_phase)
+    return ShardedSinkhorn(k, group, comm).solve(max_iter, check_every, check_phase)

@@ -461,3 +461,25 @@ def test_cuda_graph_replay_equals_eager_launches(cuda_dev):
     f1, g1, i1 = st2.finish()
     assert i0["n_iter"] == i1["n_iter"] == 37
     assert torch.equal(f0, f1) and torch.equal(g0, g1)
+
+
+def test_c_driven_shard_loop_single_shard(cuda_dev):
+    """b200ot_sinkhorn_shard_start / shard_run with comm = NULL (the loop the multi-GPU driver queues from C,
+    minus the collective) equals the ordinary solve."""
+    from b200ot import ops, sharded
+    X, Y = orc.synthetic_embeddings(500, 4096, 24, config_index=11)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(500) / 500
+    b = np.ones(4096) / 4096
+    Pref, lg = orc.sinkhorn_log(C, a, b, 0.1, max_iter=40, tol=1e-5, err_norm="l1", check_every=10, check_phase=0,
+                                log=True)
+    Cd = ops.aligned_copy(_dev(C, cuda_dev))
+    prm = ops.make_params(0.1, 40, 1e-5, 10, 0, "l1", False, "auto")
+    k = sharded.CudaShardKernels(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), prm)
+    k.setup()
+    k.start_c(None)
+    k.run_c(25, None)
+    k.run_c(25, None)  # past max_iter / convergence: no-ops
+    f, g, info = k.finish()
+    assert info["n_iter"] == lg["n_iter"] and info["converged"] == lg["converged"]
+    assert _rel(ops.plan(Cd, f, g, 0.1).cpu().numpy(), Pref) < RTOL
