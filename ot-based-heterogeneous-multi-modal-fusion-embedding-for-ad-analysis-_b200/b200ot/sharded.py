@@ -148,8 +148,9 @@ class ShardedSinkhorn:
         self.iterations_queued = 0
         self.allreduces = 0
         self._events = []  # bounds how far the host may run ahead of the GPU (see run())
-        self._win = max(1, int(os.environ.get("B200OT_SHARD_WINDOW", "8")))
+        self._win = max(1, int(os.environ.get("B200OT_SHARD_WINDOW", "10")))
         self._since_event = 0
+        self._lag = max(0, int(os.environ.get("B200OT_SHARD_LAG", "0")))  # windows the host may run ahead
         self._graph, self._graph_iters = None, 0
 
     def _allreduce(self, s: torch.Tensor) -> torch.Tensor:
@@ -206,7 +207,7 @@ class ShardedSinkhorn:
                 ev = torch.cuda.Event()
                 ev.record()
                 self._events.append(ev)
-                if len(self._events) > 2:
+                if len(self._events) > self._lag:
                     self._events.pop(0).synchronize()
             self.allreduces += iters
             self.iterations_queued += iters
@@ -228,7 +229,7 @@ class ShardedSinkhorn:
                 ev = torch.cuda.Event()
                 ev.record()
                 self._events.append(ev)
-                if len(self._events) > 1:
+                if len(self._events) > self._lag:
                     self._events.pop(0).synchronize()
         self.iterations_queued += iters
 
