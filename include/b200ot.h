@@ -96,6 +96,15 @@ const char* b200ot_last_cuda_error(void);
 size_t b200ot_cost_workspace_bytes(int n, int m, int d);
 int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, int d, int kind,
                 float* C, int ldc, void* ws, size_t ws_bytes, int terms, void* stream);
+/* The two halves of b200ot_cost for callers that keep the bf16 parts resident (the online solver re-builds
+ * row panels of C every iteration but splits X and Y once).  side = 0: rows of X (128-row tiles), 1: rows of Y
+ * (256-row tiles).  parts needs b200ot_cost_parts_bytes bytes (1024-byte aligned), norms rows (padded to the
+ * tile) floats.  cost_gemm builds n rows of C starting at 128-row tile `row_tile0` of the X parts.        */
+size_t b200ot_cost_parts_bytes(int rows, int d, int side);
+int b200ot_cost_split(const float* X, int ldx, int rows, int d, int kind, int terms, int side, void* parts,
+                      float* norms, void* stream);
+int b200ot_cost_gemm(const void* partsA, const float* normsA, int row_tile0, int n, const void* partsB,
+                     const float* normsB, int m, int d, int kind, int terms, float* C, int ldc, void* stream);
 int b200ot_cost_simt(const float* X, int ldx, const float* Y, int ldy, int n, int m, int d,
                      int kind, float* C, int ldc, float* norms, void* stream);
 
@@ -165,6 +174,15 @@ int b200ot_sinkhorn_shard_sweep(const float* C, int ldc, int n_local, int m, int
                                 float* s_local, void* stream);
 int b200ot_sinkhorn_shard_finalize(int n_local, int m, void* ws, const float* s_total,
                                    int is_prologue, void* stream);
+
+/* Row panels of ONE problem (online / C-free solver): ws describes the whole n x m problem, Cpanel holds rows
+ * [row0, row0 + rows) of the cost (rebuilt on the fly, L2-resident); the sweep updates f for those rows and adds
+ * the panel's column sums into s_accum (accumulate = 0 on the first panel of an iteration).  After the last
+ * panel: b200ot_sinkhorn_shard_finalize(n, m, ws, s_accum, is_prologue).                                */
+int b200ot_sinkhorn_panel_prologue(const float* Cpanel, int ldc, int n, int m, int row0, int rows, void* ws,
+                                   float* s_accum, int accumulate, void* stream);
+int b200ot_sinkhorn_panel_sweep(const float* Cpanel, int ldc, int n, int m, int row0, int rows, int path,
+                                void* ws, float* s_accum, int accumulate, void* stream);
 
 /* Same loop with the all-reduce issued from C on the compute stream (NCCL is bound at run time from the
  * libnccl.so.2 already loaded in the process; no link-time dependency).  unique_id: rank 0 creates the

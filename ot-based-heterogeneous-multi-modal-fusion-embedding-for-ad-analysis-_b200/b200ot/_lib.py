@@ -49,6 +49,9 @@ SIGNATURES = {
     "b200ot_last_cuda_error": (C.c_char_p, []),
     "b200ot_cost_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200ot_cost": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _sz, _i, _p]),
+    "b200ot_cost_parts_bytes": (_sz, [_i, _i, _i]),
+    "b200ot_cost_split": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "b200ot_cost_gemm": (_i, [_p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
     "b200ot_cost_simt": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
     "b200ot_fot_cost": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p]),
     "b200ot_matrix_max": (_i, [_p, _i, _i, _i, _p, _p]),
@@ -67,6 +70,8 @@ SIGNATURES = {
     "b200ot_sinkhorn_shard_prologue": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "b200ot_sinkhorn_shard_sweep": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
     "b200ot_sinkhorn_shard_finalize": (_i, [_i, _i, _p, _p, _i, _p]),
+    "b200ot_sinkhorn_panel_prologue": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
+    "b200ot_sinkhorn_panel_sweep": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p]),
     "b200ot_nccl_unique_id": (_i, [_p]),
     "b200ot_nccl_init": (_i, [_p, _i, _i, C.POINTER(C.c_void_p)]),
     "b200ot_nccl_destroy": (_i, [_p]),

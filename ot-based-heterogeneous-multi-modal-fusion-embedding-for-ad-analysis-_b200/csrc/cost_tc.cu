@@ -405,4 +405,65 @@ int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, 
   return 0;
 }
 
+// ---- split / gemm halves of b200ot_cost, for callers that keep the bf16 parts resident (online solver) ----
+size_t b200ot_cost_parts_bytes(int rows, int d, int side) {
+  if (rows <= 0 || d <= 0) return 0;
+  const int tile = side ? TC_BN : TC_BM;
+  const size_t rows_pad = (size_t)(rows + tile - 1) / tile * tile;
+  const size_t kblocks = (size_t)(d + TC_BK - 1) / TC_BK;
+  return (rows_pad * kblocks * TC_BK * 2 * 3 + 1023) / 1024 * 1024;
+}
+
+int b200ot_cost_split(const float* X, int ldx, int rows, int d, int kind, int terms, int side, void* parts,
+                      float* norms, void* stream) {
+  if (!X || !parts || !norms || rows <= 0 || d <= 0 || ldx < d) return B200OT_E_INVALID;
+  if (terms != 1 && terms != 3 && terms != 6) return B200OT_E_INVALID;
+  if ((reinterpret_cast<uintptr_t>(parts) & 1023) != 0) return B200OT_E_INVALID;
+  const int nparts = terms == 1 ? 1 : terms == 3 ? 2 : 3;
+  const int tile = side ? TC_BN : TC_BM;
+  const int rows_pad = (rows + tile - 1) / tile * tile;
+  const int kblocks = (d + TC_BK - 1) / TC_BK;
+  split_tiles_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      X, ldx, rows, d, tile, kblocks, rows_pad, kind == B200OT_COST_COSINE ? 1 : 0, nparts,
+      static_cast<uint8_t*>(parts), norms);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+// C (n x m) from resident parts; row_tile0 selects the first 128-row tile of the A parts (n rows from there)
+int b200ot_cost_gemm(const void* partsA, const float* normsA, int row_tile0, int n, const void* partsB,
+                     const float* normsB, int m, int d, int kind, int terms, float* C, int ldc, void* stream) {
+  if (!partsA || !normsA || !partsB || !normsB || !C || n <= 0 || m <= 0 || d <= 0 || ldc < m || row_tile0 < 0)
+    return B200OT_E_INVALID;
+  if (terms != 1 && terms != 3 && terms != 6) return B200OT_E_INVALID;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200OT_CUDA_OK(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    attr_set = true;
+  }
+  const int nparts = terms == 1 ? 1 : terms == 3 ? 2 : 3;
+  const int kblocks = (d + TC_BK - 1) / TC_BK;
+  CostTcArgs a;
+  a.A = static_cast<const uint8_t*>(partsA) + (size_t)row_tile0 * nparts * kblocks * TC_A_BYTES;
+  a.B = static_cast<const uint8_t*>(partsB);
+  a.xn = normsA + (size_t)row_tile0 * TC_BM;
+  a.yn = normsB;
+  a.C = C;
+  a.ldc = ldc;
+  a.n = n;
+  a.m = m;
+  a.kblocks = kblocks;
+  a.nseg = terms;
+  a.nparts = nparts;
+  a.cosine = kind == B200OT_COST_COSINE ? 1 : 0;
+  a.tiles_m = (n + TC_BM - 1) / TC_BM;
+  a.tiles_n = (m + TC_BN - 1) / TC_BN;
+  const long long tiles = (long long)a.tiles_m * a.tiles_n;
+  int grid = sm_count();
+  if (grid > tiles) grid = (int)tiles;
+  cost_tc_kernel<<<grid, TC_THREADS, TC_SMEM, static_cast<cudaStream_t>(stream)>>>(a);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
 }  // extern "C"

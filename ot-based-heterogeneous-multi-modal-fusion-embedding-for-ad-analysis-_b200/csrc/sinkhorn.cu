@@ -852,11 +852,11 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
 // fold the per-cluster column partials of this rank into one vector (row-sharded mode)
 __global__ void reduce_parts_kernel(const State* st, const float* __restrict__ part_sum,
                                     const float* __restrict__ part_max, int np, size_t stride, int m,
-                                    float* __restrict__ s_out) {
+                                    float* __restrict__ s_out, int accumulate) {
   if (st->done) return;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
-  float acc = 0.f;
+  float acc = accumulate ? s_out[j] : 0.f;
   if (part_max) {
     for (int p = 0; p < np; ++p) {
       const float pm = part_max[(size_t)p * stride + j];
@@ -1550,6 +1550,56 @@ int b200ot_sinkhorn_finish(int n, int m, void* ws, float* f, float* g, b200ot_re
   return 0;
 }
 
+// ---- row panels of one problem (online / C-free solver) -----------------------------------------
+// The workspace describes the whole n x m problem; `Cpanel` holds rows [row0, row0 + rows) of the cost, built
+// on the fly.  The sweep updates fs[row0 ...] and adds the panel's column sums into s_accum (accumulate = 0
+// for the first panel of an iteration).  After the last panel: b200ot_sinkhorn_shard_finalize(n, m, ws, s_accum).
+static WsPtrs panel_ptrs(void* ws, int n, int m, int row0) {
+  WsPtrs w = ws_ptrs(ws, ws_layout(n, m));
+  w.fs += row0;
+  w.a += row0;
+  return w;
+}
+
+int b200ot_sinkhorn_panel_prologue(const float* Cpanel, int ldc, int n, int m, int row0, int rows, void* ws,
+                                   float* s_accum, int accumulate, void* stream) {
+  int rc = check_problem(Cpanel, ldc, rows, m, ws);
+  if (rc) return rc;
+  if (!s_accum || row0 < 0 || row0 + rows > n) return B200OT_E_INVALID;
+  const WsPtrs w = panel_ptrs(ws, n, m, row0);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int np = 0;
+  rc = launch_colpass(Cpanel, ldc, rows, m, w, &np, s);
+  if (rc) return rc;
+  reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, w.part_max, np, w.m_pad, m, s_accum, accumulate);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_panel_sweep(const float* Cpanel, int ldc, int n, int m, int row0, int rows, int path, void* ws,
+                                float* s_accum, int accumulate, void* stream) {
+  int rc = check_problem(Cpanel, ldc, rows, m, ws);
+  if (rc) return rc;
+  if (!s_accum || row0 < 0 || row0 + rows > n) return B200OT_E_INVALID;
+  const WsPtrs w = panel_ptrs(ws, n, m, row0);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  path = resolve_path(path, Cpanel, ldc, rows, m);
+  int np = 0;
+  if (path == B200OT_PATH_FUSED) {
+    rc = launch_sweep_fused(Cpanel, ldc, rows, m, w, &np, s);
+    if (rc) return rc;
+    reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, nullptr, np, w.m_pad, m, s_accum, accumulate);
+  } else {
+    rc = launch_rowpass(Cpanel, ldc, rows, m, w, s);
+    if (rc) return rc;
+    rc = launch_colpass(Cpanel, ldc, rows, m, w, &np, s);
+    if (rc) return rc;
+    reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, w.part_max, np, w.m_pad, m, s_accum, accumulate);
+  }
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
 int b200ot_sinkhorn_describe(int n, int m, char* buf, int buf_len) {
   if (!buf || buf_len < 8 || n <= 0 || m <= 0) return B200OT_E_INVALID;
   if (m % 4 != 0 || (long long)m > (long long)kMaxCluster * kMaxNch * 2048) {
@@ -1661,7 +1711,7 @@ int b200ot_sinkhorn_shard_prologue(const float* C, int ldc, int n_local, int m, 
   int np = 0;
   rc = launch_colpass(C, ldc, n_local, m, w, &np, s);
   if (rc) return rc;
-  reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, w.part_max, np, w.m_pad, m, s_local);
+  reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, w.part_max, np, w.m_pad, m, s_local, 0);
   B200OT_LAUNCH_OK();
   return 0;
 }
@@ -1678,13 +1728,13 @@ int b200ot_sinkhorn_shard_sweep(const float* C, int ldc, int n_local, int m, int
   if (path == B200OT_PATH_FUSED) {
     rc = launch_sweep_fused(C, ldc, n_local, m, w, &np, s);
     if (rc) return rc;
-    reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, nullptr, np, w.m_pad, m, s_local);
+    reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, nullptr, np, w.m_pad, m, s_local, 0);
   } else {
     rc = launch_rowpass(C, ldc, n_local, m, w, s);
     if (rc) return rc;
     rc = launch_colpass(C, ldc, n_local, m, w, &np, s);
     if (rc) return rc;
-    reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, w.part_max, np, w.m_pad, m, s_local);
+    reduce_parts_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, w.part_max, np, w.m_pad, m, s_local, 0);
   }
   B200OT_LAUNCH_OK();
   return 0;

@@ -483,3 +483,31 @@ def test_c_driven_shard_loop_single_shard(cuda_dev):
     f, g, info = k.finish()
     assert info["n_iter"] == lg["n_iter"] and info["converged"] == lg["converged"]
     assert _rel(ops.plan(Cd, f, g, 0.1).cpu().numpy(), Pref) < RTOL
+
+
+@pytest.mark.parametrize("n,m,d,panel_bytes", [(1000, 2048, 64, 1 << 20), (300, 4096, 512, 8 << 20)])
+def test_online_solver_matches_streaming_and_oracle(cuda_dev, n, m, d, panel_bytes):
+    """C-free solver: cost panels rebuilt on tcgen05 every iteration, never materialised as a whole."""
+    from b200ot import ops
+    from b200ot.online import OnlineSinkhorn, choose_path
+    X, Y = orc.synthetic_embeddings(n, m, d, config_index=12)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    eps = 0.05
+    Pref, lg = orc.sinkhorn_log(C, a, b, eps, max_iter=60, tol=1e-6, err_norm="l1", check_every=10, check_phase=0,
+                                log=True)
+    xd, yd = _dev(X, cuda_dev), _dev(Y, cuda_dev)
+    sol = OnlineSinkhorn(xd, yd, _dev(a, cuda_dev), _dev(b, cuda_dev), eps, max_iter=60, tol=1e-6, check_every=10,
+                         check_phase=0, err_norm="l1", panel_bytes=panel_bytes)
+    assert sol.panel_rows < n  # several panels per iteration
+    f, g, info = sol.solve()
+    assert info["n_iter"] == lg["n_iter"] and info["converged"] == lg["converged"] and info["status"] == 0
+    Cd = ops.cost_matrix(xd, yd, impl="tc")
+    P = ops.plan(Cd, f, g, eps).cpu().numpy()
+    assert _rel(P, Pref) < RTOL
+    fs, gs, _ = ops.sinkhorn_potentials(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), eps, max_iter=60, tol=1e-6,
+                                        check_every=10, check_phase=0, err_norm="l1")
+    assert float((fs - f).abs().max()) / eps < 1e-4 and float((gs - g).abs().max()) / eps < 1e-4
+    assert choose_path(65536, 65536, 512, 180 << 30) == "streaming"
+    assert choose_path(300000, 300000, 512, 180 << 30) == "online"
