@@ -485,7 +485,7 @@ def test_c_driven_shard_loop_single_shard(cuda_dev):
     assert _rel(ops.plan(Cd, f, g, 0.1).cpu().numpy(), Pref) < RTOL
 
 
-@pytest.mark.parametrize("n,m,d,panel_bytes", [(1000, 2048, 64, 1 << 20), (300, 4096, 512, 8 << 20)])
+@pytest.mark.parametrize("n,m,d,panel_bytes", [(1000, 2048, 64, 1 << 20), (300, 4096, 512, 2 << 20)])
 def test_online_solver_matches_streaming_and_oracle(cuda_dev, n, m, d, panel_bytes):
     """C-free solver: cost panels rebuilt on tcgen05 every iteration, never materialised as a whole."""
     from b200ot import ops
