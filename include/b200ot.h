@@ -65,13 +65,18 @@ typedef struct b200ot_params {
   int err_norm;        /* B200OT_NORM_*                                                      */
   int stop_inclusive;  /* 1: stop when err <= tol (mirror); 0: err < tol (POT, ott)          */
   int path;            /* B200OT_PATH_*                                                      */
+  int floor_patience;  /* 0 = the reference rule only.  k > 0: also stop once the error has set no   */
+                       /* new minimum for k consecutive checks while already below 1e-4 of |b| --    */
+                       /* fp32 cannot resolve POT's default stopThr = 1e-9 on small problems, and    */
+                       /* without this the solve would spin to numItermax (result status 1).         */
 } b200ot_params;
 
 /* result block written by b200ot_sinkhorn_finish (device memory, 32 bytes) */
 typedef struct b200ot_result {
   int n_iter;     /* completed (g,f) updates                                                 */
   int converged;  /* 1 if the stopping rule fired                                            */
-  int status;     /* 0 ok, B200OT_E_NUMERIC if the fast path met a non-finite / vanished sum */
+  int status;     /* 0 ok, 1 stopped at the fp32 resolution floor (floor_patience),          */
+                  /* B200OT_E_NUMERIC if the fast path met a non-finite / vanished sum       */
   int n_err;      /* number of recorded error checks                                         */
   float err;      /* last evaluated marginal error                                           */
   float reserved[3];

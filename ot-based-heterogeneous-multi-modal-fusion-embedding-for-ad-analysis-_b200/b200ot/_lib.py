@@ -25,7 +25,7 @@ COSTS = {"sqeuclidean": COST_SQEUCLIDEAN, "cosine": COST_COSINE}
 class Params(C.Structure):
     _fields_ = [("eps", C.c_float), ("max_iter", C.c_int), ("tol", C.c_float),
                 ("check_every", C.c_int), ("check_phase", C.c_int), ("err_norm", C.c_int),
-                ("stop_inclusive", C.c_int), ("path", C.c_int)]
+                ("stop_inclusive", C.c_int), ("path", C.c_int), ("floor_patience", C.c_int)]
 
 
 class Result(C.Structure):

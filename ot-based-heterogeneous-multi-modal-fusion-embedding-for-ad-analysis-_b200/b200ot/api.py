@@ -93,7 +93,7 @@ def dist(x1, x2=None, metric="sqeuclidean", *, device=None):
 
 def sinkhorn(a, b, M, reg, method="sinkhorn", numItermax=1000, stopThr=1e-9, verbose=False,
              log=False, warn=True, warmstart=None, *, check_every=10, err_norm="l2", stop_inclusive=False,
-             path="auto", device=None, **kwargs):
+             path="auto", floor_patience=3, device=None, **kwargs):
     """Drop-in for ``ot.sinkhorn`` as called at MRI_PET_OT_nojax.py:143.
 
     Same stopping rule as POT 0.9.6 ``sinkhorn_knopp`` (L2 norm of the column-marginal
@@ -101,6 +101,11 @@ def sinkhorn(a, b, M, reg, method="sinkhorn", numItermax=1000, stopThr=1e-9, ver
     (``u = 1/n, v = 1/m``), same return value ``diag(u) K diag(v)`` -- evaluated in the
     log domain in fp32, so it stays finite where the reference's ``exp(-M/reg)``
     underflows.  Empty ``a`` / ``b`` mean uniform marginals, as in POT.
+
+    ``floor_patience`` (default 3, 0 = off): fp32 cannot resolve POT's default ``stopThr = 1e-9`` on small
+    problems (the marginal error bottoms out near 1e-7 |b|); once the error has set no new minimum for that
+    many checks the solve stops instead of spinning to ``numItermax`` (``log["status"] == 1``).  Iteration
+    counts equal the float64 reference's whenever ``stopThr`` is above that floor.
     """
     if method.lower() not in ("sinkhorn", "sinkhorn_log", "sinkhorn_stabilized"):
         raise B200OTError(f"method {method!r} is not part of the reference's OT path")
@@ -117,7 +122,7 @@ def sinkhorn(a, b, M, reg, method="sinkhorn", numItermax=1000, stopThr=1e-9, ver
     f, g, info = ops.sinkhorn_potentials(Md, ad, bd, float(reg), max_iter=int(numItermax),
                                          tol=float(stopThr), check_every=check_every, check_phase=1,
                                          err_norm=err_norm, stop_inclusive=stop_inclusive, path=path, f0=f0,
-                                         g0=g0)
+                                         g0=g0, floor_patience=floor_patience)
     if warn and not info["converged"] and stopThr > 0:
         warnings.warn("Sinkhorn did not converge. You might want to increase the number of "
                       "iterations `numItermax` or the regularization parameter `reg`.")

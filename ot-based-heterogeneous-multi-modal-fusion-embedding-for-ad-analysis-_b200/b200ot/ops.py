@@ -175,16 +175,16 @@ def describe_kernel(n: int, m: int) -> str:
 
 
 def make_params(eps, max_iter, tol, check_every=10, check_phase=1, err_norm="l2",
-                stop_inclusive=False, path="auto") -> Params:
+                stop_inclusive=False, path="auto", floor_patience=0) -> Params:
     return Params(float(eps), int(max_iter), float(tol), int(check_every), int(check_phase),
-                  _lib.NORMS[err_norm], int(bool(stop_inclusive)), _lib.PATHS[path])
+                  _lib.NORMS[err_norm], int(bool(stop_inclusive)), _lib.PATHS[path], int(floor_patience))
 
 
 def sinkhorn_potentials(Cm: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float,
                         max_iter: int = 1000, tol: float = 1e-9, check_every: int = 10,
                         check_phase: int = 1, err_norm: str = "l2", stop_inclusive: bool = False,
                         path: str = "auto", f0: Optional[torch.Tensor] = None,
-                        g0: Optional[torch.Tensor] = None, err_hist_cap: int = 512):
+                        g0: Optional[torch.Tensor] = None, err_hist_cap: int = 512, floor_patience: int = 0):
     """Log-domain Sinkhorn on a cost matrix resident in HBM (b200ot_sinkhorn_solve).
 
     Returns ``(f, g, info)`` with ``P = exp((f_i + g_j - C_ij)/eps)``; ``info`` has
@@ -201,7 +201,8 @@ def sinkhorn_potentials(Cm: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps:
     f = torch.empty(n, dtype=torch.float32, device=Cm.device)
     g = torch.empty(m, dtype=torch.float32, device=Cm.device)
     errs = torch.zeros(max(1, err_hist_cap), dtype=torch.float32, device=Cm.device)
-    prm = make_params(eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive, path)
+    prm = make_params(eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive, path,
+                      floor_patience)
     res = Result()
     t0 = time.perf_counter()
     check(lib.b200ot_sinkhorn_solve(_ptr(Cm), ldc, n, m, _ptr(a), _ptr(b), _ptr(f0), _ptr(g0),

@@ -47,6 +47,9 @@ struct State {
   // range of the scaled row potentials fs; slot [it & 1] is valid when `it` iterations are complete,
   // the sweep of iteration it+1 fills slot [(it+1) & 1].  lo > hi means "unknown".
   float fs_lo[2], fs_hi[2];
+  // fp32-floor stop (b200ot_params::floor_patience)
+  int floor_patience, stall, floor_hit, pad6;
+  float best_err, b_l1, b_l2sq, pad7;
 };
 
 __device__ __forceinline__ void atomic_min_float(float* addr, float v) {
@@ -152,6 +155,8 @@ __global__ void init_state_kernel(State* st, b200ot_params prm) {
   s.err = INFINITY;
   s.initialised = 1;
   s.done = prm.max_iter <= 0 ? 1 : 0;
+  s.floor_patience = prm.floor_patience;
+  s.best_err = INFINITY;
   s.fs_lo[0] = INFINITY;
   s.fs_hi[0] = -INFINITY;
   s.fs_lo[1] = INFINITY;
@@ -173,21 +178,32 @@ __global__ void __launch_bounds__(256) init_kernel(State* st, float eps, int n, 
     wa[i] = a[i];
     if (fabsf(v) < INFINITY) lo = hi = v;
   }
+  float bl1 = 0.f, bl2 = 0.f;
   if (i < m) {
     const float g = g0 ? g0[i] * k : 0.f;
     gs0[i] = g;
     gs1[i] = g;
     wb[i] = b[i];
     log2b[i] = log2f(b[i]);
+    bl1 = fabsf(b[i]);
+    bl2 = b[i] * b[i];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if ((threadIdx.x & 31) == 0 && lo <= hi) {
-    atomic_min_float(&st->fs_lo[0], lo);
-    atomic_max_float(&st->fs_hi[0], hi);
+  bl1 = warp_sum(bl1);
+  bl2 = warp_sum(bl2);
+  if ((threadIdx.x & 31) == 0) {
+    if (lo <= hi) {
+      atomic_min_float(&st->fs_lo[0], lo);
+      atomic_max_float(&st->fs_hi[0], hi);
+    }
+    if (bl1 > 0.f) {  // |b| only scales the floor guard: summation order is irrelevant
+      atomicAdd(&st->b_l1, bl1);
+      atomicAdd(&st->b_l2sq, bl2);
+    }
   }
 }
 
@@ -321,6 +337,18 @@ __global__ void __launch_bounds__(kFinalizeThreads)
     if (ne < kErrHistCap) err_hist[ne] = err;
     st->n_err = ne + 1;
     stop = st->stop_inclusive ? (err <= st->tol) : (err < st->tol);
+    if (!stop && st->floor_patience > 0 && st->tol > 0.f) {  // tol == 0 asks for a fixed iteration count
+      // resolution floor: no new minimum for `patience` checks, and already far below |b|
+      const float scale = norm == B200OT_NORM_L1 ? st->b_l1 * 1e-4f
+                          : norm == B200OT_NORM_L2 ? sqrtf(st->b_l2sq) * 1e-4f : st->b_l2sq * 1e-8f;
+      if (err < st->best_err * 0.999f) {
+        st->best_err = err;
+        st->stall = 0;
+      } else if (++st->stall >= st->floor_patience && err <= scale) {
+        stop = true;
+        st->floor_hit = 1;
+      }
+    }
   }
   if (stop) {
     st->converged = 1;
@@ -1034,6 +1062,7 @@ __global__ void rewind_kernel(State* st, int n, int m, float* fs, float* gs0, fl
     st->converged = 0;
     st->bad = 0;
     st->ticket = 0;
+    st->stall = 0;
     st->fs_lo[0] = st->fs_lo[1] = INFINITY;  // range unknown after a rewind: per-row shift
     st->fs_hi[0] = st->fs_hi[1] = -INFINITY;
   }
@@ -1051,7 +1080,7 @@ __global__ void export_kernel(const State* st, int n, int m, const float* fs, co
   if (i == 0 && res) {
     res->n_iter = st->it;
     res->converged = st->converged;
-    res->status = st->bad ? B200OT_E_NUMERIC : 0;
+    res->status = st->bad ? B200OT_E_NUMERIC : (st->floor_hit ? 1 : 0);
     res->n_err = st->n_err;
     res->err = st->err;
     res->reserved[0] = res->reserved[1] = res->reserved[2] = 0.f;

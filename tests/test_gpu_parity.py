@@ -511,3 +511,24 @@ def test_online_solver_matches_streaming_and_oracle(cuda_dev, n, m, d, panel_byt
     assert float((fs - f).abs().max()) / eps < 1e-4 and float((gs - g).abs().max()) / eps < 1e-4
     assert choose_path(65536, 65536, 512, 180 << 30) == "streaming"
     assert choose_path(300000, 300000, 512, 180 << 30) == "online"
+
+
+def test_fp32_floor_stop_instead_of_spinning_to_numItermax(cuda_dev, golden_dir):
+    """POT's default stopThr = 1e-9 (un-squared L2) is below what fp32 can resolve at 64 x 64: with the floor
+    rule the drop-in stops a few checks after the float64 reference converged, flags it (status 1) and returns
+    the converged plan; with floor_patience = 0 it keeps the pure reference rule and runs to numItermax."""
+    import b200ot
+    g = _load(golden_dir, "c1_sample_64.npz")
+    a = np.ones(64) / 64
+    eps = float(g["eps"])
+    Pref, rl = orc.sinkhorn_knopp(a, a, M=g["C"], reg=eps, numItermax=2000, stopThr=1e-9, err_norm="l2", log=True)
+    P, lg = b200ot.sinkhorn(a, a, g["C"], eps, numItermax=2000, stopThr=1e-9, log=True, warn=False)
+    assert lg["status"] == 1 and lg["converged"]
+    assert rl["n_iter"] <= lg["n_iter"] <= rl["n_iter"] + 60
+    assert _rel(P, Pref) < RTOL
+    P0, lg0 = b200ot.sinkhorn(a, a, g["C"], eps, numItermax=300, stopThr=1e-9, log=True, warn=False, floor_patience=0)
+    assert lg0["n_iter"] == 300 and lg0["status"] == 0 and not lg0["converged"]
+    # a threshold above the floor: identical iteration count to the float64 reference, floor rule never fires
+    Pref2, rl2 = orc.sinkhorn_knopp(a, a, M=g["C"], reg=eps, numItermax=2000, stopThr=1e-6, err_norm="l2", log=True)
+    P2, lg2 = b200ot.sinkhorn(a, a, g["C"], eps, numItermax=2000, stopThr=1e-6, log=True, warn=False)
+    assert lg2["n_iter"] == rl2["n_iter"] and lg2["status"] == 0
