@@ -242,6 +242,11 @@ int b200ot_apply_plan_t(const float* C, int ldc, int n, int m, const float* f, c
 int b200ot_cosine_loss(const float* A, int lda, const float* B, int ldb, int rows, int d,
                        float* out, void* stream);
 
+/* FOSCTTM plan-quality metric (perturbot/perturbot/eval/utils.py:18-45): D is the n x n matrix of squared
+ * distances between predictions (rows) and true targets (columns), e.g. from b200ot_cost; out[i] = (rank of
+ * D[i][i] within row i, ties at their mean position) / (n - 1).                                     */
+int b200ot_foscttm(const float* D, int ldd, int n, float* out, void* stream);
+
 /* ---- attention fusion core ----------------------------------------------------
  * softmax(Q K^T / sqrt(dh)) V for the S <= 4 fusion tokens of the reference's SelfAttentionBlock
  * (MRI_PET_OT_OT_per_epoch_attn.py:523-549, tokens built at :731-738; one token in

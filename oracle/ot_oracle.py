@@ -35,7 +35,8 @@ __all__ = [
     "fot_cost_pot", "fot_cost_ott", "mdict_to_matrix", "sinkhorn_knopp",
     "sinkhorn_log", "sinkhorn_log_ott", "plan_from_potentials", "fot_bcd_ott",
     "get_feature_coupling_pot", "get_coupling_fot", "plan_guard_rownorm",
-    "apply_plan_T", "barycentric", "cosine_loss", "ot_cost", "envelope_grads",
+    "apply_plan_T", "barycentric", "cosine_loss", "ot_cost", "envelope_grads", "foscttm",
+    "group_features_by_label",
 ]
 
 
@@ -434,3 +435,30 @@ def envelope_grads(X, Y, P):
     dX = 2.0 * (P.sum(1)[:, None] * X - P @ Y)
     dY = 2.0 * (P.sum(0)[:, None] * Y - P.T @ X)
     return dX, dY
+
+
+def foscttm(Y_pred, Y_true):
+    """Fraction of samples closer than the true match (``perturbot/perturbot/eval/utils.py:18-45``): per row,
+    Euclidean distances to every true sample, sorted; rank = mean position of the true match's distance."""
+    Y_pred = np.asarray(Y_pred, dtype=np.float64)
+    Y_true = np.asarray(Y_true, dtype=np.float64)
+    n = Y_pred.shape[0]
+    fracs = []
+    for i in range(n):
+        dist = np.sqrt(np.sum(np.square(Y_pred[i, :] - Y_true), axis=1))
+        rank = np.where(np.sort(dist) == dist[i])[0].mean()
+        fracs.append(float(rank) / (n - 1))
+    return fracs
+
+
+def group_features_by_label(y, p, max_samples_per_label=None):
+    """``MRI_PET_OT_OT_per_epoch_attn.py:918-937``: rows of p bucketed by label (np.unique order), truncated."""
+    y = np.asarray(y)
+    p = np.asarray(p)
+    out = {}
+    for label in np.unique(y):
+        arr = p[y == label]
+        if max_samples_per_label is not None and max_samples_per_label > 0 and arr.shape[0] > max_samples_per_label:
+            arr = arr[:max_samples_per_label]
+        out[int(label)] = arr
+    return out

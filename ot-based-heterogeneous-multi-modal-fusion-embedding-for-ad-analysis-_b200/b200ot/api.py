@@ -323,6 +323,58 @@ def get_coupling_fot(data, Ts, eps=5e-3, *, device=None, path="auto"):
     return Tv, lg
 
 
+def group_features_by_label(y, p, max_samples_per_label=None):
+    """Drop-in for ``group_features_by_label`` (MRI_PET_OT_OT_per_epoch_attn.py:918-937): bucket the rows of
+    ``p`` by label (labels in ascending order, rows in their original order, at most ``max_samples_per_label``
+    per bucket).  With CUDA tensors the buckets are built by device indexing: no device->host copy."""
+    if isinstance(p, torch.Tensor):
+        y = torch.as_tensor(y, device=p.device)
+        out = {}
+        for label in torch.unique(y).tolist():
+            idx = torch.nonzero(y == label, as_tuple=False).reshape(-1)
+            if max_samples_per_label is not None and max_samples_per_label > 0:
+                idx = idx[:max_samples_per_label]
+            out[int(label)] = p.index_select(0, idx)
+        return out
+    y = np.asarray(y)
+    p = np.asarray(p)
+    out = {}
+    for label in np.unique(y):
+        arr = p[y == label]
+        if max_samples_per_label is not None and max_samples_per_label > 0:
+            arr = arr[:max_samples_per_label]
+        out[int(label)] = arr
+    return out
+
+
+def foscttm(Y_pred, Y_true, idx=None, *, device=None):
+    """Drop-in for ``foscttm`` (perturbot/perturbot/eval/utils.py:18-45): fraction of samples closer than the
+    true match, per sample, as a list.  The O(n^2) distance matrix and the per-row ranks are computed on the GPU
+    (the reference sorts one row at a time in Python)."""
+    if idx is not None:
+        Y_pred, Y_true = Y_pred[:, idx], Y_true[:, idx]
+    cv = _Conv(Y_pred, device)
+    out = ops.foscttm(cv.to_dev(Y_pred), cv.to_dev(Y_true))
+    return out.double().cpu().tolist()
+
+
+def get_FOSCTTM(T, Xs_true, Xt_true, use_barycenter=True, use_agg="mean", *, device=None):
+    """Drop-in for the dense-plan branch of ``get_FOSCTTM`` (perturbot/perturbot/eval/match.py:178-206):
+    barycentric projection ``(T / rowsum) @ Xt`` (``rowsum == 0 -> 1e-30``) then FOSCTTM, aggregated."""
+    cv = _Conv(Xt_true, device)
+    Xt = cv.to_dev(Xt_true)
+    if use_barycenter:
+        Td = cv.to_dev(T)
+        marg = Td.sum(dim=-1, keepdim=True)
+        marg = torch.where(marg == 0, torch.full_like(marg, 1e-30), marg)
+        pred = (Td / marg) @ Xt
+    else:
+        pred = cv.to_dev(Xs_true)
+    vals = ops.foscttm(pred.contiguous(), Xt).double().cpu().numpy()
+    agg = np.nanmedian if use_agg == "median" else np.nanmean
+    return vals.tolist(), float(agg(vals))
+
+
 # ---------------------------------------------------------------------------
 # north-star surface: embeddings in, plan / loss / fused embedding out
 # ---------------------------------------------------------------------------

@@ -386,3 +386,14 @@ def cosine_loss(A, B):
     check(lib.b200ot_cosine_loss(_ptr(A), lda, _ptr(B), ldb, A.shape[0], A.shape[1], _ptr(out), _stream()),
           "b200ot_cosine_loss")
     return out
+
+
+def foscttm(pred: torch.Tensor, true: torch.Tensor) -> torch.Tensor:
+    """Fraction of samples closer than the true match, per sample (b200ot_cost + b200ot_foscttm)."""
+    lib = _lib.load()
+    if pred.shape != true.shape:
+        raise B200OTError("foscttm operands must have the same shape")
+    D = cost_matrix(pred, true, impl="simt" if pred.shape[0] < 512 else "auto")
+    out = torch.empty(pred.shape[0], dtype=torch.float32, device=pred.device)
+    check(lib.b200ot_foscttm(_ptr(D), D.stride(0), pred.shape[0], _ptr(out), _stream()), "b200ot_foscttm")
+    return out

@@ -169,6 +169,29 @@ __global__ void __launch_bounds__(256) cosine_loss_kernel(const float* __restric
 }
 __global__ void set_one_kernel(float* p) { *p = 1.f; }
 
+// FOSCTTM (perturbot/perturbot/eval/utils.py:18-45): for sample i, the rank of its true match among all
+// distances d(pred_i, true_j), ties at their mean position, divided by n - 1.  D is the n x n matrix of
+// squared distances (monotone in the reference's Euclidean distances).  One warp per row.
+__global__ void __launch_bounds__(256) foscttm_kernel(const float* __restrict__ D, long long ldd, int n,
+                                                      float* __restrict__ out) {
+  const int row = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* d = D + (long long)row * ldd;
+  const float self = d[row];
+  int less = 0, equal = 0;
+  for (int j = lane; j < n; j += 32) {
+    const float v = d[j];
+    less += v < self;
+    equal += v == self;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    less += __shfl_xor_sync(0xffffffffu, less, o);
+    equal += __shfl_xor_sync(0xffffffffu, equal, o);
+  }
+  if (lane == 0) out[row] = n > 1 ? ((float)less + 0.5f * (float)(equal - 1)) / (float)(n - 1) : 0.f;
+}
+
 }  // namespace b200ot
 
 using namespace b200ot;
@@ -219,6 +242,13 @@ int b200ot_apply_plan_t(const float* C, int ldc, int n, int m, const float* f, c
   dim3 grid((du + AT_C - 1) / AT_C, (m + AT_I - 1) / AT_I);
   apply_plan_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       C, 1, ldc, m, n, g, f, kLog2e / eps, U, ldu, du, normalise, Z, ldz);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_foscttm(const float* D, int ldd, int n, float* out, void* stream) {
+  if (!D || !out || n <= 0 || ldd < n) return B200OT_E_INVALID;
+  foscttm_kernel<<<(n * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(D, ldd, n, out);
   B200OT_LAUNCH_OK();
   return 0;
 }

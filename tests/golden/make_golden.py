@@ -65,7 +65,33 @@ def extract_function(path, name, namespace):
     raise KeyError(name)
 
 
+def extras():
+    """Case 7: FOSCTTM (perturbot/perturbot/eval/utils.py:18-45, imported by file path) and
+    group_features_by_label (MRI_PET_OT_OT_per_epoch_attn.py:918-937, compiled from the AST)."""
+    spec = importlib.util.spec_from_file_location(
+        "ref_eval_utils", os.path.join(REF, "perturbot/perturbot/eval/utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    ref_group = extract_function(os.path.join(REF, "MRI_PET_OT_OT_per_epoch_attn.py"),
+                                 "group_features_by_label", {"np": np})
+    rng = np.random.default_rng(77)
+    n, d = 120, 10
+    true = rng.standard_normal((n, d))
+    pred = true + 0.7 * rng.standard_normal((n, d))
+    pred[11], true[11] = pred[4], true[4]  # an exact tie
+    fos = np.array(mod.foscttm(pred, true))
+    labels = rng.integers(0, 3, size=90)
+    feats = rng.standard_normal((90, 6)).astype(np.float32)
+    grouped = ref_group(labels, feats, max_samples_per_label=20)
+    np.savez_compressed(os.path.join(HERE, "metrics_helpers.npz"), pred=pred, true=true, foscttm=fos,
+                        labels=labels, feats=feats, keys=np.array(sorted(grouped.keys())),
+                        **{f"group{k}": v for k, v in grouped.items()})
+    print("metrics_helpers.npz written:", fos.mean(), {k: v.shape for k, v in grouped.items()})
+
+
 def main():
+    if "--extras" in sys.argv:
+        return extras()
     ref_utils = load_ref_utils()
     out = {}
 
@@ -175,6 +201,7 @@ def main():
         bary_rows=orc.barycentric(P3, Y3)[::512])
     out["c3"] = (len(lg3["err"]), len(lg3c["err"]))
     print("golden vectors written:", out)
+    extras()
 
 
 if __name__ == "__main__":

@@ -532,3 +532,31 @@ def test_fp32_floor_stop_instead_of_spinning_to_numItermax(cuda_dev, golden_dir)
     Pref2, rl2 = orc.sinkhorn_knopp(a, a, M=g["C"], reg=eps, numItermax=2000, stopThr=1e-6, err_norm="l2", log=True)
     P2, lg2 = b200ot.sinkhorn(a, a, g["C"], eps, numItermax=2000, stopThr=1e-6, log=True, warn=False)
     assert lg2["n_iter"] == rl2["n_iter"] and lg2["status"] == 0
+
+
+def test_foscttm_and_label_grouping(cuda_dev):
+    """Plan-quality metric on device (perturbot/perturbot/eval/utils.py:18-45) and the label bucketing of the
+    per-epoch coupling (MRI_PET_OT_OT_per_epoch_attn.py:918-937) on device tensors."""
+    import b200ot
+    rng = np.random.default_rng(21)
+    n, d = 300, 24
+    true = rng.standard_normal((n, d))
+    pred = true + 0.8 * rng.standard_normal((n, d))
+    pred[7] = pred[3]          # exact tie handling
+    true[7] = true[3]
+    ref = np.array(orc.foscttm(pred, true))
+    got = np.array(b200ot.foscttm(pred.astype(np.float32), true.astype(np.float32)))
+    assert np.abs(got - ref).max() <= 1.0 / (n - 1) + 1e-9  # at most one near-tie flips between fp32 and fp64
+    assert abs(got.mean() - ref.mean()) < 2e-4
+    P = np.abs(rng.standard_normal((n, n)))
+    P[5] = 0.0
+    vals, agg = b200ot.get_FOSCTTM(P, pred, true)
+    refv = orc.foscttm(orc.barycentric(P, true), true)
+    assert abs(agg - float(np.mean(refv))) < 2e-3
+    labels = rng.integers(0, 3, size=n)
+    feats = rng.standard_normal((n, 8)).astype(np.float32)
+    ref_g = orc.group_features_by_label(labels, feats, max_samples_per_label=64)
+    dev_g = b200ot.group_features_by_label(torch.tensor(labels, device=cuda_dev), torch.tensor(feats, device=cuda_dev), 64)
+    assert list(dev_g.keys()) == list(ref_g.keys())
+    for k in ref_g:
+        assert dev_g[k].is_cuda and np.array_equal(dev_g[k].cpu().numpy(), ref_g[k])

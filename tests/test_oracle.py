@@ -150,3 +150,13 @@ def test_envelope_grads_match_autograd():
     dX, dY = orc.envelope_grads(X, Y, P)
     np.testing.assert_allclose(dX, Xt.grad.numpy(), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(dY, Yt.grad.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_foscttm_and_grouping_match_reference(golden_dir):
+    """oracle.foscttm / group_features_by_label against outputs of the reference's own functions."""
+    g = _load(golden_dir, "metrics_helpers.npz")
+    np.testing.assert_allclose(orc.foscttm(g["pred"], g["true"]), g["foscttm"], rtol=0, atol=1e-15)
+    grouped = orc.group_features_by_label(g["labels"], g["feats"], max_samples_per_label=20)
+    assert sorted(grouped.keys()) == list(g["keys"])
+    for k in grouped:
+        assert np.array_equal(grouped[k], g[f"group{k}"])
