@@ -29,113 +29,9 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "solver_state.cuh"
 
 namespace b200ot {
-
-constexpr int kErrHistCap = 4096;
-constexpr int kNpCap = 160;  // max partial slabs (>= clusters of the fused sweep, row splits of the robust one)
-constexpr int kFinalizeThreads = 256;
-
-struct State {
-  int it, done, converged, cur;
-  int bad, n_err, ticket, initialised;
-  float err, kscale, eps, tol;
-  int max_iter, check_every, check_phase, err_norm;
-  int stop_inclusive, path, snap_it, snap_cur;
-  int snap_n_err, pad0, pad1, pad2;
-  float snap_err, pad3, pad4, pad5;
-  // range of the scaled row potentials fs; slot [it & 1] is valid when `it` iterations are complete,
-  // the sweep of iteration it+1 fills slot [(it+1) & 1].  lo > hi means "unknown".
-  float fs_lo[2], fs_hi[2];
-  // fp32-floor stop (b200ot_params::floor_patience)
-  int floor_patience, stall, floor_hit, pad6;
-  float best_err, b_l1, b_l2sq, pad7;
-};
-
-__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *a;
-  while (__int_as_float(old) > v) {
-    const int prev = atomicCAS(a, old, __float_as_int(v));
-    if (prev == old) break;
-    old = prev;
-  }
-}
-__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  int* a = reinterpret_cast<int*>(addr);
-  int old = *a;
-  while (__int_as_float(old) < v) {
-    const int prev = atomicCAS(a, old, __float_as_int(v));
-    if (prev == old) break;
-    old = prev;
-  }
-}
-static_assert(sizeof(State) <= 256, "state block");
-
-struct WsLayout {
-  size_t state, err_hist, errpart, fs, gs0, gs1, a, b, log2b, snap_fs, snap_gs, part_sum, part_max,
-      total;
-  size_t m_pad, n_pad;
-};
-
-static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-static WsLayout ws_layout(int n, int m) {
-  WsLayout L;
-  L.m_pad = align_up((size_t)m, 64);
-  L.n_pad = align_up((size_t)n, 64);
-  size_t off = 0;
-  L.state = off;
-  off += 256;
-  L.err_hist = off;
-  off += kErrHistCap * sizeof(float);
-  L.errpart = off;
-  off += 4096 * sizeof(double);
-  auto vec = [&](size_t elems) {
-    size_t o = off;
-    off += align_up(elems * sizeof(float), 256);
-    return o;
-  };
-  L.fs = vec(L.n_pad);
-  L.gs0 = vec(L.m_pad);
-  L.gs1 = vec(L.m_pad);
-  L.a = vec(L.n_pad);
-  L.b = vec(L.m_pad);
-  L.log2b = vec(L.m_pad);
-  L.snap_fs = vec(L.n_pad);
-  L.snap_gs = vec(L.m_pad);
-  L.part_sum = vec((size_t)kNpCap * L.m_pad);
-  L.part_max = vec((size_t)kNpCap * L.m_pad);
-  L.total = off;
-  return L;
-}
-
-struct WsPtrs {
-  State* st;
-  float* err_hist;
-  double* errpart;
-  float *fs, *gs0, *gs1, *a, *b, *log2b, *snap_fs, *snap_gs, *part_sum, *part_max;
-  size_t m_pad;
-};
-static WsPtrs ws_ptrs(void* ws, const WsLayout& L) {
-  char* p = static_cast<char*>(ws);
-  WsPtrs w;
-  w.st = reinterpret_cast<State*>(p + L.state);
-  w.err_hist = reinterpret_cast<float*>(p + L.err_hist);
-  w.errpart = reinterpret_cast<double*>(p + L.errpart);
-  w.fs = reinterpret_cast<float*>(p + L.fs);
-  w.gs0 = reinterpret_cast<float*>(p + L.gs0);
-  w.gs1 = reinterpret_cast<float*>(p + L.gs1);
-  w.a = reinterpret_cast<float*>(p + L.a);
-  w.b = reinterpret_cast<float*>(p + L.b);
-  w.log2b = reinterpret_cast<float*>(p + L.log2b);
-  w.snap_fs = reinterpret_cast<float*>(p + L.snap_fs);
-  w.snap_gs = reinterpret_cast<float*>(p + L.snap_gs);
-  w.part_sum = reinterpret_cast<float*>(p + L.part_sum);
-  w.part_max = reinterpret_cast<float*>(p + L.part_max);
-  w.m_pad = L.m_pad;
-  return w;
-}
 
 // =============================================================================
 // state / vector initialisation
@@ -269,7 +165,7 @@ __global__ void __launch_bounds__(kFinalizeThreads)
     const float bj = b[j];
     const double d = (double)s - (double)bj;
     e = (norm == B200OT_NORM_L1) ? fabs(d) : d * d;
-    const float gn = gcur[j] + (log2b[j] - l2s);
+    const float gn = bj > 0.f ? gcur[j] + (log2b[j] - l2s) : -INFINITY;  // b_j = 0: no mass, v_j = 0
     gnext[j] = gn;
     if (bj > 0.f && !(fabsf(gn) < INFINITY)) bad = 1;
   }
@@ -318,47 +214,9 @@ __global__ void __launch_bounds__(kFinalizeThreads)
     st->cur = cur ^ 1;
     return;
   }
-  const int it = st->it + 1;
-  st->it = it;
-  // fs range bookkeeping: the sweep that just ran filled slot [it & 1] (the two-sweep path does not
-  // track it: mark unknown); open the other slot for the next sweep
-  if (part_max) {
-    st->fs_lo[it & 1] = INFINITY;
-    st->fs_hi[it & 1] = -INFINITY;
-  }
-  st->fs_lo[(it + 1) & 1] = INFINITY;
-  st->fs_hi[(it + 1) & 1] = -INFINITY;
-  const int ce = st->check_every;
-  const bool check = (it % ce) == (st->check_phase % ce);
-  bool stop = false;
-  if (check) {
-    st->err = err;
-    const int ne = st->n_err;
-    if (ne < kErrHistCap) err_hist[ne] = err;
-    st->n_err = ne + 1;
-    stop = st->stop_inclusive ? (err <= st->tol) : (err < st->tol);
-    if (!stop && st->floor_patience > 0 && st->tol > 0.f) {  // tol == 0 asks for a fixed iteration count
-      // resolution floor: no new minimum for `patience` checks, and already far below |b|
-      const float scale = norm == B200OT_NORM_L1 ? st->b_l1 * 1e-4f
-                          : norm == B200OT_NORM_L2 ? sqrtf(st->b_l2sq) * 1e-4f : st->b_l2sq * 1e-8f;
-      if (err < st->best_err * 0.999f) {
-        st->best_err = err;
-        st->stall = 0;
-      } else if (++st->stall >= st->floor_patience && err <= scale) {
-        stop = true;
-        st->floor_hit = 1;
-      }
-    }
-  }
-  if (stop) {
-    st->converged = 1;
-    st->done = 1;
-  } else if (it >= st->max_iter) {
-    if (!check) st->err = err;
-    st->done = 1;
-  } else {
-    st->cur = cur ^ 1;
-  }
+  State ls = *st;
+  advance_state(ls, err, part_max != nullptr, err_hist);
+  *st = ls;
 }
 
 // =============================================================================
@@ -1549,6 +1407,11 @@ int b200ot_sinkhorn_enqueue(const float* C, int ldc, int n, int m, int iters, in
   path = resolve_path(path, C, ldc, n, m);
   rc = b200ot_sinkhorn_snapshot(n, m, ws, stream);
   if (rc) return rc;
+  if (path == B200OT_PATH_FUSED && iters > 0) {
+    // short iterations: the whole chunk as one persistent launch (resident.cu)
+    rc = resident_try_enqueue(C, ldc, n, m, iters, w, s);
+    if (rc <= 0) return rc;
+  }
   for (int i = 0; i < iters; ++i) {
     int np = 0;
     if (path == B200OT_PATH_FUSED) {
@@ -1635,6 +1498,7 @@ int b200ot_sinkhorn_describe(int n, int m, char* buf, int buf_len) {
     snprintf(buf, buf_len, "robust two-sweep kernels (m=%d is not eligible for the single-sweep kernel)", m);
     return 0;
   }
+  if (resident_describe(n, m, buf, buf_len)) return 0;
   FusedCfg cfg;
   const char* ev = getenv("B200OT_FUSED_VARIANT");
   bool lite = !(ev && !strcmp(ev, "pipe"));
@@ -1688,6 +1552,8 @@ int b200ot_sinkhorn_solve(const float* C, int ldc, int n, int m, const float* a,
     if (it_enq < prm->max_iter) {
       len = (((phase - it_enq - 1) % ce) + ce) % ce + 1;
       if (len > prm->max_iter - it_enq) len = prm->max_iter - it_enq;
+      // the resident kernel applies the stopping rule itself: one launch runs to convergence or max_iter
+      if (path == B200OT_PATH_FUSED && resident_applicable(n, m)) len = prm->max_iter - it_enq;
       rc = b200ot_sinkhorn_enqueue(C, ldc, n, m, len, path, ws, stream);
       if (rc) return rc;
       it_enq += len;

@@ -170,8 +170,12 @@ def test_paths_match_oracle(cuda_dev, n, m, path):
     Pref, lg = orc.sinkhorn_log(C, a, b, eps, max_iter=25, tol=0.0, err_norm="l1", check_every=5,
                                 check_phase=0, log=True)
     Cd = ops.aligned_copy(_dev(C, cuda_dev))
-    f, g, info = ops.sinkhorn_potentials(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), eps, max_iter=25, tol=0.0,
-                                         check_every=5, check_phase=0, err_norm="l1", path=path)
+    os.environ["B200OT_RESIDENT"] = "0"  # the launch-per-sweep kernels; tests/test_gpu_resident.py covers the other
+    try:
+        f, g, info = ops.sinkhorn_potentials(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), eps, max_iter=25, tol=0.0,
+                                             check_every=5, check_phase=0, err_norm="l1", path=path)
+    finally:
+        del os.environ["B200OT_RESIDENT"]
     assert info["n_iter"] == 25 and info["status"] == 0
     P = ops.plan(Cd, f, g, eps).cpu().numpy()
     assert _rel(P, Pref) < RTOL

@@ -106,6 +106,59 @@ def main():
         "fusion_head_fwd_bwd_batch32_ms": 1e3 * t_fuse,
         "note": "C = 64 MiB is L2-resident: launch- and latency-bound, not HBM-bound",
     }
+    # ---- iteration rate by size: resident (persistent cooperative) kernel vs one launch per sweep
+    sweep = {}
+    for nn in (512, 1024, 2048, 4096, 8192):
+        Xs, Ys = orc.synthetic_embeddings(nn, nn, 512, config_index=3)
+        Cs = ops.cost_matrix(torch.tensor(Xs, device=dev), torch.tensor(Ys, device=dev))
+        an = torch.full((nn,), 1.0 / nn, device=dev)
+        rec = {}
+        for label, env in (("resident", {"B200OT_RESIDENT": "1"}), ("resident_forward_only", {"B200OT_RESIDENT": "1", "B200OT_RES_SNAKE": "0"}),
+                           ("per_sweep_launches", {"B200OT_RESIDENT": "0"})):
+            if label == "resident_forward_only" and nn < 4096:
+                continue
+            os.environ.update(env)
+            try:
+                stp = ops.SinkhornStepper(Cs, an, an, eps, max_iter=200, tol=0.0)
+                if label == "per_sweep_launches":
+                    stp.build_graph(10)
+                for _ in range(3):
+                    stp.reset()
+                    stp.run(200)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 5
+                e0.record()
+                for _ in range(reps):
+                    stp.reset()
+                    stp.run(200)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                _, _, inf = stp.finish()
+                assert inf["n_iter"] == 200 and inf["status"] == 0, inf
+                rec[label] = {"ms_200it": ms, "iterations_per_s": 200e3 / ms, "us_per_iteration": 5.0 * ms,
+                              "matrix_GBps": 4.0 * nn * nn * 200 / (ms * 1e-3) / 1e9,
+                              "kernel": ops.describe_kernel(nn, nn)}
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+        sweep[f"n=m={nn}"] = rec
+    out["sinkhorn_200it_by_size"] = sweep
+    # ---- reference-native feature problems (MRI_PET_OT_nojax.py:91-145): d x d plan from 64 samples
+    fot = {}
+    for dd in (512, 2048):
+        rng = np.random.default_rng(dd)
+        Xf = rng.standard_normal((64, dd)).astype(np.float32)
+        Yf = (rng.standard_normal((64, dd)) + 0.3).astype(np.float32)
+        data = ({0: Xf}, {0: Yf})
+        Ts = {0: np.eye(64) / 64}
+        t_dev = timed(lambda: b200ot.get_feature_coupling_pot(data, Ts, eps=5e-3 if dd == 2048 else 1e-2), reps=5)
+        t0 = time.perf_counter()
+        orc.get_feature_coupling_pot(data, Ts, eps=5e-3 if dd == 2048 else 1e-2)
+        t_ref = time.perf_counter() - t0
+        fot[f"d={dd}"] = {"b200_ms_numpy_in_out": 1e3 * t_dev, "cpu_oracle_ms": 1e3 * t_ref}
+    out["feature_coupling_pot"] = fot
     print(json.dumps(out, indent=1))
 
 
