@@ -56,10 +56,12 @@ struct ResidentArgs {
 };
 
 // All CTAs are co-resident (cooperative launch).  Monotonic counter: barrier k completes at k * grid.
+// bar.sync + red.release.gpu / ld.acquire.gpu + bar.sync (the CUTLASS semaphore pattern): the release is
+// cumulative over the CTA's writes ordered before it by the block barrier, so no extra fences (a
+// __threadfence() on each side, MEMBAR.SC.GPU, cost ~4 us per iteration when measured).
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
     unsigned v;
     const long long t0 = clock64();
@@ -68,17 +70,41 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
       if (v >= target) break;
       if (clock64() - t0 > 4000000000ll) __trap();  // a lost CTA traps instead of hanging the GPU box
     }
-    __threadfence();
   }
   __syncthreads();
 }
 
-template <int T, int NCH, int R>
+// Sum R per-lane values over the warp with (R - 1) + 5 - log2(R) shuffles instead of 5 R: each of the first
+// log2(R) butterfly steps halves the number of values a lane carries.  Returns, in every lane, the total of row
+// lane >> (5 - log2 R).  Fixed order: deterministic.
+template <int R>
+__device__ __forceinline__ float warp_sum_rows(float (&v)[R], int lane) {
+  static_assert(R == 1 || R == 2 || R == 4 || R == 8, "rows per group");
+  int off = 16;
+#pragma unroll
+  for (int h = R / 2; h >= 1; h >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float send = upper ? v[i] : v[i + h];
+      const float keep = upper ? v[i + h] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  float x = v[0];
+  for (; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+  return x;
+}
+
+template <int T, int NCH, int R, bool PIPE>
 __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
   constexpr int CPT = 4 * NCH;
   constexpr int W = T * CPT;  // floats per staged row
   constexpr int NW = T / 32;
-  static_assert(NW <= 16 && R <= 32, "second-stage reduction reads one warp partial per lane of a half warp");
+  constexpr int LPR = 32 / R;        // lanes per row in the warp-level reductions
+  constexpr int V = R * NW / 32;     // warp partials each lane folds in the second stage
+  static_assert(R * NW >= 32 && (R * NW) % 32 == 0 && V <= 4, "second-stage layout");
   extern __shared__ __align__(128) unsigned char smem[];
 
   if (p.st->done) return;  // grid-uniform
@@ -99,8 +125,8 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
   q += kResMaxStages * 4;
   int* bad_sm = reinterpret_cast<int*>(q);
   q += 16;
-  float* red = reinterpret_cast<float*>(q);  // [2][R][NW]
-  q += 2 * R * NW * 4;
+  float* red = reinterpret_cast<float*>(q);  // [3][R][NW] warp partials of the row sums (3 groups in flight)
+  q += 3 * R * NW * 4;
   float* shs = reinterpret_cast<float*>(q);  // [T] slice-fold scratch
   q += T * 4;
   float* fs_sm = reinterpret_cast<float*>(q);  // [rows_cap] scaled row potentials of this CTA's rows
@@ -168,43 +194,49 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
   const bool last_ok = ((NCH - 1) * T + tid) * 4 < p.m;
   const bool last_any = __any_sync(0xffffffffu, last_ok);
 
+  float gsv[CPT], acc[CPT];
+  auto load_g = [&](const float* gsrc) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * T + tid) * 4;
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < p.m) g4 = __ldcg(reinterpret_cast<const float4*>(gsrc + col));  // written by peers: L2, not L1
+      gsv[c * 4 + 0] = g4.x;
+      gsv[c * 4 + 1] = g4.y;
+      gsv[c * 4 + 2] = g4.z;
+      gsv[c * 4 + 3] = g4.w;
+    }
+  };
+  load_g(ls->cur ? p.gs1 : p.gs0);
+  int bad = 0;  // sticky: reported with the next error fold
+
   for (int li = 0; li < p.iters; ++li) {
     if (ls->done) break;  // identical on every CTA
     const int cur = ls->cur;
     const float* gs = cur ? p.gs1 : p.gs0;
     float* gnext = cur ? p.gs0 : p.gs1;
-
-    float gsv[CPT], acc[CPT];
+    // the marginal error is only consumed on check iterations, at max_iter, and (to report a lost sum before
+    // the host looks) on the last iteration of the launch
+    const int itn = ls->it + 1;
+    const bool need_err = (itn % ls->check_every) == (ls->check_phase % ls->check_every) ||
+                          itn >= ls->max_iter || li + 1 == p.iters;
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = (c * T + tid) * 4;
-      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col < p.m) g4 = __ldcg(reinterpret_cast<const float4*>(gs + col));  // written by peers: L2, not L1
-      gsv[c * 4 + 0] = g4.x;
-      gsv[c * 4 + 1] = g4.y;
-      gsv[c * 4 + 2] = g4.z;
-      gsv[c * 4 + 3] = g4.w;
-      acc[c * 4 + 0] = acc[c * 4 + 1] = acc[c * 4 + 2] = acc[c * 4 + 3] = 0.f;
-    }
+    for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
 
     const bool fwd = !(p.snake && streaming && (li & 1));
-    for (int pos = 0; pos < cnt; ++pos) {
-      const int gi = fwd ? pos : cnt - 1 - pos;
+    auto gidx = [&](int pos) { return fwd ? pos : cnt - 1 - pos; };
+
+    // P1 of the group at sweep position pos: exponentials into registers, row sums warp -> red[pos % 3]
+    auto front = [&](int pos, float (&t)[R][CPT]) {
+      const int gi = gidx(pos);
       const int s = gi % NG;
       const int lr0 = gi * R;
-      float shv[R], arv[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        shv[r] = fs_sm[lr0 + r];
-        arv[r] = a_sm[lr0 + r];
-      }
       mbar_wait(smem_u32(full + s), (uint32_t)((fillcnt[s] - 1) & 1));
-
-      float t[R][CPT], ps[R];
+      float ps[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const float* srow = stage + ((size_t)s * R + r) * W + tid * 4;
-        const float sh = shv[r];
+        const float sh = fs_sm[lr0 + r];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           if (c < NCH - 1 || last_any) {
@@ -222,41 +254,85 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
           sum += (t[r][c * 4 + 0] + t[r][c * 4 + 1]) + (t[r][c * 4 + 2] + t[r][c * 4 + 3]);
         ps[r] = sum;
       }
-      const int par = pos & 1;
+      const float v = warp_sum_rows<R>(ps, lane);
+      if ((lane & (LPR - 1)) == 0) red[((pos % 3) * R + lane / LPR) * NW + warp] = v;
+    };
+
+    // P2: fold the warp partials, w_i = a_i / r_i, new row potential, column accumulators
+    auto back = [&](int pos, float (&t)[R][CPT]) {
+      const int lr0 = gidx(pos) * R;
+      // lane l folds V consecutive warp partials of row l / LPR, then LPR lanes are combined
+      float x = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float v = warp_sum(ps[r]);
-        if (lane == 0) red[(par * R + r) * NW + warp] = v;
-      }
-      __syncthreads();  // the stage is drained by every warp; red[par] is complete
-      if (tid == 0 && streaming) {
-        const int nxt = fwd ? gi + NG : gi - NG;
-        if (nxt >= 0 && nxt < cnt) {
-          fence_proxy_async();
-          issue(nxt);
-        }
-      }
+      for (int i = 0; i < V; ++i) x += red[(pos % 3) * R * NW + lane * V + i];
+#pragma unroll
+      for (int off = LPR / 2; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
       float wr[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float rt = (lane & 15) < NW ? red[(par * R + r) * NW + (lane & 15)] : 0.f;
-        rt += __shfl_xor_sync(0xffffffffu, rt, 8);
-        rt += __shfl_xor_sync(0xffffffffu, rt, 4);
-        rt += __shfl_xor_sync(0xffffffffu, rt, 2);
-        rt += __shfl_xor_sync(0xffffffffu, rt, 1);
-        const bool live = arv[r] > 0.f;
-        wr[r] = live ? __fdividef(arv[r], rt) : 0.f;
+        const float rt = __shfl_sync(0xffffffffu, x, r * LPR);
+        const float ar = a_sm[lr0 + r];
+        const bool live = ar > 0.f;
+        wr[r] = live ? __fdividef(ar, rt) : 0.f;
         if (tid == r && row_base + lr0 + r < p.n) {
-          const float fnew = live ? shv[r] + (log2f(arv[r]) - log2f(rt)) : -INFINITY;
+          const float fnew = live ? fs_sm[lr0 + r] + (log2f(ar) - log2f(rt)) : -INFINITY;
           fs_sm[lr0 + r] = fnew;
           p.fs[row_base + lr0 + r] = fnew;
-          if (live && !(fabsf(fnew) < INFINITY)) *bad_sm = 1;  // vanished / overflowed row sum
+          if (live && !(fabsf(fnew) < INFINITY)) bad = 1;  // vanished / overflowed row sum
         }
       }
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[r][c], wr[r], acc[c]);
+    };
+
+    // after the block barrier that follows front(pos + 1): the stages of positions <= pos + 1 are drained
+    auto refill = [&](int pos) {
+      if (tid != 0 || !streaming) return;
+      auto one = [&](int d) {
+        if (d >= cnt) return;
+        const int gi = gidx(d);
+        const int nxt = fwd ? gi + NG : gi - NG;
+        if (nxt >= 0 && nxt < cnt) {
+          fence_proxy_async();
+          issue(nxt);
+        }
+      };
+      if (PIPE) {
+        if (pos == 0) one(0);
+        one(pos + 1);
+      } else {
+        one(pos);
+      }
+    };
+
+    if (PIPE) {
+      // software pipeline over groups: the reduction chain of group pos (shuffles, block barrier, divide)
+      // overlaps the exponentials of group pos + 1.  Two register sets; red[] is triple-buffered because
+      // front(pos + 2) may run while a slower warp is still in back(pos).
+      float tA[R][CPT], tB[R][CPT];
+      front(0, tA);
+      for (int pos = 0; pos < cnt; pos += 2) {
+        if (pos + 1 < cnt) front(pos + 1, tB);
+        __syncthreads();
+        refill(pos);
+        back(pos, tA);
+        if (pos + 1 < cnt) {
+          if (pos + 2 < cnt) front(pos + 2, tA);
+          __syncthreads();
+          refill(pos + 1);
+          back(pos + 1, tB);
+        }
+      }
+    } else {
+      float tA[R][CPT];
+      for (int pos = 0; pos < cnt; ++pos) {
+        front(pos, tA);
+        __syncthreads();
+        refill(pos);
+        back(pos, tA);
+      }
     }
 
     // ---- column partials of this CTA -> global ---------------------------------------------------------
@@ -271,7 +347,6 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
 
     // ---- fold this CTA's column slice over all CTAs (fixed order), next g, error partial ----------------
     double e = 0.0;
-    int bad = 0;
     for (int jj0 = 0; jj0 < CB; jj0 += CBT) {  // uniform trip count
       const int jj = jj0 + rc;
       const int j = j0 + jj;
@@ -285,35 +360,42 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
         for (int g2 = 0; g2 < groups; ++g2) sj += shs[g2 * CBT + rc];
         const float l2s = log2f(sj);
         const float bj = p.b[j];
-        const double d = (double)sj - (double)bj;
-        e += (norm == B200OT_NORM_L1) ? fabs(d) : d * d;
+        if (need_err) {
+          const double d = (double)sj - (double)bj;
+          e += (norm == B200OT_NORM_L1) ? fabs(d) : d * d;
+        }
         const float gn = bj > 0.f ? __ldcg(gs + j) + (p.log2b[j] - l2s) : -INFINITY;  // b_j = 0: v_j = 0
         gnext[j] = gn;
         if (bj > 0.f && !(fabsf(gn) < INFINITY)) bad = 1;
       }
-      __syncthreads();
+      if (jj0 + CBT < CB) __syncthreads();  // shs is reused by the next pass
     }
-    e = warp_sum(e);
-    if (lane == 0) dred[warp] = e;
-    if (tid == 0 && *bad_sm) bad = 1;
-    const int anybad = __syncthreads_or(bad);
-    if (tid == 0) {
-      double tot = 0.0;
-      for (int w2 = 0; w2 < NW; ++w2) tot += dred[w2];
-      // a lost sum anywhere poisons the error every CTA folds next: all of them stop together
-      p.errpart[cta] = anybad ? (double)NAN : tot;
+    if (need_err) {
+      e = warp_sum(e);
+      if (lane == 0) dred[warp] = e;
+      const int anybad = __syncthreads_or(bad);
+      if (tid == 0) {
+        double tot = 0.0;
+        for (int w2 = 0; w2 < NW; ++w2) tot += dred[w2];
+        // a lost sum anywhere poisons the error every CTA folds next: all of them stop together
+        p.errpart[cta] = anybad ? (double)NAN : tot;
+      }
     }
     grid_barrier(p.gbar, (unsigned)G * (++nbar));
 
-    // ---- every CTA folds the same error partials and advances its copy of the state --------------------
-    double ep = 0.0;
-    for (int i = tid; i < G; i += T) ep += __ldcg(p.errpart + i);
-    ep = warp_sum(ep);
-    if (lane == 0) dred[warp] = ep;
-    __syncthreads();
+    // ---- next g into registers; every CTA folds the same error partials and advances its state copy ----
+    load_g(gnext);
+    if (need_err) {
+      double ep = 0.0;
+      for (int i = tid; i < G; i += T) ep += __ldcg(p.errpart + i);
+      ep = warp_sum(ep);
+      if (lane == 0) dred[warp] = ep;
+      __syncthreads();
+    }
     if (tid == 0) {
       double tot = 0.0;
-      for (int w2 = 0; w2 < NW; ++w2) tot += dred[w2];
+      if (need_err)
+        for (int w2 = 0; w2 < NW; ++w2) tot += dred[w2];
       if (!(tot == tot)) {  // fast path lost a sum: stop here, the host rewinds and replays robustly
         ls->bad = 1;
         ls->done = 1;
@@ -351,7 +433,7 @@ static bool resident_pick(int n, int m, ResCfg* c) {
   const int cnt_max = (ngroups + G - 1) / G;
   const int rows_cap = cnt_max * R;
   const size_t stage = (size_t)R * T * 4 * NCH * sizeof(float);
-  const size_t fixed = kResMaxStages * 8 + 256 + 32 * 8 + kResMaxStages * 4 + 16 + 2 * R * (T / 32) * 4 +
+  const size_t fixed = kResMaxStages * 8 + 256 + 32 * 8 + kResMaxStages * 4 + 16 + 3 * R * (T / 32) * 4 +
                        (size_t)T * 4 + 2 * (size_t)rows_cap * 4 + 128;
   if (fixed + 2 * stage > kResSmemMax) return false;
   int NG = (int)((kResSmemMax - fixed) / stage);
@@ -373,11 +455,11 @@ static bool resident_pick(int n, int m, ResCfg* c) {
   return true;
 }
 
-template <int T, int NCH, int R>
+template <int T, int NCH, int R, bool PIPE>
 static cudaError_t resident_launch(const ResidentArgs& a, int G, size_t smem, cudaStream_t s) {
   static bool attr_set = false;  // one flag per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(resident_kernel<T, NCH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(resident_kernel<T, NCH, R, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kResSmemMax);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -393,7 +475,7 @@ static cudaError_t resident_launch(const ResidentArgs& a, int G, size_t smem, cu
   at[0].val.cooperative = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, resident_kernel<T, NCH, R>, a);
+  return cudaLaunchKernelEx(&cfg, resident_kernel<T, NCH, R, PIPE>, a);
 }
 
 // auto rule: iterations short enough that launches and the finalize kernel dominate the sweep
@@ -438,18 +520,23 @@ int resident_try_enqueue(const float* C, int ldc, int n, int m, int iters, const
   a.red_groups = c.red_groups;
   B200OT_CUDA_OK(cudaMemsetAsync(w.gbar, 0, sizeof(unsigned), s));
   cudaError_t e = cudaSuccess;
+  const char* ep = getenv("B200OT_RES_PIPE");
+  const bool pipe = !(ep && ep[0] == '0');
+#define B200OT_RES(T_, N_, R_) \
+  e = pipe ? resident_launch<T_, N_, R_, true>(a, c.G, c.smem, s) : resident_launch<T_, N_, R_, false>(a, c.G, c.smem, s)
   if (c.T == 128)
-    e = resident_launch<128, 1, 8>(a, c.G, c.smem, s);
+    B200OT_RES(128, 1, 8);
   else if (c.T == 256)
-    e = resident_launch<256, 1, 8>(a, c.G, c.smem, s);
+    B200OT_RES(256, 1, 8);
   else if (c.NCH == 1)
-    e = resident_launch<512, 1, 8>(a, c.G, c.smem, s);
+    B200OT_RES(512, 1, 8);
   else if (c.NCH == 2)
-    e = resident_launch<512, 2, 4>(a, c.G, c.smem, s);
+    B200OT_RES(512, 2, 4);
   else if (c.NCH == 3)
-    e = resident_launch<512, 3, 2>(a, c.G, c.smem, s);
+    B200OT_RES(512, 3, 2);
   else
-    e = resident_launch<512, 4, 2>(a, c.G, c.smem, s);
+    B200OT_RES(512, 4, 2);
+#undef B200OT_RES
   if (e != cudaSuccess) {  // e.g. cooperative launch not possible here: use the launch-per-sweep path
     set_last_cuda_error(e, "resident_kernel launch (falling back to per-sweep launches)");
     (void)cudaGetLastError();

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
   // otherwise each row uses its own previous potential.
   const int it0 = st->it;
   const float flo = st->fs_lo[it0 & 1], fhi = st->fs_hi[it0 & 1];
-  const bool uniform = (fhi - flo) < 48.f;  // false when the range is unknown (lo > hi) or infinite
+  const bool uniform = flo <= fhi && (fhi - flo) < 48.f;  // false when the range is unknown (lo > hi) or infinite
   const float sigma = uniform ? 0.5f * (flo + fhi) : 0.f;
 
   float* stage = reinterpret_cast<float*>(smem);
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
 
   const int it0 = st->it;
   const float flo = st->fs_lo[it0 & 1], fhi = st->fs_hi[it0 & 1];
-  const bool uniform = (fhi - flo) < 48.f;
+  const bool uniform = flo <= fhi && (fhi - flo) < 48.f;
   const float sigma = uniform ? 0.5f * (flo + fhi) : 0.f;
 
   float* stage = reinterpret_cast<float*>(smem);
