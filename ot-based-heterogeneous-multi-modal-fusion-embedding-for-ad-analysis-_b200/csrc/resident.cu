@@ -29,7 +29,7 @@
 namespace b200ot {
 
 constexpr int kResMaxStages = 16;
-constexpr size_t kResSmemMax = 232448 - 1024;
+constexpr size_t kResSmemMax = 113 * 1024;  // two CTAs per SM
 
 struct ResidentArgs {
   const float* C;
@@ -42,12 +42,12 @@ struct ResidentArgs {
   const float* a;
   const float* b;
   const float* log2b;
-  float* part;  // [grid][stride] column partials
+  unsigned long long* part64;  // [grid][stride] column partials, each word = {value, sequence tag}
   size_t stride;
-  double* errpart;  // [grid]
+  unsigned long long* g64;    // [m] next scaled g, tagged
+  unsigned long long* err64;  // [grid][2] error partial (the two halves of a double), tagged
   float* err_hist;
-  unsigned* gbar;   // zeroed by the host before the launch
-  int iters;        // iteration budget of this launch (>= 1)
+  int iters;        // iteration budget of this launch (1 .. kResMaxItersPerLaunch)
   int ng;           // ring depth in row groups
   int rows_cap;     // rows per CTA, rounded up to whole groups
   int snake;        // alternate the sweep direction when the block does not fit the ring
@@ -55,23 +55,36 @@ struct ResidentArgs {
   int red_groups;   // thread groups of the slice fold (power of two)
 };
 
-// All CTAs are co-resident (cooperative launch).  Monotonic counter: barrier k completes at k * grid.
-// bar.sync + red.release.gpu / ld.acquire.gpu + bar.sync (the CUTLASS semaphore pattern): the release is
-// cumulative over the CTA's writes ordered before it by the block barrier, so no extra fences (a
-// __threadfence() on each side, MEMBAR.SC.GPU, cost ~4 us per iteration when measured).
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
-    unsigned v;
-    const long long t0 = clock64();
-    for (;;) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-      if (v >= target) break;
-      if (clock64() - t0 > 4000000000ll) __trap();  // a lost CTA traps instead of hanging the GPU box
-    }
-  }
-  __syncthreads();
+// ---- tagged words: the exchange between CTAs needs no barrier and no fence ------------------------------------
+// Every value that crosses CTAs travels in ONE naturally aligned 64-bit word {fp32 value, 32-bit sequence tag}
+// (the NCCL "LL" idea): a 64-bit access is single-copy atomic, so a consumer that sees the tag of iteration k
+// has the value of iteration k.  Consumers poll the word itself.  Tags are (launch epoch, iteration in launch);
+// the epoch lives in the state block and b200ot_sinkhorn_setup zeroes the buffers, so a stale word never matches.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack_tag(float v, unsigned tag) { return ((u64)tag << 32) | (u64)__float_as_uint(v); }
+__device__ __forceinline__ u64 pack_tag_u(unsigned v, unsigned tag) { return ((u64)tag << 32) | (u64)v; }
+__device__ __forceinline__ u64 ld_poll(const u64* p) {
+  u64 v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ld_poll2(const u64* p, u64& a, u64& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_tag(u64* p, u64 v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_tag2(u64* p, u64 a, u64 b) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ bool tag_is(u64 v, unsigned tag) { return (unsigned)(v >> 32) == tag; }
+// a producer that never shows up traps instead of hanging the GPU box
+__device__ __forceinline__ void spin_guard(long long& t0) {
+  if (t0 == 0)
+    t0 = clock64();
+  else if (clock64() - t0 > 4000000000ll)
+    __trap();
+  __nanosleep(20);
 }
 
 // Sum R per-lane values over the warp with (R - 1) + 5 - log2(R) shuffles instead of 5 R: each of the first
@@ -93,18 +106,19 @@ __device__ __forceinline__ float warp_sum_rows(float (&v)[R], int lane) {
     off >>= 1;
   }
   float x = v[0];
-  for (; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+#pragma unroll
+  for (int o = 16 / R; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
 }
 
-template <int T, int NCH, int R, bool PIPE>
-__global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
+template <int T, int NCH, int R>
+__global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   constexpr int CPT = 4 * NCH;
   constexpr int W = T * CPT;  // floats per staged row
   constexpr int NW = T / 32;
-  constexpr int LPR = 32 / R;        // lanes per row in the warp-level reductions
-  constexpr int V = R * NW / 32;     // warp partials each lane folds in the second stage
-  static_assert(R * NW >= 32 && (R * NW) % 32 == 0 && V <= 4, "second-stage layout");
+  constexpr int LPR = 32 / R;                  // lanes per row in the warp-level reductions
+  constexpr int V = (NW * R + 31) / 32;        // warp partials each lane folds in the second stage
+  static_assert(NW <= 32 && R * CPT <= 32, "register budget: R * CPT exponentials per thread and group");
   extern __shared__ __align__(128) unsigned char smem[];
 
   if (p.st->done) return;  // grid-uniform
@@ -123,10 +137,8 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
   q += 32 * 8;
   int* fillcnt = reinterpret_cast<int*>(q);
   q += kResMaxStages * 4;
-  int* bad_sm = reinterpret_cast<int*>(q);
-  q += 16;
-  float* red = reinterpret_cast<float*>(q);  // [3][R][NW] warp partials of the row sums (3 groups in flight)
-  q += 3 * R * NW * 4;
+  float* red = reinterpret_cast<float*>(q);  // [2][R][NW] warp partials of the row sums
+  q += 2 * R * NW * 4;
   float* shs = reinterpret_cast<float*>(q);  // [T] slice-fold scratch
   q += T * 4;
   float* fs_sm = reinterpret_cast<float*>(q);  // [rows_cap] scaled row potentials of this CTA's rows
@@ -150,8 +162,7 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
   }
   const uint64_t pol = p.evict_first ? policy_evict_first() : 0ull;
   const uint32_t row_bytes = (uint32_t)p.m * 4u;
-  auto issue = [&](int gi) {  // thread 0 only
-    const int s = gi % NG;
+  auto issue = [&](int gi, int s) {  // thread 0 only: group gi into ring slot s
     const uint32_t bar = smem_u32(full + s);
     fillcnt[s] += 1;
     mbar_arrive_expect_tx(bar, row_bytes * R);
@@ -172,16 +183,15 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
       mbar_init(smem_u32(full + s), 1);
       fillcnt[s] = 0;
     }
-    *bad_sm = 0;
     fence_mbar_init();
     const int pre = cnt < NG ? cnt : NG;
-    for (int i = 0; i < pre; ++i) issue(i);
+    for (int i = 0; i < pre; ++i) issue(i, i);  // slot of group gi is gi % NG
   }
   __syncthreads();
 
   const float k = ls->kscale;
   const int norm = ls->err_norm;
-  unsigned nbar = 0;
+  const unsigned epoch = ((unsigned)ls->res_epoch + 1u) & 0xffffu;
 
   // column slice this CTA folds after the sweep
   const int CB = (p.m + G - 1) / G;
@@ -195,26 +205,24 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
   const bool last_any = __any_sync(0xffffffffu, last_ok);
 
   float gsv[CPT], acc[CPT];
-  auto load_g = [&](const float* gsrc) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int col = (c * T + tid) * 4;
-      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (col < p.m) g4 = __ldcg(reinterpret_cast<const float4*>(gsrc + col));  // written by peers: L2, not L1
-      gsv[c * 4 + 0] = g4.x;
-      gsv[c * 4 + 1] = g4.y;
-      gsv[c * 4 + 2] = g4.z;
-      gsv[c * 4 + 3] = g4.w;
-    }
-  };
-  load_g(ls->cur ? p.gs1 : p.gs0);
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * T + tid) * 4;
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < p.m) g4 = *reinterpret_cast<const float4*>((ls->cur ? p.gs1 : p.gs0) + col);
+    gsv[c * 4 + 0] = g4.x;
+    gsv[c * 4 + 1] = g4.y;
+    gsv[c * 4 + 2] = g4.z;
+    gsv[c * 4 + 3] = g4.w;
+  }
   int bad = 0;  // sticky: reported with the next error fold
+  const int s_last = (cnt - 1) % NG;
 
   for (int li = 0; li < p.iters; ++li) {
     if (ls->done) break;  // identical on every CTA
     const int cur = ls->cur;
-    const float* gs = cur ? p.gs1 : p.gs0;
     float* gnext = cur ? p.gs0 : p.gs1;
+    const unsigned tag = (epoch << 16) | (unsigned)(li + 1);
     // the marginal error is only consumed on check iterations, at max_iter, and (to report a lost sum before
     // the host looks) on the last iteration of the launch
     const int itn = ls->it + 1;
@@ -223,50 +231,71 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
 #pragma unroll
     for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
 
+    // ---- sweep over this CTA's row groups ---------------------------------------------------------------
     const bool fwd = !(p.snake && streaming && (li & 1));
-    auto gidx = [&](int pos) { return fwd ? pos : cnt - 1 - pos; };
-
-    // P1 of the group at sweep position pos: exponentials into registers, row sums warp -> red[pos % 3]
-    auto front = [&](int pos, float (&t)[R][CPT]) {
-      const int gi = gidx(pos);
-      const int s = gi % NG;
+    int gi = fwd ? 0 : cnt - 1;
+    int s = fwd ? 0 : s_last;
+    for (int pos = 0; pos < cnt; ++pos) {
       const int lr0 = gi * R;
       mbar_wait(smem_u32(full + s), (uint32_t)((fillcnt[s] - 1) & 1));
-      float ps[R];
+      float t[R][CPT], ps[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const float* srow = stage + ((size_t)s * R + r) * W + tid * 4;
         const float sh = fs_sm[lr0 + r];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          if (c < NCH - 1 || last_any) {
-            const float4 v = *reinterpret_cast<const float4*>(srow + c * (T * 4));
-            t[r][c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + sh));
-            t[r][c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + sh));
-            t[r][c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + sh));
-            t[r][c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + sh));
-          }
+        for (int c = 0; c < NCH - 1; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(srow + c * (T * 4));
+          t[r][c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + sh));
+          t[r][c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + sh));
+          t[r][c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + sh));
+          t[r][c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + sh));
         }
-        if (!last_ok) t[r][CPT - 4] = t[r][CPT - 3] = t[r][CPT - 2] = t[r][CPT - 1] = 0.f;  // past m: stale smem
+      }
+      if (last_any) {  // the last quad may lie past m: stale shared memory there, masked after the fact
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float* srow = stage + ((size_t)s * R + r) * W + tid * 4;
+          const float sh = fs_sm[lr0 + r];
+          constexpr int c = NCH - 1;
+          const float4 v = *reinterpret_cast<const float4*>(srow + c * (T * 4));
+          t[r][c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + sh));
+          t[r][c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + sh));
+          t[r][c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + sh));
+          t[r][c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + sh));
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!last_ok) t[r][CPT - 4] = t[r][CPT - 3] = t[r][CPT - 2] = t[r][CPT - 1] = 0.f;
         float sum = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
           sum += (t[r][c * 4 + 0] + t[r][c * 4 + 1]) + (t[r][c * 4 + 2] + t[r][c * 4 + 3]);
         ps[r] = sum;
       }
-      const float v = warp_sum_rows<R>(ps, lane);
-      if ((lane & (LPR - 1)) == 0) red[((pos % 3) * R + lane / LPR) * NW + warp] = v;
-    };
-
-    // P2: fold the warp partials, w_i = a_i / r_i, new row potential, column accumulators
-    auto back = [&](int pos, float (&t)[R][CPT]) {
-      const int lr0 = gidx(pos) * R;
-      // lane l folds V consecutive warp partials of row l / LPR, then LPR lanes are combined
+      const int par = pos & 1;
+      {
+        const float v = warp_sum_rows<R>(ps, lane);
+        if ((lane & (LPR - 1)) == 0) red[(par * R + lane / LPR) * NW + warp] = v;
+      }
+      __syncthreads();  // the stage is drained by every warp; red[par] is complete
+      if (tid == 0 && streaming) {
+        const int nxt = fwd ? gi + NG : gi - NG;  // lands in the slot just drained
+        if (nxt >= 0 && nxt < cnt) {
+          fence_proxy_async();
+          issue(nxt, s);
+        }
+      }
+      // lane l folds V consecutive warp partials of row l / LPR, then the LPR lanes of a row are combined
       float x = 0.f;
 #pragma unroll
-      for (int i = 0; i < V; ++i) x += red[(pos % 3) * R * NW + lane * V + i];
+      for (int i = 0; i < V; ++i) {
+        const int w2 = (lane & (LPR - 1)) * V + i;
+        if (w2 < NW) x += red[(par * R + lane / LPR) * NW + w2];
+      }
 #pragma unroll
-      for (int off = LPR / 2; off >= 1; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+      for (int o = LPR / 2; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       float wr[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -285,65 +314,25 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[r][c], wr[r], acc[c]);
-    };
-
-    // after the block barrier that follows front(pos + 1): the stages of positions <= pos + 1 are drained
-    auto refill = [&](int pos) {
-      if (tid != 0 || !streaming) return;
-      auto one = [&](int d) {
-        if (d >= cnt) return;
-        const int gi = gidx(d);
-        const int nxt = fwd ? gi + NG : gi - NG;
-        if (nxt >= 0 && nxt < cnt) {
-          fence_proxy_async();
-          issue(nxt);
-        }
-      };
-      if (PIPE) {
-        if (pos == 0) one(0);
-        one(pos + 1);
+      if (fwd) {
+        ++gi;
+        s = (s + 1 == NG) ? 0 : s + 1;
       } else {
-        one(pos);
-      }
-    };
-
-    if (PIPE) {
-      // software pipeline over groups: the reduction chain of group pos (shuffles, block barrier, divide)
-      // overlaps the exponentials of group pos + 1.  Two register sets; red[] is triple-buffered because
-      // front(pos + 2) may run while a slower warp is still in back(pos).
-      float tA[R][CPT], tB[R][CPT];
-      front(0, tA);
-      for (int pos = 0; pos < cnt; pos += 2) {
-        if (pos + 1 < cnt) front(pos + 1, tB);
-        __syncthreads();
-        refill(pos);
-        back(pos, tA);
-        if (pos + 1 < cnt) {
-          if (pos + 2 < cnt) front(pos + 2, tA);
-          __syncthreads();
-          refill(pos + 1);
-          back(pos + 1, tB);
-        }
-      }
-    } else {
-      float tA[R][CPT];
-      for (int pos = 0; pos < cnt; ++pos) {
-        front(pos, tA);
-        __syncthreads();
-        refill(pos);
-        back(pos, tA);
+        --gi;
+        s = (s == 0) ? NG - 1 : s - 1;
       }
     }
 
-    // ---- column partials of this CTA -> global ---------------------------------------------------------
+    // ---- publish the column partials of this CTA (tagged words) -------------------------------------------
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = (c * T + tid) * 4;
-      if (col < p.m)
-        *reinterpret_cast<float4*>(p.part + (size_t)cta * p.stride + col) =
-            make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
+      if (col < p.m) {
+        u64* dst = p.part64 + (size_t)cta * p.stride + col;
+        st_tag2(dst, pack_tag(acc[c * 4 + 0], tag), pack_tag(acc[c * 4 + 1], tag));
+        st_tag2(dst + 2, pack_tag(acc[c * 4 + 2], tag), pack_tag(acc[c * 4 + 3], tag));
+      }
     }
-    grid_barrier(p.gbar, (unsigned)G * (++nbar));
 
     // ---- fold this CTA's column slice over all CTAs (fixed order), next g, error partial ----------------
     double e = 0.0;
@@ -351,8 +340,28 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
       const int jj = jj0 + rc;
       const int j = j0 + jj;
       float pa = 0.f;
-      if (jj < ncol)
-        for (int pp = rgrp; pp < G; pp += groups) pa += __ldcg(p.part + (size_t)pp * p.stride + j);
+      if (jj < ncol) {
+        for (int base = rgrp; base < G; base += groups * 8) {  // 8 independent loads in flight per thread
+          u64 v[8];
+          long long t0 = 0;
+          for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int pp = base + u * groups;
+              if (pp < G) {
+                v[u] = ld_poll(p.part64 + (size_t)pp * p.stride + j);
+                ok = ok && tag_is(v[u], tag);
+              }
+            }
+            if (ok) break;
+            spin_guard(t0);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (base + u * groups < G) pa += __uint_as_float((unsigned)v[u]);
+        }
+      }
       shs[tid] = pa;
       __syncthreads();
       if (rgrp == 0 && jj < ncol) {
@@ -364,8 +373,11 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
           const double d = (double)sj - (double)bj;
           e += (norm == B200OT_NORM_L1) ? fabs(d) : d * d;
         }
-        const float gn = bj > 0.f ? __ldcg(gs + j) + (p.log2b[j] - l2s) : -INFINITY;  // b_j = 0: v_j = 0
-        gnext[j] = gn;
+        // g of the sweep that just ran: own slice, published by this thread one iteration ago (or by init)
+        const float gold = (li == 0) ? (cur ? p.gs1 : p.gs0)[j] : __uint_as_float((unsigned)ld_poll(p.g64 + j));
+        const float gn = bj > 0.f ? gold + (p.log2b[j] - l2s) : -INFINITY;  // b_j = 0: v_j = 0
+        gnext[j] = gn;  // plain copy for the kernels that run after this launch
+        st_tag(p.g64 + j, pack_tag(gn, tag));
         if (bj > 0.f && !(fabsf(gn) < INFINITY)) bad = 1;
       }
       if (jj0 + CBT < CB) __syncthreads();  // shs is reused by the next pass
@@ -378,17 +390,58 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
         double tot = 0.0;
         for (int w2 = 0; w2 < NW; ++w2) tot += dred[w2];
         // a lost sum anywhere poisons the error every CTA folds next: all of them stop together
-        p.errpart[cta] = anybad ? (double)NAN : tot;
+        if (anybad) tot = (double)NAN;
+        const u64 bits = (u64)__double_as_longlong(tot);
+        st_tag2(p.err64 + 2 * (size_t)cta, pack_tag_u((unsigned)bits, tag), pack_tag_u((unsigned)(bits >> 32), tag));
       }
     }
-    grid_barrier(p.gbar, (unsigned)G * (++nbar));
 
-    // ---- next g into registers; every CTA folds the same error partials and advances its state copy ----
-    load_g(gnext);
+    // ---- gather the next g (all columns) into registers ------------------------------------------------
+#pragma unroll
+    for (int c0 = 0; c0 < NCH; c0 += 2) {  // two quads (8 words) in flight per thread
+      u64 w[2][4];
+      long long t0 = 0;
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = c0 + cc;
+          const int col = (c * T + tid) * 4;
+          if (c < NCH && col < p.m) {
+            ld_poll2(p.g64 + col, w[cc][0], w[cc][1]);
+            ld_poll2(p.g64 + col + 2, w[cc][2], w[cc][3]);
+            ok = ok && tag_is(w[cc][0], tag) && tag_is(w[cc][1], tag) && tag_is(w[cc][2], tag) && tag_is(w[cc][3], tag);
+          }
+        }
+        if (ok) break;
+        spin_guard(t0);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = c0 + cc;
+        const int col = (c * T + tid) * 4;
+        if (c < NCH) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) gsv[c * 4 + i] = col < p.m ? __uint_as_float((unsigned)w[cc][i]) : 0.f;
+        }
+      }
+    }
+
+    // ---- every CTA folds the same error partials and advances its copy of the state ----------------------
     if (need_err) {
       double ep = 0.0;
-      for (int i = tid; i < G; i += T) ep += __ldcg(p.errpart + i);
+      for (int i = tid; i < G; i += T) {
+        u64 lo, hi;
+        long long t0 = 0;
+        for (;;) {
+          ld_poll2(p.err64 + 2 * (size_t)i, lo, hi);
+          if (tag_is(lo, tag) && tag_is(hi, tag)) break;
+          spin_guard(t0);
+        }
+        ep += __longlong_as_double((long long)(((u64)(unsigned)hi << 32) | (u64)(unsigned)lo));
+      }
       ep = warp_sum(ep);
+      __syncthreads();  // dred: the publisher above has read it
       if (lane == 0) dred[warp] = ep;
       __syncthreads();
     }
@@ -406,35 +459,94 @@ __global__ void __launch_bounds__(T, 1) resident_kernel(const ResidentArgs p) {
       // one-directional streaming: the ring holds the tail of this sweep, refill it with the head of the next
       if (streaming && !p.snake && !ls->done && li + 1 < p.iters) {
         fence_proxy_async();
-        for (int i = 0; i < NG; ++i) issue(i);
+        for (int i = 0; i < NG; ++i) issue(i, i);
       }
     }
     __syncthreads();
   }
-  if (cta == 0 && tid == 0) *p.st = *ls;
+  if (cta == 0 && tid == 0) {
+    ls->res_epoch = (int)epoch;
+    *p.st = *ls;
+  }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
+constexpr int kResMaxItersPerLaunch = 60000;  // the iteration-in-launch half of the tag is 16 bits
+
 struct ResCfg {
   int T, NCH, R, G, NG, rows_cap, red_groups, cnt_max;
   size_t smem;
 };
 
+template <int T, int NCH, int R>
+static cudaError_t resident_launch(const ResidentArgs* a, int G, size_t smem, cudaStream_t s, int* occ_out) {
+  static bool attr_set = false;  // one flag per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(resident_kernel<T, NCH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kResSmemMax);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (!a) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, resident_kernel<T, NCH, R>, T, smem);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)G);
+  cfg.blockDim = dim3((unsigned)T);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch fails
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, resident_kernel<T, NCH, R>, *a);
+}
+
+static cudaError_t resident_dispatch(int T, int NCH, const ResidentArgs* a, int G, size_t smem, cudaStream_t s,
+                                     int* occ_out) {
+  if (T == 128) return resident_launch<128, 1, 8>(a, G, smem, s, occ_out);
+  switch (NCH) {
+    case 1: return resident_launch<256, 1, 8>(a, G, smem, s, occ_out);
+    case 2: return resident_launch<256, 2, 4>(a, G, smem, s, occ_out);
+    case 3: return resident_launch<256, 3, 2>(a, G, smem, s, occ_out);
+    case 4: return resident_launch<256, 4, 2>(a, G, smem, s, occ_out);
+    case 5: return resident_launch<256, 5, 1>(a, G, smem, s, occ_out);
+    case 6: return resident_launch<256, 6, 1>(a, G, smem, s, occ_out);
+    case 7: return resident_launch<256, 7, 1>(a, G, smem, s, occ_out);
+    default: return resident_launch<256, 8, 1>(a, G, smem, s, occ_out);
+  }
+}
+
 static bool resident_pick(int n, int m, ResCfg* c) {
-  if (n < 1 || m < 4 || (m & 3) || m > 8192) return false;
-  const int T = m <= 512 ? 128 : m <= 1024 ? 256 : 512;
+  if (n < 1 || m < 4 || (m & 3) || m > kResMaxM) return false;
+  const int T = m <= 512 ? 128 : 256;
   const int NCH = (m + 4 * T - 1) / (4 * T);
-  const int R = NCH == 1 ? 8 : NCH == 2 ? 4 : 2;
+  const int R = NCH == 1 ? 8 : NCH == 2 ? 4 : NCH <= 4 ? 2 : 1;
   const int ngroups = (n + R - 1) / R;
-  int G = sm_count();
+  const size_t stage = (size_t)R * T * 4 * NCH * sizeof(float);
+  auto fixed_for = [&](int rows_cap) {
+    return (size_t)(kResMaxStages * 8 + 256 + 32 * 8 + kResMaxStages * 4 + 2 * R * (T / 32) * 4) + (size_t)T * 4 +
+           2 * (size_t)rows_cap * 4 + 128;
+  };
+  // CTAs per SM the hardware will co-schedule for this instantiation (cached): the cooperative grid may not exceed it
+  static int occ_cache[2][9];
+  int& occ = occ_cache[T == 128 ? 0 : 1][NCH];
+  if (occ == 0) {
+    int v = 0;
+    if (resident_dispatch(T, NCH, nullptr, 0, kResSmemMax, nullptr, &v) != cudaSuccess) {
+      (void)cudaGetLastError();
+      v = -1;
+    }
+    occ = v > 0 ? (v > 2 ? 2 : v) : -1;
+  }
+  if (occ < 1) return false;
+  int G = sm_count() * occ;
   if (G < 1) return false;
-  if (G > kNpCap) G = kNpCap;
+  if (G > kResMaxCtas) G = kResMaxCtas;
   if (G > ngroups) G = ngroups;
   const int cnt_max = (ngroups + G - 1) / G;
   const int rows_cap = cnt_max * R;
-  const size_t stage = (size_t)R * T * 4 * NCH * sizeof(float);
-  const size_t fixed = kResMaxStages * 8 + 256 + 32 * 8 + kResMaxStages * 4 + 16 + 3 * R * (T / 32) * 4 +
-                       (size_t)T * 4 + 2 * (size_t)rows_cap * 4 + 128;
+  const size_t fixed = fixed_for(rows_cap);
   if (fixed + 2 * stage > kResSmemMax) return false;
   int NG = (int)((kResSmemMax - fixed) / stage);
   if (NG > kResMaxStages) NG = kResMaxStages;
@@ -455,29 +567,6 @@ static bool resident_pick(int n, int m, ResCfg* c) {
   return true;
 }
 
-template <int T, int NCH, int R, bool PIPE>
-static cudaError_t resident_launch(const ResidentArgs& a, int G, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;  // one flag per instantiation
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(resident_kernel<T, NCH, R, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kResSmemMax);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)G);
-  cfg.blockDim = dim3((unsigned)T);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch fails
-  at[0].val.cooperative = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, resident_kernel<T, NCH, R, PIPE>, a);
-}
-
 // auto rule: iterations short enough that launches and the finalize kernel dominate the sweep
 static bool resident_wanted(int n, int m) {
   const char* e = getenv("B200OT_RESIDENT");
@@ -489,7 +578,7 @@ static bool resident_wanted(int n, int m) {
 static bool g_resident_broken = false;  // a failed cooperative launch disables the path for the process
 
 int resident_try_enqueue(const float* C, int ldc, int n, int m, int iters, const WsPtrs& w, cudaStream_t s) {
-  if (iters < 1 || g_resident_broken || !resident_wanted(n, m)) return 1;
+  if (iters < 1 || g_resident_broken || !resident_wanted(n, m) || !w.res_ll) return 1;
   if ((ldc & 3) || (reinterpret_cast<uintptr_t>(C) & 15)) return 1;
   ResCfg c;
   if (!resident_pick(n, m, &c)) return 1;
@@ -505,12 +594,11 @@ int resident_try_enqueue(const float* C, int ldc, int n, int m, int iters, const
   a.a = w.a;
   a.b = w.b;
   a.log2b = w.log2b;
-  a.part = w.part_sum;
+  a.part64 = reinterpret_cast<unsigned long long*>(w.res_ll);
   a.stride = w.m_pad;
-  a.errpart = w.errpart;
+  a.g64 = a.part64 + (size_t)kResMaxCtas * w.m_pad;
+  a.err64 = a.g64 + w.m_pad;
   a.err_hist = w.err_hist;
-  a.gbar = w.gbar;
-  a.iters = iters;
   a.ng = c.NG;
   a.rows_cap = c.rows_cap;
   const char* es = getenv("B200OT_RES_SNAKE");
@@ -518,30 +606,17 @@ int resident_try_enqueue(const float* C, int ldc, int n, int m, int iters, const
   const char* ee = getenv("B200OT_RES_EVICT");
   a.evict_first = (ee && ee[0] == '1') ? 1 : 0;
   a.red_groups = c.red_groups;
-  B200OT_CUDA_OK(cudaMemsetAsync(w.gbar, 0, sizeof(unsigned), s));
-  cudaError_t e = cudaSuccess;
-  const char* ep = getenv("B200OT_RES_PIPE");
-  const bool pipe = !(ep && ep[0] == '0');
-#define B200OT_RES(T_, N_, R_) \
-  e = pipe ? resident_launch<T_, N_, R_, true>(a, c.G, c.smem, s) : resident_launch<T_, N_, R_, false>(a, c.G, c.smem, s)
-  if (c.T == 128)
-    B200OT_RES(128, 1, 8);
-  else if (c.T == 256)
-    B200OT_RES(256, 1, 8);
-  else if (c.NCH == 1)
-    B200OT_RES(512, 1, 8);
-  else if (c.NCH == 2)
-    B200OT_RES(512, 2, 4);
-  else if (c.NCH == 3)
-    B200OT_RES(512, 3, 2);
-  else
-    B200OT_RES(512, 4, 2);
-#undef B200OT_RES
-  if (e != cudaSuccess) {  // e.g. cooperative launch not possible here: use the launch-per-sweep path
-    set_last_cuda_error(e, "resident_kernel launch (falling back to per-sweep launches)");
-    (void)cudaGetLastError();
-    g_resident_broken = true;
-    return 1;
+  for (int left = iters; left > 0;) {
+    a.iters = left > kResMaxItersPerLaunch ? kResMaxItersPerLaunch : left;
+    left -= a.iters;
+    const cudaError_t e = resident_dispatch(c.T, c.NCH, &a, c.G, c.smem, s, nullptr);
+    if (e != cudaSuccess) {
+      set_last_cuda_error(e, "resident_kernel launch");
+      (void)cudaGetLastError();
+      g_resident_broken = true;
+      // nothing was queued by a failed first launch: the caller can still use the launch-per-sweep path
+      return left + a.iters == iters ? 1 : B200OT_E_LAUNCH;
+    }
   }
   return 0;
 }
@@ -558,7 +633,7 @@ bool resident_describe(int n, int m, char* buf, int buf_len) {
   const bool snake = !(es && es[0] == '0');
   snprintf(buf, buf_len,
            "resident_kernel (persistent, cooperative): %d CTAs x %d threads, %d cols/thread, %d rows/group, "
-           "<=%d groups/CTA, ring %d x %zu B (%s), 2 grid barriers/iteration, smem %zu B/CTA",
+           "<=%d groups/CTA, ring %d x %zu B (%s), tagged-word exchange (no grid barrier), smem %zu B/CTA",
            c.G, c.T, 4 * c.NCH, c.R, c.cnt_max, c.NG, (size_t)c.R * c.T * 4 * c.NCH * 4,
            c.cnt_max <= c.NG ? "C shared-memory resident" : (snake ? "snake sweeps" : "forward sweeps"), c.smem);
   return true;

@@ -1353,6 +1353,8 @@ int b200ot_sinkhorn_setup(int n, int m, const float* a, const float* b, const fl
   const int mx = n > m ? n : m;
   init_state_kernel<<<1, 1, 0, s>>>(w.st, *prm);
   B200OT_LAUNCH_OK();
+  // the resident kernel's tagged words: zero never matches a tag, so stale workspace bytes cannot be mistaken for data
+  if (L.res_ll_bytes) B200OT_CUDA_OK(cudaMemsetAsync(static_cast<char*>(ws) + L.res_ll, 0, L.res_ll_bytes, s));
   init_kernel<<<(mx + 255) / 256, 256, 0, s>>>(w.st, prm->eps, n, m, a, b, f0, g0, w.fs, w.gs0, w.gs1, w.a,
                                                w.b, w.log2b);
   B200OT_LAUNCH_OK();

@@ -13,6 +13,8 @@ namespace b200ot {
 constexpr int kErrHistCap = 4096;
 constexpr int kNpCap = 160;  // max partial slabs (>= clusters of the fused sweep, row splits of the robust one)
 constexpr int kFinalizeThreads = 256;
+constexpr int kResMaxCtas = 320;  // resident kernel: 2 CTAs per SM
+constexpr int kResMaxM = 8192;    // widest row one resident CTA covers
 
 struct State {
   int it, done, converged, cur;
@@ -20,7 +22,7 @@ struct State {
   float err, kscale, eps, tol;
   int max_iter, check_every, check_phase, err_norm;
   int stop_inclusive, path, snap_it, snap_cur;
-  int snap_n_err, pad0, pad1, pad2;
+  int snap_n_err, res_epoch, pad1, pad2;  // res_epoch: launches of the resident kernel on this workspace
   float snap_err, pad3, pad4, pad5;
   // range of the scaled row potentials fs; slot [it & 1] is valid when `it` iterations are complete,
   // the sweep of iteration it+1 fills slot [(it+1) & 1].  lo > hi means "unknown".
@@ -52,7 +54,7 @@ static_assert(sizeof(State) <= 256, "state block");
 
 struct WsLayout {
   size_t state, gbar, err_hist, errpart, fs, gs0, gs1, a, b, log2b, snap_fs, snap_gs, part_sum, part_max,
-      total;
+      res_ll, res_ll_bytes, total;
   size_t m_pad, n_pad;
 };
 
@@ -65,7 +67,7 @@ static inline WsLayout ws_layout(int n, int m) {
   size_t off = 0;
   L.state = off;
   off += 256;
-  L.gbar = off;  // grid-barrier counter of the resident kernel (own 256-byte line)
+  L.gbar = off;  // spare 256-byte line (was: grid-barrier counter of the first resident kernel)
   off += 256;
   L.err_hist = off;
   off += kErrHistCap * sizeof(float);
@@ -86,6 +88,10 @@ static inline WsLayout ws_layout(int n, int m) {
   L.snap_gs = vec(L.m_pad);
   L.part_sum = vec((size_t)kNpCap * L.m_pad);
   L.part_max = vec((size_t)kNpCap * L.m_pad);
+  // tagged 64-bit words of the resident kernel: column partials [kResMaxCtas][m_pad], g [m_pad], error [kResMaxCtas][2]
+  L.res_ll = off;
+  L.res_ll_bytes = m <= kResMaxM ? ((size_t)kResMaxCtas * L.m_pad + L.m_pad + 2 * (size_t)kResMaxCtas) * 8 : 0;
+  off += align_up(L.res_ll_bytes, 256);
   L.total = off;
   return L;
 }
@@ -96,6 +102,7 @@ struct WsPtrs {
   float* err_hist;
   double* errpart;
   float *fs, *gs0, *gs1, *a, *b, *log2b, *snap_fs, *snap_gs, *part_sum, *part_max;
+  void* res_ll;  // null when the rows are too wide for the resident kernel
   size_t m_pad;
 };
 static inline WsPtrs ws_ptrs(void* ws, const WsLayout& L) {
@@ -115,6 +122,7 @@ static inline WsPtrs ws_ptrs(void* ws, const WsLayout& L) {
   w.snap_gs = reinterpret_cast<float*>(p + L.snap_gs);
   w.part_sum = reinterpret_cast<float*>(p + L.part_sum);
   w.part_max = reinterpret_cast<float*>(p + L.part_max);
+  w.res_ll = L.res_ll_bytes ? static_cast<void*>(p + L.res_ll) : nullptr;
   w.m_pad = L.m_pad;
   return w;
 }

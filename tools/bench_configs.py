@@ -114,7 +114,6 @@ def main():
         an = torch.full((nn,), 1.0 / nn, device=dev)
         rec = {}
         for label, env in (("resident", {"B200OT_RESIDENT": "1"}), ("resident_forward_only", {"B200OT_RESIDENT": "1", "B200OT_RES_SNAKE": "0"}),
-                           ("resident_no_pipeline", {"B200OT_RESIDENT": "1", "B200OT_RES_PIPE": "0"}),
                            ("per_sweep_launches", {"B200OT_RESIDENT": "0"})):
             if label == "resident_forward_only" and nn < 4096:
                 continue
