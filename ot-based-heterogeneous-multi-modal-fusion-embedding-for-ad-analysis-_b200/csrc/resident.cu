@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   constexpr int NW = T / 32;
   constexpr int LPR = 32 / R;                  // lanes per row in the warp-level reductions
   constexpr int V = (NW * R + 31) / 32;        // warp partials each lane folds in the second stage
-  static_assert(NW <= 32 && R * CPT <= 32, "register budget: R * CPT exponentials per thread and group");
+  static_assert(NW <= 32 && (NW & (NW - 1)) == 0 && R * CPT <= 32, "register budget: R * CPT exponentials per thread and group");
   extern __shared__ __align__(128) unsigned char smem[];
 
   if (p.st->done) return;  // grid-uniform
@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   float* fs_sm = reinterpret_cast<float*>(q);  // [rows_cap] scaled row potentials of this CTA's rows
   q += (size_t)p.rows_cap * 4;
   float* a_sm = reinterpret_cast<float*>(q);  // [rows_cap]
+  q += (size_t)p.rows_cap * 4;
+  float* la_sm = reinterpret_cast<float*>(q);  // [rows_cap] log2 a_i
 
   // rows of this CTA: whole groups of R rows, contiguous
   const int ngroups = (p.n + R - 1) / R;
@@ -158,7 +160,9 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
     const int row = row_base + i;
     const bool ok = row < p.n;
     fs_sm[i] = ok ? p.fs[row] : -INFINITY;  // rows past n: t = 2^-inf = 0, weight 0
-    a_sm[i] = ok ? p.a[row] : 0.f;
+    const float ai = ok ? p.a[row] : 0.f;
+    a_sm[i] = ai;
+    la_sm[i] = ai > 0.f ? log2f(ai) : -INFINITY;
   }
   const uint64_t pol = p.evict_first ? policy_evict_first() : 0ull;
   const uint32_t row_bytes = (uint32_t)p.m * 4u;
@@ -280,7 +284,9 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
         if ((lane & (LPR - 1)) == 0) red[(par * R + lane / LPR) * NW + warp] = v;
       }
       __syncthreads();  // the stage is drained by every warp; red[par] is complete
-      if (tid == 0 && streaming) {
+      // the per-group serial chores (ring refill, new row potentials) rotate over the warps so that no warp
+      // is systematically late at the next block barrier
+      if (streaming && lane == 0 && warp == ((pos + 1) & (NW - 1))) {
         const int nxt = fwd ? gi + NG : gi - NG;  // lands in the slot just drained
         if (nxt >= 0 && nxt < cnt) {
           fence_proxy_async();
@@ -296,20 +302,20 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
       }
 #pragma unroll
       for (int o = LPR / 2; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      // every lane now holds the total of row lane / LPR: one divide per lane, the weights are broadcast
+      const int myrow = lane / LPR;
+      const float ar = a_sm[lr0 + myrow];
+      const bool live = ar > 0.f;
+      const float wl = live ? __fdividef(ar, x) : 0.f;
+      if (warp == (pos & (NW - 1)) && (lane & (LPR - 1)) == 0 && row_base + lr0 + myrow < p.n) {
+        const float fnew = live ? fs_sm[lr0 + myrow] + (la_sm[lr0 + myrow] - log2f(x)) : -INFINITY;
+        fs_sm[lr0 + myrow] = fnew;
+        p.fs[row_base + lr0 + myrow] = fnew;
+        if (live && !(fabsf(fnew) < INFINITY)) bad = 1;  // vanished / overflowed row sum
+      }
       float wr[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float rt = __shfl_sync(0xffffffffu, x, r * LPR);
-        const float ar = a_sm[lr0 + r];
-        const bool live = ar > 0.f;
-        wr[r] = live ? __fdividef(ar, rt) : 0.f;
-        if (tid == r && row_base + lr0 + r < p.n) {
-          const float fnew = live ? fs_sm[lr0 + r] + (log2f(ar) - log2f(rt)) : -INFINITY;
-          fs_sm[lr0 + r] = fnew;
-          p.fs[row_base + lr0 + r] = fnew;
-          if (live && !(fabsf(fnew) < INFINITY)) bad = 1;  // vanished / overflowed row sum
-        }
-      }
+      for (int r = 0; r < R; ++r) wr[r] = __shfl_sync(0xffffffffu, wl, r * LPR);
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -526,7 +532,7 @@ static bool resident_pick(int n, int m, ResCfg* c) {
   const size_t stage = (size_t)R * T * 4 * NCH * sizeof(float);
   auto fixed_for = [&](int rows_cap) {
     return (size_t)(kResMaxStages * 8 + 256 + 32 * 8 + kResMaxStages * 4 + 2 * R * (T / 32) * 4) + (size_t)T * 4 +
-           2 * (size_t)rows_cap * 4 + 128;
+           3 * (size_t)rows_cap * 4 + 128;
   };
   // CTAs per SM the hardware will co-schedule for this instantiation (cached): the cooperative grid may not exceed it
   static int occ_cache[2][9];

@@ -637,6 +637,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
     constexpr bool UNI = decltype(uni_tag)::value;
     float a_next = cnt > 0 ? p.a[cid] : 0.f;
     float sh_next = (!UNI && cnt > 0) ? p.fs[cid] : sigma;
+    int qsel = 0;  // CTA of the cluster that writes this row's potential
     for (int i = 0; i < cnt; ++i) {
       const int row = cid + i * NC;
       const int s = i % NG;
@@ -678,13 +679,13 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
       if (lane == 0) red[par * kLiteWarps + warp] = ps;
       __syncthreads();  // ring stage drained by every warp; red[par] complete
       const int xb = i % kXBuf;
-      if (tid == 0) {
-        if (i + NG < cnt) {
-          fence_proxy_async();
-          issue(i + NG);
-        }
-        mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
+      // per-row serial chores rotate over warps (and the potential update over the CTAs of the cluster) so that
+      // no warp is systematically the last one at the next block barrier
+      if (lane == 0 && warp == ((i + 4) & (kLiteWarps - 1)) && i + NG < cnt) {
+        fence_proxy_async();
+        issue(i + NG);
       }
+      if (tid == 0) mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
       if (tid < Q) {
         float v = 0.f;
 #pragma unroll
@@ -699,7 +700,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
         if (qq < Q) rt += xch[xb * kMaxCluster + qq];
       const bool live = ar > 0.f;
       const float w = live ? __fdividef(ar, rt) : 0.f;
-      if (q == 0 && tid == 0) {
+      if (q == qsel && lane == 0 && warp == ((i + 2) & (kLiteWarps - 1))) {
         const float fnew = live ? sh + (log2f(ar) - log2f(rt)) : -INFINITY;
         p.fs[row] = fnew;
         if (live) {
@@ -713,6 +714,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
       }
 #pragma unroll
       for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[c], w, acc[c]);
+      qsel = (qsel + 1 == Q) ? 0 : qsel + 1;
     }
   };
   if (uniform)
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
   else
     row_loop(std::false_type{});
 
-  if (q == 0 && tid == 0 && f_lo <= f_hi) {
+  if (lane == 0 && f_lo <= f_hi) {  // every thread that wrote potentials
     atomic_min_float(&st->fs_lo[(it0 + 1) & 1], f_lo);
     atomic_max_float(&st->fs_hi[(it0 + 1) & 1], f_hi);
   }
