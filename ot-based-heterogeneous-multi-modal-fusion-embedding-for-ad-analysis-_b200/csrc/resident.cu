@@ -65,17 +65,17 @@ __device__ __forceinline__ u64 pack_tag(float v, unsigned tag) { return ((u64)ta
 __device__ __forceinline__ u64 pack_tag_u(unsigned v, unsigned tag) { return ((u64)tag << 32) | (u64)v; }
 __device__ __forceinline__ u64 ld_poll(const u64* p) {
   u64 v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void ld_poll2(const u64* p, u64& a, u64& b) {
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void st_tag(u64* p, u64 v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_tag2(u64* p, u64 a, u64 b) {
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ bool tag_is(u64 v, unsigned tag) { return (unsigned)(v >> 32) == tag; }
 // a producer that never shows up traps instead of hanging the GPU box
@@ -118,6 +118,8 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   constexpr int NW = T / 32;
   constexpr int LPR = 32 / R;                  // lanes per row in the warp-level reductions
   constexpr int V = (NW * R + 31) / 32;        // warp partials each lane folds in the second stage
+  constexpr int kFold = 10;                     // tagged words a thread polls at once in the slice fold
+  constexpr int kGq = NCH <= 4 ? NCH : 2;      // column quads a thread polls at once when it gathers g
   static_assert(NW <= 32 && (NW & (NW - 1)) == 0 && R * CPT <= 32, "register budget: R * CPT exponentials per thread and group");
   extern __shared__ __align__(128) unsigned char smem[];
 
@@ -127,8 +129,8 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   const int G = (int)gridDim.x, cta = (int)blockIdx.x;
   const int NG = p.ng;
 
-  float* stage = reinterpret_cast<float*>(smem);  // [NG][R][W]
-  unsigned char* q = smem + (size_t)NG * R * W * sizeof(float);
+  // fixed-size arrays first (compile-time offsets), then the per-row vectors, then the ring
+  unsigned char* q = smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(q);
   q += kResMaxStages * 8;
   State* ls = reinterpret_cast<State*>(q);
@@ -146,6 +148,9 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   float* a_sm = reinterpret_cast<float*>(q);  // [rows_cap]
   q += (size_t)p.rows_cap * 4;
   float* la_sm = reinterpret_cast<float*>(q);  // [rows_cap] log2 a_i
+  q += (size_t)p.rows_cap * 4;
+  float* stage = reinterpret_cast<float*>(smem + (((size_t)(q - smem) + 127) & ~(size_t)127));  // [NG][R][W]
+  const uint32_t full_u32 = smem_u32(full);
 
   // rows of this CTA: whole groups of R rows, contiguous
   const int ngroups = (p.n + R - 1) / R;
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   const uint64_t pol = p.evict_first ? policy_evict_first() : 0ull;
   const uint32_t row_bytes = (uint32_t)p.m * 4u;
   auto issue = [&](int gi, int s) {  // thread 0 only: group gi into ring slot s
-    const uint32_t bar = smem_u32(full + s);
+    const uint32_t bar = full_u32 + 8u * (uint32_t)s;
     fillcnt[s] += 1;
     mbar_arrive_expect_tx(bar, row_bytes * R);
 #pragma unroll
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   };
   if (tid == 0) {
     for (int s = 0; s < NG; ++s) {
-      mbar_init(smem_u32(full + s), 1);
+      mbar_init(full_u32 + 8u * (uint32_t)s, 1);
       fillcnt[s] = 0;
     }
     fence_mbar_init();
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
     int s = fwd ? 0 : s_last;
     for (int pos = 0; pos < cnt; ++pos) {
       const int lr0 = gi * R;
-      mbar_wait(smem_u32(full + s), (uint32_t)((fillcnt[s] - 1) & 1));
+      mbar_wait(full_u32 + 8u * (uint32_t)s, (uint32_t)((fillcnt[s] - 1) & 1));
       float t[R][CPT], ps[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -347,13 +352,13 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
       const int j = j0 + jj;
       float pa = 0.f;
       if (jj < ncol) {
-        for (int base = rgrp; base < G; base += groups * 8) {  // 8 independent loads in flight per thread
-          u64 v[8];
+        for (int base = rgrp; base < G; base += groups * kFold) {  // all of a thread's loads in flight at once
+          u64 v[kFold];
           long long t0 = 0;
           for (;;) {
             bool ok = true;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < kFold; ++u) {
               const int pp = base + u * groups;
               if (pp < G) {
                 v[u] = ld_poll(p.part64 + (size_t)pp * p.stride + j);
@@ -364,7 +369,7 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
             spin_guard(t0);
           }
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
+          for (int u = 0; u < kFold; ++u)
             if (base + u * groups < G) pa += __uint_as_float((unsigned)v[u]);
         }
       }
@@ -404,13 +409,13 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
 
     // ---- gather the next g (all columns) into registers ------------------------------------------------
 #pragma unroll
-    for (int c0 = 0; c0 < NCH; c0 += 2) {  // two quads (8 words) in flight per thread
-      u64 w[2][4];
+    for (int c0 = 0; c0 < NCH; c0 += kGq) {  // kGq quads (4 words each) in flight per thread
+      u64 w[kGq][4];
       long long t0 = 0;
       for (;;) {
         bool ok = true;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+        for (int cc = 0; cc < kGq; ++cc) {
           const int c = c0 + cc;
           const int col = (c * T + tid) * 4;
           if (c < NCH && col < p.m) {
@@ -423,7 +428,7 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
         spin_guard(t0);
       }
 #pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
+      for (int cc = 0; cc < kGq; ++cc) {
         const int c = c0 + cc;
         const int col = (c * T + tid) * 4;
         if (c < NCH) {
