@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
   constexpr int NW = T / 32;
   constexpr int LPR = 32 / R;                  // lanes per row in the warp-level reductions
   constexpr int V = (NW * R + 31) / 32;        // warp partials each lane folds in the second stage
-  constexpr int kFold = 10;                     // tagged words a thread polls at once in the slice fold
+  constexpr int kFold = NCH <= 4 ? 10 : 8;      // tagged words a thread polls at once in the slice fold
   constexpr int kGq = NCH <= 4 ? NCH : 2;      // column quads a thread polls at once when it gathers g
   static_assert(NW <= 32 && (NW & (NW - 1)) == 0 && R * CPT <= 32, "register budget: R * CPT exponentials per thread and group");
   extern __shared__ __align__(128) unsigned char smem[];

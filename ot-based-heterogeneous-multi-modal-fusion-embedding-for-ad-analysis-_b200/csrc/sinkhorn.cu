@@ -685,13 +685,15 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
         fence_proxy_async();
         issue(i + NG);
       }
-      if (tid == 0) mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
-      if (tid < Q) {
-        float v = 0.f;
+      if (warp == ((i + 6) & (kLiteWarps - 1))) {  // the row-sum exchange rotates too
+        if (lane == 0) mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
+        if (lane < Q) {
+          float v = 0.f;
 #pragma unroll
-        for (int w = 0; w < kLiteWarps; ++w) v += red[par * kLiteWarps + w];
-        st_async_f32(map_to_cta(smem_u32(xch + xb * kMaxCluster + q), (uint32_t)tid), v,
-                     map_to_cta(smem_u32(xbar + xb), (uint32_t)tid));
+          for (int w = 0; w < kLiteWarps; ++w) v += red[par * kLiteWarps + w];
+          st_async_f32(map_to_cta(smem_u32(xch + xb * kMaxCluster + q), (uint32_t)lane), v,
+                       map_to_cta(smem_u32(xbar + xb), (uint32_t)lane));
+        }
       }
       mbar_wait(smem_u32(xbar + xb), (uint32_t)((i / kXBuf) & 1));
       float rt = 0.f;
