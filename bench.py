@@ -214,7 +214,23 @@ def run_b200(args):
     prm = ops.make_params(EPS, iters, 0.0, 10, 1, "l2", False, args.path)
     kern = sharded.CudaShardKernels(Cmat, a_loc, b, prm, path=args.path)
     comm = sharded.NcclComm() if (world > 1 and args.loop == "c") else None
-    solver = sharded.ShardedSinkhorn(kern, comm=comm)
+    peer = None
+    if world > 1 and args.loop == "peer":
+        try:  # exchange buffers mapped into every rank with CUDA IPC; all ranks must agree on the outcome
+            peer = sharded.PeerExchange(m)
+            ok = 1
+        except Exception as exc:  # noqa: BLE001
+            peer, ok = None, 0
+            if rank == 0:
+                print(f"peer exchange unavailable ({exc}); using the NCCL loop", file=sys.stderr)
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if peer is not None:
+                peer.close()
+            peer, args.loop = None, "c"
+            comm = sharded.NcclComm()
+    solver = sharded.ShardedSinkhorn(kern, comm=comm, peer=peer)
     stepper = None
     resident = world == 1 and "resident_kernel" in ops.describe_kernel(n_loc, m)
     if resident:
@@ -275,7 +291,8 @@ def run_b200(args):
         xd = Xp.to(dev, non_blocking=True)
         yd = Yp.to(dev, non_blocking=True)
         ops.cost_matrix(xd, yd, out=Cmat)
-        f, g, inf = sharded.solve_sharded(Cmat, a_loc, b, EPS, max_iter=iters, tol=0.0, path=args.path, comm=comm)
+        f, g, inf = sharded.solve_sharded(Cmat, a_loc, b, EPS, max_iter=iters, tol=0.0, path=args.path, comm=comm,
+                                          peer=peer)
         f.cpu(), g.cpu()
         return inf["err"]
 
@@ -314,7 +331,7 @@ def run_b200(args):
     # our kernels per step: init (init_state, init, colpass, finalize) + snapshot per enqueue + 2 per iteration;
     # sharded: setup (2) + prologue (colpass, reduce_parts) + finalize, then sweep + reduce_parts + finalize per iteration
     n_enq = (iters // args.graph + (1 if iters % args.graph else 0)) if args.graph else 1
-    launches_per_step = (4 + n_enq + 2 * iters) if world == 1 else (5 + 3 * iters)
+    launches_per_step = (4 + n_enq + 2 * iters) if world == 1 else (5 + 3 * iters)  # peer loop: sweep, reduce+push, finalize
     if resident:
         launches_per_step = 4 + 1 + 1  # init, snapshot, one resident launch for all iterations
     c_bytes = 4.0 * n_loc * m
@@ -374,9 +391,10 @@ def main():
     ap.add_argument("--path", default="auto", choices=["auto", "fused", "robust"])
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--graph", type=int, default=10, help="iterations per CUDA-graph replay at N=1 (0 = eager launches)")
-    ap.add_argument("--loop", default="c", choices=["c", "python", "graph"],
-                    help="N>1: who queues the per-iteration loop (c = one C call incl. ncclAllReduce on the compute "
-                         "stream; python = torch.distributed all_reduce per iteration; graph = python loop captured)")
+    ap.add_argument("--loop", default="peer", choices=["peer", "c", "python", "graph"],
+                    help="N>1: how the column sums are exchanged (peer = pushed as tagged words into peer memory over "
+                         "NVLink by the kernels themselves, no collective call; c = ncclAllReduce queued from C on the "
+                         "compute stream; python = torch.distributed all_reduce per iteration; graph = python loop captured)")
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--cpu-iters", type=int, default=100)
     ap.add_argument("--no-cpu", action="store_true")

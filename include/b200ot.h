@@ -203,6 +203,30 @@ int b200ot_sinkhorn_shard_start(const float* C, int ldc, int n_local, int m, voi
 int b200ot_sinkhorn_shard_run(const float* C, int ldc, int n_local, int m, int iters, int path, void* ws,
                               float* s_buf, void* comm, void* stream);
 
+/* The same row-sharded loop WITHOUT a collective library call in it (the all-reduce of m column
+ * partials fused into the kernels that produce and consume them).  Every rank owns an exchange buffer of
+ * b200ot_peer_exchange_bytes(world, m) bytes that its peers map with CUDA IPC (peer_alloc on the owner -> 64-byte
+ * handle -> peer_open on the others; one box, NVLink / NVSwitch).  shard_push runs the local sweep (or, with
+ * is_prologue, the column pass of the first g update), folds the cluster partials and STORES the m column sums as
+ * tagged 64-bit words {value, tag} straight into slab [parity][rank] of every peer's buffer; shard_finalize_peer
+ * polls the world slabs of this rank's own buffer, adds them in rank order (identical result on every rank, no
+ * atomics) and applies the usual finalize (marginal error, stopping rule, next g).  `epoch` distinguishes solves
+ * that reuse the buffers (same value on every rank, change it per solve); the iteration part of the tag comes from
+ * the device-side state, so shard_run_peer can queue any number of iterations ahead and stays graph-capturable.
+ * peer_bufs: HOST array of `world` device pointers, entry r = rank r's buffer as mapped in this process.        */
+int b200ot_peer_alloc(size_t bytes, void** dptr, unsigned char* handle64_host);
+int b200ot_peer_open(const unsigned char* handle64_host, void** dptr);
+int b200ot_peer_close(void* dptr);
+int b200ot_peer_free(void* dptr);
+size_t b200ot_peer_exchange_bytes(int world, int m);
+int b200ot_sinkhorn_shard_push(const float* C, int ldc, int n_local, int m, int path, void* ws,
+                               void* const* peer_bufs, int world, int rank, unsigned epoch, int is_prologue,
+                               void* stream);
+int b200ot_sinkhorn_shard_finalize_peer(int n_local, int m, void* ws, const void* my_buf, int world, unsigned epoch,
+                                        int is_prologue, void* stream);
+int b200ot_sinkhorn_shard_run_peer(const float* C, int ldc, int n_local, int m, int iters, int path, void* ws,
+                                   void* const* peer_bufs, int world, int rank, unsigned epoch, void* stream);
+
 /* ---- batched small problems (one problem per CTA, float64, kernel domain) --
  * BASELINE config 2: per-training-step minibatch OT (MRI_PET_OT_nojax.py:679-715).
  * Runs POT's sinkhorn_knopp arithmetic itself (u = 1/n start, v then u update, error every

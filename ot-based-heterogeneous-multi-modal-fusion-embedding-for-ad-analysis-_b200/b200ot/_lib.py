@@ -77,6 +77,14 @@ SIGNATURES = {
     "b200ot_nccl_destroy": (_i, [_p]),
     "b200ot_sinkhorn_shard_start": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "b200ot_sinkhorn_shard_run": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "b200ot_peer_alloc": (_i, [_sz, C.POINTER(C.c_void_p), _p]),
+    "b200ot_peer_open": (_i, [_p, C.POINTER(C.c_void_p)]),
+    "b200ot_peer_close": (_i, [_p]),
+    "b200ot_peer_free": (_i, [_p]),
+    "b200ot_peer_exchange_bytes": (_sz, [_i, _i]),
+    "b200ot_sinkhorn_shard_push": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, C.c_uint, _i, _p]),
+    "b200ot_sinkhorn_shard_finalize_peer": (_i, [_i, _i, _p, _p, _i, C.c_uint, _i, _p]),
+    "b200ot_sinkhorn_shard_run_peer": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, C.c_uint, _p]),
     "b200ot_sinkhorn_batched": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, C.POINTER(Params), _p, _p, _p,
                                      _p, _p, _p]),
     "b200ot_plan": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _p]),

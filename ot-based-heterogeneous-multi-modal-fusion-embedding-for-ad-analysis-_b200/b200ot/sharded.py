@@ -61,6 +61,57 @@ class NcclComm:
             self.handle = C.c_void_p()
 
 
+class PeerExchange:
+    """Exchange buffers for the NCCL-free sharded loop: one buffer per rank, mapped into every peer with CUDA IPC
+    (collective constructor: every rank of `group` must call it).  `local_bufs` builds the same object from
+    plain device tensors of ONE process instead -- several shards emulated on one GPU, used by the tests."""
+
+    def __init__(self, m: int, group: Optional[dist.ProcessGroup] = None, local_bufs=None, rank: int = 0):
+        self.lib = _lib.load()
+        self.m = int(m)
+        self._opened, self._own = [], None
+        if local_bufs is not None:
+            self.world, self.rank = len(local_bufs), int(rank)
+            self._keep = local_bufs
+            ptrs = [t.data_ptr() for t in local_bufs]
+        else:
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            nbytes = self.lib.b200ot_peer_exchange_bytes(self.world, self.m)
+            own, handle = C.c_void_p(), (C.c_ubyte * 64)()
+            check(self.lib.b200ot_peer_alloc(nbytes, C.byref(own), handle), "b200ot_peer_alloc")
+            self._own = own
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            ptrs = []
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    ptrs.append(own.value)
+                    continue
+                p = C.c_void_p()
+                check(self.lib.b200ot_peer_open(hb, C.byref(p)), "b200ot_peer_open")
+                self._opened.append(p)
+                ptrs.append(p.value)
+        self.ptrs = (C.c_void_p * self.world)(*ptrs)
+        self.epoch = 0
+
+    @staticmethod
+    def nbytes(world: int, m: int) -> int:
+        return _lib.load().b200ot_peer_exchange_bytes(int(world), int(m))
+
+    def next_epoch(self) -> int:
+        """A new solve on the same buffers: the same sequence of values on every rank."""
+        self.epoch = (self.epoch + 1) & 0xFFF
+        return self.epoch
+
+    def close(self):
+        for p in self._opened:
+            self.lib.b200ot_peer_close(p)
+        self._opened = []
+        if self._own is not None:
+            self.lib.b200ot_peer_free(self._own)
+            self._own = None
+
+
 class CudaShardKernels:
     """The C-ABI implementation of the per-rank kernels (include/b200ot.h, row-sharded form)."""
 
@@ -114,6 +165,24 @@ class CudaShardKernels:
                                                  comm.handle if comm else None, ops._stream()),
               "b200ot_sinkhorn_shard_run")
 
+    # -- peer-memory loop: no collective call, the column sums travel as tagged words over NVLink
+    def push(self, peer: "PeerExchange", is_prologue: bool):
+        check(self.lib.b200ot_sinkhorn_shard_push(ops._ptr(self.C), self.ldc, self.n, self.m, self.path,
+                                                  ops._ws_ptr(self.ws), peer.ptrs, peer.world, peer.rank, peer.epoch,
+                                                  int(is_prologue), ops._stream()), "b200ot_sinkhorn_shard_push")
+
+    def finalize_peer(self, peer: "PeerExchange", is_prologue: bool):
+        check(self.lib.b200ot_sinkhorn_shard_finalize_peer(self.n, self.m, ops._ws_ptr(self.ws),
+                                                           peer.ptrs[peer.rank], peer.world, peer.epoch,
+                                                           int(is_prologue), ops._stream()),
+              "b200ot_sinkhorn_shard_finalize_peer")
+
+    def run_peer(self, iters: int, peer: "PeerExchange"):
+        check(self.lib.b200ot_sinkhorn_shard_run_peer(ops._ptr(self.C), self.ldc, self.n, self.m, int(iters),
+                                                      self.path, ops._ws_ptr(self.ws), peer.ptrs, peer.world,
+                                                      peer.rank, peer.epoch, ops._stream()),
+              "b200ot_sinkhorn_shard_run_peer")
+
     def flags(self) -> dict:
         out = torch.empty(8, dtype=torch.int32, device=self.C.device)
         check(self.lib.b200ot_sinkhorn_peek(ops._ws_ptr(self.ws), ops._ptr(out), ops._stream()),
@@ -138,13 +207,16 @@ class CudaShardKernels:
 class ShardedSinkhorn:
     """Drives one row shard; `kernels` implements the per-rank kernel interface."""
 
-    def __init__(self, kernels, group: Optional[dist.ProcessGroup] = None, comm: Optional[NcclComm] = None):
+    def __init__(self, kernels, group: Optional[dist.ProcessGroup] = None, comm: Optional[NcclComm] = None,
+                 peer: Optional[PeerExchange] = None):
         self.k = kernels
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         # with a libb200ot-owned communicator the loop is driven from C (one call queues everything)
         self.comm = comm
-        self.c_loop = comm is not None and hasattr(kernels, "run_c")
+        # with peer exchange buffers there is no collective call in the loop at all
+        self.peer = peer if (peer is not None and hasattr(kernels, "run_peer")) else None
+        self.c_loop = self.peer is not None or (comm is not None and hasattr(kernels, "run_c"))
         self.iterations_queued = 0
         self.allreduces = 0
         self._events = []  # bounds how far the host may run ahead of the GPU (see run())
@@ -162,6 +234,15 @@ class ShardedSinkhorn:
     def start(self):
         """State setup + the first g update (one all-reduce)."""
         self.k.setup()
+        if self.peer is not None:
+            if self.world > 1 and dist.is_initialized() and torch.cuda.is_available():
+                # a new solve reuses the exchange slabs: no rank may still be polling the previous solve's words
+                torch.cuda.current_stream().synchronize()
+                dist.barrier(group=self.group)
+            self.peer.next_epoch()
+            self.k.push(self.peer, True)
+            self.k.finalize_peer(self.peer, True)
+            return
         if self.c_loop:
             self.k.start_c(self.comm)
             self.allreduces += 1
@@ -202,14 +283,18 @@ class ShardedSinkhorn:
             done = 0
             while done < iters:  # chunks keep the host at most two windows ahead of the device
                 step = min(self._win, iters - done)
-                self.k.run_c(step, self.comm)
+                if self.peer is not None:
+                    self.k.run_peer(step, self.peer)
+                else:
+                    self.k.run_c(step, self.comm)
                 done += step
                 ev = torch.cuda.Event()
                 ev.record()
                 self._events.append(ev)
                 if len(self._events) > self._lag:
                     self._events.pop(0).synchronize()
-            self.allreduces += iters
+            if self.peer is None:
+                self.allreduces += iters
             self.iterations_queued += iters
             return
         i = 0
@@ -250,9 +335,11 @@ class ShardedSinkhorn:
 
 
 def solve_sharded(C_local, a_local, b, eps, max_iter=1000, tol=1e-9, check_every=10, check_phase=1,
-                  err_norm="l2", stop_inclusive=False, path="auto", f0=None, g0=None, group=None, comm=None):
+                  err_norm="l2", stop_inclusive=False, path="auto", f0=None, g0=None, group=None, comm=None,
+                  peer=None):
     """One call: row-sharded log-domain Sinkhorn; returns this rank's (f_local, g, info).
-    Pass a `NcclComm` to drive the loop from C (recommended at 4+ GPUs)."""
+    Pass a `PeerExchange` (column sums pushed over NVLink as tagged words, no collective call in the loop) or a
+    `NcclComm` (ncclAllReduce queued from C on the compute stream); with neither the loop runs from Python."""
     prm = ops.make_params(eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive, path)
     k = CudaShardKernels(C_local, a_local, b, prm, path=path, f0=f0, g0=g0)
-    return ShardedSinkhorn(k, group, comm).solve(max_iter, check_every, check_phase)
+    return ShardedSinkhorn(k, group, comm, peer).solve(max_iter, check_every, check_phase)

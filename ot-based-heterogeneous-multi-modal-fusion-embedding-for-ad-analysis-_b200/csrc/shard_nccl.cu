@@ -87,6 +87,48 @@ int b200ot_nccl_destroy(void* comm) {
   return api.CommDestroy(comm) == 0 ? 0 : B200OT_E_LAUNCH;
 }
 
+// ---- peer memory over NVLink (CUDA IPC): exchange buffers of the NCCL-free sharded loop ----------------------
+int b200ot_peer_alloc(size_t bytes, void** dptr, unsigned char* handle64_host) {
+  if (!dptr || !handle64_host || bytes == 0) return B200OT_E_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  B200OT_CUDA_OK(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);  // tag 0 never matches
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    set_last_cuda_error(e, "cudaIpcGetMemHandle");
+    (void)cudaGetLastError();
+    cudaFree(p);
+    return B200OT_E_LAUNCH;
+  }
+  memcpy(handle64_host, &h, 64);
+  *dptr = p;
+  return 0;
+}
+
+int b200ot_peer_open(const unsigned char* handle64_host, void** dptr) {
+  if (!handle64_host || !dptr) return B200OT_E_INVALID;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64_host, 64);
+  void* p = nullptr;
+  B200OT_CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dptr = p;
+  return 0;
+}
+
+int b200ot_peer_close(void* dptr) {
+  if (!dptr) return B200OT_E_INVALID;
+  B200OT_CUDA_OK(cudaIpcCloseMemHandle(dptr));
+  return 0;
+}
+
+int b200ot_peer_free(void* dptr) {
+  if (!dptr) return B200OT_E_INVALID;
+  B200OT_CUDA_OK(cudaFree(dptr));
+  return 0;
+}
+
 // First g update of a row-sharded solve (after b200ot_sinkhorn_setup): column sums, all-reduce, finalize.
 int b200ot_sinkhorn_shard_start(const float* C, int ldc, int n_local, int m, void* ws, float* s_buf, void* comm,
                                 void* stream) {

@@ -109,12 +109,39 @@ __global__ void __launch_bounds__(256) init_kernel(State* st, float eps, int n, 
 // part_sum[p][j] (and optional part_max[p][j]: the sums are relative to 2^max) for p < np.
 // Writes gs_next = gs_cur + log2 b - log2 s and lets the LAST block (ticket) fold the
 // per-block error partials in fixed order and advance the state machine.
+// Tagged 64-bit words {fp32 value, 32-bit tag} written by peer GPUs over NVLink (row-sharded solve without NCCL in
+// the loop, see reduce_push_kernel): a 64-bit access is single-copy atomic, so the tag of exchange x carries the
+// value of exchange x.  Exchange index x = 0 for the prologue, it + 1 for the iteration that follows `it` completed
+// ones; slabs are double-buffered by the parity of x.
+__device__ __forceinline__ unsigned peer_tag(unsigned epoch, int x) { return (epoch << 20) | ((unsigned)(x + 1) & 0xfffffu); }
+__device__ __forceinline__ float peer_poll(const unsigned long long* p, unsigned tag) {
+  unsigned long long v;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if ((unsigned)(v >> 32) == tag) break;
+    if (t0 == 0)
+      t0 = clock64();
+    else if (clock64() - t0 > 8000000000ll)
+      __trap();  // a peer that never pushes traps this rank instead of hanging the box
+    __nanosleep(40);
+  }
+  return __uint_as_float((unsigned)v);
+}
+
 __global__ void __launch_bounds__(kFinalizeThreads)
     finalize_kernel(State* st, const float* __restrict__ part_sum, const float* __restrict__ part_max,
                     int np, size_t stride, int m, const float* __restrict__ b,
                     const float* __restrict__ log2b, float* gs0, float* gs1, double* errpart,
-                    float* err_hist, int is_prologue, int groups) {
+                    float* err_hist, int is_prologue, int groups,
+                    const unsigned long long* tagged = nullptr, unsigned epoch = 0) {
   if (st->done) return;
+  unsigned tag = 0;
+  if (tagged) {  // np = world slabs of this exchange's parity
+    const int x = is_prologue ? 0 : st->it + 1;
+    tag = peer_tag(epoch, x);
+    tagged += (size_t)(x & 1) * np * stride;
+  }
   const int cur = st->cur;
   const float* gcur = cur ? gs1 : gs0;
   float* gnext = cur ? gs0 : gs1;
@@ -134,6 +161,8 @@ __global__ void __launch_bounds__(kFinalizeThreads)
           const float pm = part_max[(size_t)p * stride + j];
           if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm - M);
         }
+      } else if (tagged) {
+        for (int p = grp; p < np; p += groups) acc += peer_poll(tagged + (size_t)p * stride + j, tag);
       } else {
         for (int p = grp; p < np; p += groups) acc += part_sum[(size_t)p * stride + j];
       }
@@ -758,6 +787,38 @@ __global__ void reduce_parts_kernel(const State* st, const float* __restrict__ p
   s_out[j] = acc;
 }
 
+// Row-sharded solve without NCCL in the loop: fold this rank's cluster partials and PUSH the result, as tagged
+// words, into slab [parity][rank] of every peer's exchange buffer (peer memory mapped over NVLink / NVSwitch with
+// CUDA IPC; stores are posted, nobody waits).  The finalize kernel of each rank then polls its own buffer.
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+  unsigned long long* buf[kMaxPeers];
+};
+__global__ void __launch_bounds__(256)
+    reduce_push_kernel(const State* st, const float* __restrict__ part_sum, const float* __restrict__ part_max, int np,
+                       size_t stride, int m, PeerPtrs peers, int world, int rank, size_t xstride, unsigned epoch,
+                       int is_prologue) {
+  if (st->done) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  float acc = 0.f;
+  if (part_max) {
+    for (int p = 0; p < np; ++p) {
+      const float pm = part_max[(size_t)p * stride + j];
+      if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm);
+    }
+  } else {
+    for (int p = 0; p < np; ++p) acc += part_sum[(size_t)p * stride + j];
+  }
+  const int x = is_prologue ? 0 : st->it + 1;
+  const unsigned long long word = ((unsigned long long)peer_tag(epoch, x) << 32) | (unsigned long long)__float_as_uint(acc);
+  const size_t off = ((size_t)(x & 1) * world + rank) * xstride + j;
+  for (int r = 0; r < world; ++r) {
+    const int dst = (rank + r) % world;  // spread the ranks over the links: everyone starts with itself
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(peers.buf[dst] + off), "l"(word) : "memory");
+  }
+}
+
 // =============================================================================
 // ROBUST kernels (running-max logsumexp, any shape / alignment)
 // =============================================================================
@@ -1308,14 +1369,15 @@ static int launch_colpass(const float* C, int ldc, int n, int m, const WsPtrs& w
 }
 
 static int launch_finalize(int m, const WsPtrs& w, const float* psum, const float* pmax, int np,
-                           size_t stride, int is_prologue, cudaStream_t s) {
+                           size_t stride, int is_prologue, cudaStream_t s,
+                           const unsigned long long* tagged = nullptr, unsigned epoch = 0) {
   int groups = np >= 32 ? 8 : np >= 16 ? 4 : np >= 8 ? 2 : 1;
   while (groups > 1 && (long long)(m + kFinalizeThreads / groups - 1) / (kFinalizeThreads / groups) > 4096) groups >>= 1;
   const int cb = kFinalizeThreads / groups;
   const int grid = (m + cb - 1) / cb;
   if (grid > 4096) return B200OT_E_UNSUPPORTED;
   finalize_kernel<<<grid, kFinalizeThreads, 0, s>>>(w.st, psum, pmax, np, stride, m, w.b, w.log2b, w.gs0,
-                                                    w.gs1, w.errpart, w.err_hist, is_prologue, groups);
+                                                    w.gs1, w.errpart, w.err_hist, is_prologue, groups, tagged, epoch);
   B200OT_LAUNCH_OK();
   return 0;
 }
@@ -1646,6 +1708,68 @@ int b200ot_sinkhorn_shard_finalize(int n_local, int m, void* ws, const float* s_
   if (!ws || !s_total || n_local <= 0 || m <= 0) return B200OT_E_INVALID;
   const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
   return launch_finalize(m, w, s_total, nullptr, 1, 0, is_prologue, static_cast<cudaStream_t>(stream));
+}
+
+// ---- row-sharded entry points, peer-memory form (no NCCL in the loop) ---------------------------------------
+size_t b200ot_peer_exchange_bytes(int world, int m) {
+  if (world < 1 || world > kMaxPeers || m <= 0) return 0;
+  return (size_t)2 * world * align_up((size_t)m, 64) * sizeof(unsigned long long);
+}
+
+int b200ot_sinkhorn_shard_push(const float* C, int ldc, int n_local, int m, int path, void* ws,
+                               void* const* peer_bufs, int world, int rank, unsigned epoch, int is_prologue,
+                               void* stream) {
+  int rc = check_problem(C, ldc, n_local, m, ws);
+  if (rc) return rc;
+  if (!peer_bufs || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PeerPtrs pp;
+  for (int r = 0; r < kMaxPeers; ++r) pp.buf[r] = r < world ? static_cast<unsigned long long*>(peer_bufs[r]) : nullptr;
+  for (int r = 0; r < world; ++r)
+    if (!pp.buf[r]) return B200OT_E_INVALID;
+  int np = 0;
+  const float* pmax = nullptr;
+  if (is_prologue) {
+    rc = launch_colpass(C, ldc, n_local, m, w, &np, s);
+    pmax = w.part_max;
+  } else {
+    path = resolve_path(path, C, ldc, n_local, m);
+    if (path == B200OT_PATH_FUSED) {
+      rc = launch_sweep_fused(C, ldc, n_local, m, w, &np, s);
+    } else {
+      rc = launch_rowpass(C, ldc, n_local, m, w, s);
+      if (rc) return rc;
+      rc = launch_colpass(C, ldc, n_local, m, w, &np, s);
+      pmax = w.part_max;
+    }
+  }
+  if (rc) return rc;
+  reduce_push_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, pmax, np, w.m_pad, m, pp, world, rank,
+                                                     align_up((size_t)m, 64), epoch & 0xfffu, is_prologue);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_sinkhorn_shard_finalize_peer(int n_local, int m, void* ws, const void* my_buf, int world, unsigned epoch,
+                                        int is_prologue, void* stream) {
+  if (!ws || !my_buf || n_local <= 0 || m <= 0 || world < 1 || world > kMaxPeers) return B200OT_E_INVALID;
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
+  return launch_finalize(m, w, nullptr, nullptr, world, align_up((size_t)m, 64), is_prologue,
+                         static_cast<cudaStream_t>(stream), static_cast<const unsigned long long*>(my_buf),
+                         epoch & 0xfffu);
+}
+
+int b200ot_sinkhorn_shard_run_peer(const float* C, int ldc, int n_local, int m, int iters, int path, void* ws,
+                                   void* const* peer_bufs, int world, int rank, unsigned epoch, void* stream) {
+  if (iters < 0 || !peer_bufs || rank < 0 || rank >= world) return B200OT_E_INVALID;
+  for (int i = 0; i < iters; ++i) {
+    int rc = b200ot_sinkhorn_shard_push(C, ldc, n_local, m, path, ws, peer_bufs, world, rank, epoch, 0, stream);
+    if (rc) return rc;
+    rc = b200ot_sinkhorn_shard_finalize_peer(n_local, m, ws, peer_bufs[rank], world, epoch, 0, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -448,6 +448,78 @@ def test_row_sharded_kernels_emulated_on_one_gpu(cuda_dev, n, m, shards):
     assert _rel(P, Pref) < RTOL
 
 
+@pytest.mark.parametrize("n,m,shards", [(301, 2048, 2), (1000, 8192, 4), (520, 1000, 8)])
+def test_peer_exchange_kernels_emulated_on_one_gpu(cuda_dev, n, m, shards):
+    """The NCCL-free sharded loop (shard_push -> tagged words in every peer's buffer -> shard_finalize_peer polls
+    its own buffer), with the peers' buffers living on one GPU: all pushes of an exchange are queued before the
+    finalizes that poll for them.  Same plan and iteration count as the oracle, g replicated bit for bit, equal to
+    the all-reduce form bit for bit (same fold order), and a second solve on the same buffers (new epoch) works."""
+    from b200ot import ops, sharded
+    X, Y = orc.synthetic_embeddings(n, m, 24, config_index=9)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    eps = 0.1
+    Pref, lg = orc.sinkhorn_log(C, a, b, eps, max_iter=60, tol=1e-4, err_norm="l1", check_every=10, check_phase=0,
+                                log=True)
+    Cd = ops.aligned_copy(_dev(C, cuda_dev))
+    bd = _dev(b, cuda_dev)
+    prm = ops.make_params(eps, 60, 1e-4, 10, 0, "l1", False, "auto")
+    nbytes = sharded.PeerExchange.nbytes(shards, m)
+    assert nbytes == 2 * shards * ((m + 63) // 64 * 64) * 8
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=cuda_dev) for _ in range(shards)]
+    ks, peers = [], []
+    for r in range(shards):
+        lo, hi = sharded.row_range(n, shards, r)
+        ks.append(sharded.CudaShardKernels(Cd[lo:hi], _dev(a[lo:hi], cuda_dev), bd, prm))
+        peers.append(sharded.PeerExchange(m, local_bufs=bufs, rank=r))
+    g_first = None
+    for solve in range(2):
+        for k, pe in zip(ks, peers):
+            k.setup()
+            pe.next_epoch()
+        for k, pe in zip(ks, peers):
+            k.push(pe, True)
+        for k, pe in zip(ks, peers):
+            k.finalize_peer(pe, True)
+        for _ in range(60):
+            for k, pe in zip(ks, peers):
+                k.push(pe, False)
+            for k, pe in zip(ks, peers):
+                k.finalize_peer(pe, False)
+        outs = [k.finish() for k in ks]
+        assert len({o[2]["n_iter"] for o in outs}) == 1 and outs[0][2]["n_iter"] == lg["n_iter"]
+        assert all(o[2]["converged"] == lg["converged"] and o[2]["status"] == 0 for o in outs)
+        for o in outs[1:]:
+            assert torch.equal(o[1], outs[0][1])  # g is replicated bit for bit
+        f = torch.cat([o[0] for o in outs])
+        P = ops.plan(Cd, f, outs[0][1], eps).cpu().numpy()
+        assert _rel(P, Pref) < RTOL
+        if g_first is None:
+            g_first = outs[0][1].clone()
+        else:
+            assert torch.equal(g_first, outs[0][1])
+    # the all-reduce form of the same loop, summing the shards in rank order
+    for k in ks:
+        k.setup()
+    tot = ks[0].prologue().clone()
+    for k in ks[1:]:
+        tot = tot + k.prologue()
+    for k in ks:
+        k.finalize(tot, True)
+    for _ in range(60):
+        tot = ks[0].sweep().clone()
+        for k in ks[1:]:
+            tot = tot + k.sweep()
+        for k in ks:
+            k.finalize(tot, False)
+    g_allreduce = ks[0].finish()[1]
+    if shards < 8:  # finalize folds up to 7 slabs left to right, like the running sum above
+        assert torch.equal(g_allreduce, g_first)
+    else:
+        torch.testing.assert_close(g_allreduce, g_first, rtol=0, atol=1e-5)
+
+
 def test_cuda_graph_replay_equals_eager_launches(cuda_dev):
     """SinkhornStepper.build_graph / run: replaying a captured 10-iteration graph (and past the stopping
     rule) gives bit-identical potentials to eager launches."""
