@@ -271,6 +271,19 @@ int b200ot_cosine_loss(const float* A, int lda, const float* B, int ldb, int row
  * D[i][i] within row i, ties at their mean position) / (n - 1).                                     */
 int b200ot_foscttm(const float* D, int ldd, int n, float* out, void* stream);
 
+/* Entropic Gromov-Wasserstein sample couplings, one label per CTA, float64, everything in shared memory
+ * (get_coupling_egw_ott_fixed, MRI_PET_OT_OT_per_epoch_attn.py:129-186).  X: all labels'
+ * rows concatenated ((sum n_l) x dx fp32), xoff: nprob + 1 row offsets (device int32); same for Y; n_l, m_l <= 64.
+ * Geometries: squared Euclidean / max (PointCloud(scale_cost="max_cost"), :155-156); square loss; uniform
+ * marginals; outer loop = ott GromovWasserstein(epsilon, max_iterations = gw_max_iter, min_iterations,
+ * threshold), inner = log-domain Sinkhorn(max_iterations = sk_max_iter, threshold, inner_iterations =
+ * sk_check_every), warm-started (:168-173).  Outputs: T (float64, label l at element offset toff[l], n_l x m_l),
+ * info4[l] = {outer iterations, outer converged, last inner converged, inner iterations in total}, cost[l].   */
+int b200ot_egw_batched(const float* X, const float* Y, const int* xoff, const int* yoff, const long long* toff,
+                       int nprob, int max_n, int max_m, int dx, int dy, float eps, int gw_max_iter, int gw_min_iter,
+                       float gw_threshold, int sk_max_iter, int sk_check_every, float sk_threshold, double* T,
+                       int* info4, double* cost, void* stream);
+
 /* ---- attention fusion core ----------------------------------------------------
  * softmax(Q K^T / sqrt(dh)) V for the S <= 4 fusion tokens of the reference's SelfAttentionBlock
  * (MRI_PET_OT_OT_per_epoch_attn.py:523-549, tokens built at :731-738; one token in

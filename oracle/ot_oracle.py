@@ -25,6 +25,8 @@ Parity status
   flavours **parity is unpinned**: they are restatements of the published
   algorithms anchored on the reference's call sites
   (``MRI_PET_OT_nojax.py:143``, ``perturbot/perturbot/match/fot.py:129-134``).
+* ``egw_ott`` restates ott-jax 0.6.0 ``GromovWasserstein`` (square loss, constant epsilon, warm-started inner
+  Sinkhorn) as called at ``MRI_PET_OT_OT_per_epoch_attn.py:155-175``; same situation, **parity unpinned**.
 """
 from __future__ import annotations
 
@@ -36,7 +38,7 @@ __all__ = [
     "sinkhorn_log", "sinkhorn_log_ott", "plan_from_potentials", "fot_bcd_ott",
     "get_feature_coupling_pot", "get_coupling_fot", "plan_guard_rownorm",
     "apply_plan_T", "barycentric", "cosine_loss", "ot_cost", "envelope_grads", "foscttm",
-    "group_features_by_label",
+    "group_features_by_label", "egw_ott", "get_coupling_egw_ott_fixed",
 ]
 
 
@@ -376,6 +378,76 @@ def get_coupling_fot(data, Ts, eps=5e-3):
     Y = np.concatenate([Y_dict[l] for l in keys])
     Tv, cost, lg = fot_bcd_ott(X, Y, Ts, reg2=eps, niter=2000, log=True)
     return Tv, lg
+
+
+# --------------------------------------------------------------------------
+# entropic Gromov-Wasserstein sample couplings
+# --------------------------------------------------------------------------
+def egw_ott(X, Y, eps=5e-3, gw_max_iterations=2000, sinkhorn_max_iterations=2000, gw_threshold=1e-3,
+            gw_min_iterations=5, sk_threshold=1e-3, sk_check_every=10):
+    """ott-jax 0.6.0 ``GromovWasserstein(epsilon=eps, max_iterations=..., linear_solver=Sinkhorn(max_iterations=...))``
+    on ``QuadraticProblem(PointCloud(x, x, scale_cost="max_cost"), PointCloud(y, y, scale_cost="max_cost"))``
+    (``MRI_PET_OT_OT_per_epoch_attn.py:155-175``).  PARITY UNPINNED: ott is not in the tree; this restates its
+    published algorithm -- squared-Euclidean geometries divided by their maximum, square loss decomposition
+    ``f1(x) = x^2, f2(y) = y^2, h1(x) = x, h2(y) = 2y``, uniform marginals, ``T0 = a b^T``; every outer iteration
+    linearises at the current coupling (marginal terms from the coupling's own marginals), solves the linear
+    problem with the log-domain Sinkhorn of ``sinkhorn_log_ott`` (absolute epsilon, L1 error of the b-marginal
+    every 10 iterations, threshold 1e-3) warm-started from the previous potentials, and records
+    ``cost = <a, f> + <b, g>``; it stops once ``iteration >= min_iterations`` and
+    ``isclose(costs[i - 2], costs[i - 1], rtol=threshold)``.  Returns ``(T, log)``."""
+    X = np.asarray(X, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    n, m = X.shape[0], Y.shape[0]
+    C1 = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)
+    C2 = ((Y[:, None, :] - Y[None, :, :]) ** 2).sum(-1)
+    C1 = C1 / C1.max() if C1.max() > 0 else C1
+    C2 = C2 / C2.max() if C2.max() > 0 else C2
+    a = np.full(n, 1.0 / n)
+    b = np.full(m, 1.0 / m)
+    la, lb = np.log(a), np.log(b)
+    T = np.outer(a, b)
+    f = np.zeros(n)
+    g = np.zeros(m)
+    costs = []
+    inner_total = 0
+    inner_conv = False
+    outer_conv = False
+    while len(costs) < gw_max_iterations:
+        M = ((C1 * C1) @ T.sum(1))[:, None] + ((C2 * C2) @ T.sum(0))[None, :] - 2.0 * C1 @ T @ C2
+        it = 0
+        inner_conv = False
+        while it < sinkhorn_max_iterations:
+            g = eps * lb - eps * _lse((f[:, None] - M) / eps, axis=0)
+            f = eps * la - eps * _lse((g[None, :] - M) / eps, axis=1)
+            it += 1
+            if it % sk_check_every == 0:
+                err = np.abs(np.exp((f[:, None] + g[None, :] - M) / eps).sum(0) - b).sum()
+                if err < sk_threshold:
+                    inner_conv = True
+                    break
+        inner_total += it
+        T = np.exp((f[:, None] + g[None, :] - M) / eps)
+        costs.append(float(a @ f + b @ g))
+        k = len(costs)
+        if k >= 2:
+            outer_conv = bool(abs(costs[-2] - costs[-1]) <= 1e-8 + gw_threshold * abs(costs[-1]))
+            if outer_conv and k >= gw_min_iterations:
+                break
+    return T, {"n_iters_outer": len(costs), "converged_outer": outer_conv, "converged_inner": inner_conv,
+               "inner_iterations": inner_total, "GW cost": costs[-1], "costs": costs}
+
+
+def get_coupling_egw_ott_fixed(data, eps=5e-3, gw_max_iterations=2000, sinkhorn_max_iterations=2000):
+    """``MRI_PET_OT_OT_per_epoch_attn.py:129-186``: one coupling per label, NaN features mapped to 0 (:148-151)."""
+    X_dict, Y_dict = data
+    Ts, log = {}, {}
+    for l in X_dict.keys():
+        T, lg = egw_ott(np.nan_to_num(np.asarray(X_dict[l], dtype=np.float64)),
+                        np.nan_to_num(np.asarray(Y_dict[l], dtype=np.float64)), eps, gw_max_iterations,
+                        sinkhorn_max_iterations)
+        Ts[l] = T
+        log[l] = lg
+    return Ts, log
 
 
 # --------------------------------------------------------------------------

@@ -93,6 +93,7 @@ SIGNATURES = {
     "b200ot_apply_plan_t": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _i, _i, _p, _i, _p]),
     "b200ot_cosine_loss": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "b200ot_foscttm": (_i, [_p, _i, _i, _p, _p]),
+    "b200ot_egw_batched": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _f, _i, _i, _f, _p, _p, _p, _p]),
     "b200ot_token_attention_fwd": (_i, [_p, _i, _i, _i, _i, _p, _f, _p, _p, _p]),
     "b200ot_token_attention_bwd": (_i, [_p, _p, _p, _f, _p, _i, _i, _i, _i, _p, _p]),
 }

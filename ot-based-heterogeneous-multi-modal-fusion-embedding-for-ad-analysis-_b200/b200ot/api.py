@@ -11,6 +11,7 @@ repository), so a training script swaps one import:
     fot_numpy / get_coupling_fot(data, Ts, eps)      perturbot/perturbot/match/fot.py:14-220
     mdict_to_matrix(M_dict, src, tgt)                baseline_models_fusion.py:233-239
     init_matrix_np(X1, X2, v1, v2)                   perturbot/perturbot/match/utils.py:125-184
+    get_coupling_egw_ott_fixed(data, eps, ...)       MRI_PET_OT_OT_per_epoch_attn.py:129-186
 
 Inputs may be NumPy arrays (as in the reference: copied to the GPU, result copied
 back as NumPy in the input dtype) or torch tensors (CPU: same; CUDA: everything
@@ -345,6 +346,41 @@ def group_features_by_label(y, p, max_samples_per_label=None):
             arr = arr[:max_samples_per_label]
         out[int(label)] = arr
     return out
+
+
+def get_coupling_egw_ott_fixed(data, eps: float = 5e-3, gw_max_iterations: int = 2000,
+                               sinkhorn_max_iterations: int = 2000, *, device=None):
+    """Drop-in for ``get_coupling_egw_ott_fixed`` (MRI_PET_OT_OT_per_epoch_attn.py:129-186; also
+    ``get_coupling_egw_ott``, MRI_PET_OT.py:68-122): entropic Gromov-Wasserstein sample coupling per label between
+    the MRI and PET embeddings of that label, on max-scaled squared-Euclidean point-cloud geometries.  All labels
+    are solved by ONE kernel launch, one CTA per label.  ``data = (X_dict, Y_dict)`` with NumPy arrays (as in the
+    reference: results come back as NumPy) or torch tensors (CUDA: couplings stay on the device).  Returns
+    ``(Ts, log)`` with the reference's log keys; NaN features are mapped to 0 with a message (:148-151)."""
+    X_dict, Y_dict = data
+    labels = list(X_dict.keys())
+    conv = _Conv(X_dict[labels[0]], device)
+    t0 = time.time()
+    Xs, Ys = [], []
+    for l in labels:
+        x = conv.to_dev(X_dict[l])
+        y = conv.to_dev(Y_dict[l])
+        if bool(torch.isnan(x).any()) or bool(torch.isnan(y).any()):
+            print(f"Warning: NaNs detected in features for label {l}")
+            x, y = torch.nan_to_num(x), torch.nan_to_num(y)
+        Xs.append(x)
+        Ys.append(y)
+    cost_time = time.time() - t0
+    t0 = time.time()
+    Ts, info = ops.egw_batched(Xs, Ys, eps, gw_max_iterations, sinkhorn_max_iterations)
+    host = {k: v.cpu() for k, v in info.items()}
+    dt = time.time() - t0
+    out_T, log = {}, {}
+    for i, l in enumerate(labels):
+        out_T[l] = conv.back(Ts[i])
+        log[l] = {"n_iters_outer": int(host["n_iters_outer"][i]), "converged_inner": bool(host["converged_inner"][i]),
+                  "converged_outer": bool(host["converged_outer"][i]), "GW cost": float(host["GW cost"][i]),
+                  "inner_iterations": int(host["inner_iterations"][i]), "time": dt, "cost_time": cost_time}
+    return out_T, log
 
 
 def foscttm(Y_pred, Y_true, idx=None, *, device=None):

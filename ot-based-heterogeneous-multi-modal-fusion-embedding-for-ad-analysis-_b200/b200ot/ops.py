@@ -397,3 +397,42 @@ def foscttm(pred: torch.Tensor, true: torch.Tensor) -> torch.Tensor:
     out = torch.empty(pred.shape[0], dtype=torch.float32, device=pred.device)
     check(lib.b200ot_foscttm(_ptr(D), D.stride(0), pred.shape[0], _ptr(out), _stream()), "b200ot_foscttm")
     return out
+
+
+def egw_batched(Xs, Ys, eps: float = 5e-3, gw_max_iter: int = 2000, sk_max_iter: int = 2000, gw_threshold: float = 1e-3,
+                gw_min_iter: int = 5, sk_threshold: float = 1e-3, sk_check_every: int = 10):
+    """Entropic Gromov-Wasserstein couplings for a list of independent small problems (one per label), one CTA
+    each (b200ot_egw_batched).  Xs[l]: (n_l, dx) CUDA fp32, Ys[l]: (m_l, dy); n_l, m_l <= 64.
+    Returns ``(Ts, info)``: float64 couplings and a dict of per-problem tensors."""
+    lib = _lib.load()
+    if len(Xs) == 0 or len(Xs) != len(Ys):
+        raise B200OTError("egw_batched needs matching, non-empty lists of point clouds")
+    dev = Xs[0].device
+    for t in list(Xs) + list(Ys):
+        _need_cuda(t, "point cloud")
+        if t.dim() != 2 or t.shape[0] < 1:
+            raise B200OTError("point clouds must be non-empty 2-D tensors")
+    dx, dy = Xs[0].shape[1], Ys[0].shape[1]
+    if any(x.shape[1] != dx for x in Xs) or any(y.shape[1] != dy for y in Ys):
+        raise B200OTError("all point clouds of one side must share their width")
+    ns = [int(x.shape[0]) for x in Xs]
+    ms = [int(y.shape[0]) for y in Ys]
+    X = torch.cat([x.contiguous() for x in Xs]).contiguous()
+    Y = torch.cat([y.contiguous() for y in Ys]).contiguous()
+    xoff = torch.tensor([0] + list(torch.tensor(ns).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+    yoff = torch.tensor([0] + list(torch.tensor(ms).cumsum(0).tolist()), dtype=torch.int32, device=dev)
+    sizes = [a * b for a, b in zip(ns, ms)]
+    toff_h = [0]
+    for sz in sizes:
+        toff_h.append(toff_h[-1] + sz)
+    toff = torch.tensor(toff_h, dtype=torch.int64, device=dev)
+    T = torch.empty(toff_h[-1], dtype=torch.float64, device=dev)
+    info = torch.zeros((len(ns), 4), dtype=torch.int32, device=dev)
+    cost = torch.zeros(len(ns), dtype=torch.float64, device=dev)
+    check(lib.b200ot_egw_batched(_ptr(X), _ptr(Y), _ptr(xoff), _ptr(yoff), _ptr(toff), len(ns), max(ns), max(ms),
+                                 dx, dy, float(eps), int(gw_max_iter), int(gw_min_iter), float(gw_threshold),
+                                 int(sk_max_iter), int(sk_check_every), float(sk_threshold), _ptr(T), _ptr(info),
+                                 _ptr(cost), _stream()), "b200ot_egw_batched")
+    Ts = [T[toff_h[i]:toff_h[i + 1]].view(ns[i], ms[i]) for i in range(len(ns))]
+    return Ts, {"n_iters_outer": info[:, 0], "converged_outer": info[:, 1], "converged_inner": info[:, 2],
+                "inner_iterations": info[:, 3], "GW cost": cost}

@@ -636,3 +636,36 @@ def test_foscttm_and_label_grouping(cuda_dev):
     assert list(dev_g.keys()) == list(ref_g.keys())
     for k in ref_g:
         assert dev_g[k].is_cuda and np.array_equal(dev_g[k].cpu().numpy(), ref_g[k])
+
+
+def test_entropic_gromov_wasserstein_per_label(cuda_dev):
+    """get_coupling_egw_ott_fixed (MRI_PET_OT_OT_per_epoch_attn.py:129-186): all labels in one launch, one CTA per
+    label, against the float64 restatement of ott's GromovWasserstein: same outer / inner iteration counts, same
+    couplings; ragged label sizes, different widths on the two sides, NumPy in -> NumPy out."""
+    import b200ot
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((64, 48)).astype(np.float32)
+    Q, _ = np.linalg.qr(rng.standard_normal((48, 48)))
+    perm = rng.permutation(64)
+    Y = ((X @ Q)[perm] + 0.01 * rng.standard_normal((64, 48))).astype(np.float32)
+    Xd = {0: X, 2: rng.standard_normal((33, 48)).astype(np.float32), 1: rng.standard_normal((7, 48)).astype(np.float32)}
+    Yd = {0: Y[:, :40].copy(), 2: (2 * rng.standard_normal((50, 40))).astype(np.float32),
+          1: rng.standard_normal((9, 40)).astype(np.float32)}
+    Ts, log = b200ot.get_coupling_egw_ott_fixed((Xd, Yd), eps=5e-3)
+    Tref, lref = orc.get_coupling_egw_ott_fixed((Xd, Yd), eps=5e-3)
+    assert list(Ts.keys()) == [0, 2, 1]
+    for l in Xd:
+        assert isinstance(Ts[l], np.ndarray) and Ts[l].shape == Tref[l].shape
+        assert log[l]["n_iters_outer"] == lref[l]["n_iters_outer"], (l, log[l], lref[l])
+        assert log[l]["inner_iterations"] == lref[l]["inner_iterations"]
+        assert log[l]["converged_outer"] == lref[l]["converged_outer"]
+        assert log[l]["converged_inner"] == lref[l]["converged_inner"]
+        assert abs(log[l]["GW cost"] - lref[l]["GW cost"]) < 1e-6 * max(1.0, abs(lref[l]["GW cost"]))
+        assert _rel(Ts[l], Tref[l]) < RTOL
+    # the truncated copy (40 of 48 rotated coordinates) still identifies most of the permutation
+    assert (Ts[0].argmax(1) == np.argsort(perm)).mean() > 0.9
+    # CUDA tensors in -> couplings stay on the device
+    Tt, _ = b200ot.get_coupling_egw_ott_fixed(({0: _dev(Xd[1], cuda_dev)}, {0: _dev(Yd[1], cuda_dev)}), eps=5e-2)
+    assert Tt[0].is_cuda and Tt[0].shape == (7, 9)
+    np.testing.assert_allclose(Tt[0].double().cpu().numpy(), orc.egw_ott(Xd[1], Yd[1], eps=5e-2)[0], rtol=0,
+                               atol=RTOL * float(Tt[0].max()))

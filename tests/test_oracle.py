@@ -160,3 +160,24 @@ def test_foscttm_and_grouping_match_reference(golden_dir):
     assert sorted(grouped.keys()) == list(g["keys"])
     for k in grouped:
         assert np.array_equal(grouped[k], g[f"group{k}"])
+
+
+def test_egw_oracle_recovers_an_isometric_copy_and_keeps_marginals():
+    """egw_ott (restated ott GromovWasserstein, parity unpinned): structural checks only -- the coupling of a point
+    cloud with a rotated, permuted, slightly noisy copy of itself is the permutation; marginals are uniform; the
+    outer loop runs at least min_iterations and stops on the cost criterion."""
+    rng = np.random.default_rng(0)
+    n = 40
+    X = rng.standard_normal((n, 16))
+    Q, _ = np.linalg.qr(rng.standard_normal((16, 16)))
+    perm = rng.permutation(n)
+    Y = (X @ Q)[perm] + 0.01 * rng.standard_normal((n, 16))
+    T, lg = orc.egw_ott(X, Y, eps=5e-3)
+    assert lg["n_iters_outer"] >= 5 and lg["converged_outer"] and lg["converged_inner"]
+    np.testing.assert_allclose(T.sum(1), np.full(n, 1.0 / n), rtol=1e-9)  # the f update is exact
+    assert np.abs(T.sum(0) - 1.0 / n).sum() < 1e-3  # the inner stopping rule
+    assert (T.argmax(1) == np.argsort(perm)).all()
+    c = lg["costs"]
+    assert abs(c[-2] - c[-1]) <= 1e-8 + 1e-3 * abs(c[-1])
+    Ts, log = orc.get_coupling_egw_ott_fixed(({0: X[:10], 1: X[10:25]}, {0: Y[:12], 1: Y[12:30]}))
+    assert Ts[0].shape == (10, 12) and Ts[1].shape == (15, 18) and set(log) == {0, 1}
