@@ -644,13 +644,15 @@ def test_entropic_gromov_wasserstein_per_label(cuda_dev):
     couplings; ragged label sizes, different widths on the two sides, NumPy in -> NumPy out."""
     import b200ot
     rng = np.random.default_rng(5)
-    X = rng.standard_normal((64, 48)).astype(np.float32)
-    Q, _ = np.linalg.qr(rng.standard_normal((48, 48)))
+    X = np.zeros((64, 40), dtype=np.float32)  # a 6-dimensional cloud ...
+    X[:, :6] = rng.standard_normal((64, 6))
+    Q, _ = np.linalg.qr(rng.standard_normal((6, 6)))
     perm = rng.permutation(64)
-    Y = ((X @ Q)[perm] + 0.01 * rng.standard_normal((64, 48))).astype(np.float32)
-    Xd = {0: X, 2: rng.standard_normal((33, 48)).astype(np.float32), 1: rng.standard_normal((7, 48)).astype(np.float32)}
-    Yd = {0: Y[:, :40].copy(), 2: (2 * rng.standard_normal((50, 40))).astype(np.float32),
-          1: rng.standard_normal((9, 40)).astype(np.float32)}
+    Y = np.zeros((64, 48), dtype=np.float32)  # ... and an isometric copy of it: rotated, permuted, slightly noisy
+    Y[:, :6] = (X[:, :6] @ Q)[perm] + 0.01 * rng.standard_normal((64, 6))
+    Xd = {0: X, 2: rng.standard_normal((33, 40)).astype(np.float32), 1: rng.standard_normal((7, 40)).astype(np.float32)}
+    Yd = {0: Y, 2: (2 * rng.standard_normal((50, 48))).astype(np.float32),
+          1: rng.standard_normal((9, 48)).astype(np.float32)}
     Ts, log = b200ot.get_coupling_egw_ott_fixed((Xd, Yd), eps=5e-3)
     Tref, lref = orc.get_coupling_egw_ott_fixed((Xd, Yd), eps=5e-3)
     assert list(Ts.keys()) == [0, 2, 1]
@@ -662,8 +664,8 @@ def test_entropic_gromov_wasserstein_per_label(cuda_dev):
         assert log[l]["converged_inner"] == lref[l]["converged_inner"]
         assert abs(log[l]["GW cost"] - lref[l]["GW cost"]) < 1e-6 * max(1.0, abs(lref[l]["GW cost"]))
         assert _rel(Ts[l], Tref[l]) < RTOL
-    # the truncated copy (40 of 48 rotated coordinates) still identifies most of the permutation
-    assert (Ts[0].argmax(1) == np.argsort(perm)).mean() > 0.9
+    assert (Tref[0].argmax(1) == np.argsort(perm)).mean() > 0.9  # the isometric copy is identified ...
+    assert (Ts[0].argmax(1) == Tref[0].argmax(1)).all()           # ... by both
     # CUDA tensors in -> couplings stay on the device
     Tt, _ = b200ot.get_coupling_egw_ott_fixed(({0: _dev(Xd[1], cuda_dev)}, {0: _dev(Yd[1], cuda_dev)}), eps=5e-2)
     assert Tt[0].is_cuda and Tt[0].shape == (7, 9)
