@@ -25,6 +25,8 @@ Parity status
   flavours **parity is unpinned**: they are restatements of the published
   algorithms anchored on the reference's call sites
   (``MRI_PET_OT_nojax.py:143``, ``perturbot/perturbot/match/fot.py:129-134``).
+* ``cotl_sinkhorn`` (BCD shell of ``cotl_numpy``, ``perturbot/perturbot/match/cot_labels.py:14-225``) is PINNED the
+  same way (reference function compiled from its AST, inner ``linear.solve`` bound to ``sinkhorn_log_ott``).
 * ``egw_ott`` restates ott-jax 0.6.0 ``GromovWasserstein`` (square loss, constant epsilon, warm-started inner
   Sinkhorn) as called at ``MRI_PET_OT_OT_per_epoch_attn.py:155-175``; same situation, **parity unpinned**.
 """
@@ -38,7 +40,7 @@ __all__ = [
     "sinkhorn_log", "sinkhorn_log_ott", "plan_from_potentials", "fot_bcd_ott",
     "get_feature_coupling_pot", "get_coupling_fot", "plan_guard_rownorm",
     "apply_plan_T", "barycentric", "cosine_loss", "ot_cost", "envelope_grads", "foscttm",
-    "group_features_by_label", "egw_ott", "get_coupling_egw_ott_fixed",
+    "group_features_by_label", "egw_ott", "get_coupling_egw_ott_fixed", "cotl_sinkhorn",
 ]
 
 
@@ -378,6 +380,59 @@ def get_coupling_fot(data, Ts, eps=5e-3):
     Y = np.concatenate([Y_dict[l] for l in keys])
     Tv, cost, lg = fot_bcd_ott(X, Y, Ts, reg2=eps, niter=2000, log=True)
     return Tv, lg
+
+
+# --------------------------------------------------------------------------
+# label-constrained entropic COOT
+# --------------------------------------------------------------------------
+def cotl_sinkhorn(X_dict, Y_dict, reg=5e-3, niter=2000, log=False):
+    """``cotl_numpy(algo="sinkhorn", algo2="sinkhorn")`` (``perturbot/perturbot/match/cot_labels.py:14-225``), the
+    solver behind ``get_coupling_cotl_sinkhorn`` (:283-341).  Block coordinate descent: per label a sample coupling
+    on ``M_k = constC_s - hC1_s Tv hC2_s^T`` (:172), then ONE feature coupling on the sum over labels of
+    ``constC_v - hC1_v Ts_k hC2_v^T`` (:190-193), both through ott ``linear.solve(Geometry(cost_matrix, epsilon=reg,
+    scale_cost="max_cost"), max_iterations=2000)`` -- the feature solve also uses ``reg``, ``reg2`` is never read
+    (:201).  Default weights (:107-127): features weighted by their column sums when the data are non-negative,
+    else uniform; samples uniform per label.  ``Tsold = Ts`` aliases the dict (:162), so ``delta`` only sees the
+    change of ``Tv`` (:209-211); exit on ``delta < 1e-16`` or ``|cost_old - cost| < 1e-7`` (:219).  PINNED against the
+    reference function executed in the build container (``tests/golden/cotl_sinkhorn.npz``)."""
+    labels = list(X_dict.keys())
+    X_dict = {k: np.asarray(X_dict[k], dtype=np.float64) for k in labels}
+    Y_dict = {k: np.asarray(Y_dict[k], dtype=np.float64) for k in labels}
+    X = np.concatenate([X_dict[k] for k in labels], axis=0)
+    Y = np.concatenate([Y_dict[k] for k in labels], axis=0)
+    v1 = X.sum(0) / X.sum() if (X >= 0).all() else np.ones(X.shape[1]) / X.shape[1]
+    v2 = Y.sum(0) / Y.sum() if (Y >= 0).all() else np.ones(Y.shape[1]) / Y.shape[1]
+    w1 = {k: np.ones(X_dict[k].shape[0]) / X_dict[k].shape[0] for k in labels}
+    w2 = {k: np.ones(Y_dict[k].shape[0]) / Y_dict[k].shape[0] for k in labels}
+    Ts = {k: np.outer(w1[k], w2[k]) for k in labels}
+    d1, d2 = X.shape[1], Y.shape[1]
+    Tv = np.ones((d1, d2)) / (d1 * d2)
+    cs, cv = {}, {}
+    for k in labels:
+        cs[k] = init_matrix(X_dict[k], Y_dict[k], v1, v2)
+        cv[k] = init_matrix(X_dict[k].T, Y_dict[k].T, w1[k], w2[k])
+    cost = np.inf
+    costs = []
+    for _ in range(niter):
+        Tv_old, cost_old = Tv, cost
+        for k in labels:
+            constC, hC1, hC2 = cs[k]
+            Ts[k] = sinkhorn_log_ott(constC - hC1 @ Tv @ hC2.T, reg)
+        M = 0
+        for k in labels:
+            constC, hC1, hC2 = cv[k]
+            M = M + constC - hC1 @ Ts[k] @ hC2.T
+        Tv = sinkhorn_log_ott(M, reg)
+        if not abs(Tv.sum() - 1.0) < 1e-8:
+            Tv = Tv / Tv.sum()
+        delta = np.linalg.norm(Tv - Tv_old)
+        cost = float(np.sum(M * Tv))
+        costs.append(cost)
+        if delta < 1e-16 or abs(cost_old - cost) < 1e-7:
+            break
+    if log:
+        return Ts, Tv, cost, {"cost": costs}
+    return Ts, Tv, cost
 
 
 # --------------------------------------------------------------------------

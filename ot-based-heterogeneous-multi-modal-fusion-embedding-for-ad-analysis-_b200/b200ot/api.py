@@ -12,6 +12,7 @@ repository), so a training script swaps one import:
     mdict_to_matrix(M_dict, src, tgt)                baseline_models_fusion.py:233-239
     init_matrix_np(X1, X2, v1, v2)                   perturbot/perturbot/match/utils.py:125-184
     get_coupling_egw_ott_fixed(data, eps, ...)       MRI_PET_OT_OT_per_epoch_attn.py:129-186
+    cotl_numpy / get_coupling_cotl_sinkhorn          perturbot/perturbot/match/cot_labels.py:14-341
 
 Inputs may be NumPy arrays (as in the reference: copied to the GPU, result copied
 back as NumPy in the input dtype) or torch tensors (CPU: same; CUDA: everything
@@ -346,6 +347,97 @@ def group_features_by_label(y, p, max_samples_per_label=None):
             arr = arr[:max_samples_per_label]
         out[int(label)] = arr
     return out
+
+
+def cotl_numpy(X_dict, Y_dict, w1=None, w2=None, v1=None, v2=None, niter=100, algo="emd", reg=0.2, algo2="emd",
+               reg2=0.2, verbose=True, log=False, random_init=False, C_lin=None, *, device=None):
+    """Drop-in for ``cotl_numpy`` (perturbot/perturbot/match/cot_labels.py:14-225) in its entropic form
+    (``algo="sinkhorn", algo2="sinkhorn"``, what ``get_coupling_cotl_sinkhorn`` runs): label-constrained COOT by block
+    coordinate descent.  Per label a sample coupling on ``constC_s - hC1_s Tv hC2_s^T`` (:172), then one feature
+    coupling on the sum over labels of ``constC_v - hC1_v Ts_k hC2_v^T`` (:190-193); every cost is built on the GPU
+    (``b200ot_fot_cost``) and every solve is the engine's ott-flavoured ``linear_solve``; couplings stay on the
+    device between rounds.  Reference quirks kept: the feature solve uses ``reg`` (``reg2`` is never read, :201);
+    ``Tsold = Ts`` aliases the dict so ``delta`` only sees ``Tv`` (:162,209-211); exit on ``delta < 1e-16`` or
+    ``|cost_old - cost| < 1e-7`` (:219).  The ``"emd"`` variants are POT's network simplex and are not served."""
+    if algo != "sinkhorn" or algo2 != "sinkhorn":
+        raise B200OTError("cotl_numpy: only algo='sinkhorn', algo2='sinkhorn' run on the B200 engine "
+                          "('emd' is POT's network-simplex solver)")
+    if random_init:
+        raise B200OTError("cotl_numpy: random_init needs scipy's sparse gamma initialisation and is not served")
+    labels = list(X_dict.keys())
+    if sorted(labels) != sorted(Y_dict.keys()):
+        raise AssertionError("Labels don't match in y1 & y2.")
+    cv = _Conv(X_dict[labels[0]], device)
+    dev = cv.device
+    Xd = {k: cv.to_dev(X_dict[k]).contiguous() for k in labels}
+    Yd = {k: cv.to_dev(Y_dict[k]).contiguous() for k in labels}
+    Xt = {k: Xd[k].t().contiguous() for k in labels}
+    Yt = {k: Yd[k].t().contiguous() for k in labels}
+    d1, d2 = Xd[labels[0]].shape[1], Yd[labels[0]].shape[1]
+
+    def feature_weights(v, parts, d):
+        if v is not None:
+            return cv.to_dev(v)
+        allx = torch.cat([parts[k] for k in labels], dim=0).double()
+        if bool((allx >= 0).all()):
+            return (allx.sum(0) / allx.sum()).float()
+        return torch.full((d,), 1.0 / d, dtype=torch.float32, device=dev)
+
+    v1d, v2d = feature_weights(v1, Xd, d1), feature_weights(v2, Yd, d2)
+    w1d = {k: (cv.to_dev(w1[k]) if w1 is not None else _uniform(Xd[k].shape[0], dev)) for k in labels}
+    w2d = {k: (cv.to_dev(w2[k]) if w2 is not None else _uniform(Yd[k].shape[0], dev)) for k in labels}
+    Clin = None if C_lin is None else cv.to_dev(C_lin)
+    Ts = {k: torch.full((Xd[k].shape[0], Yd[k].shape[0]), 1.0 / (Xd[k].shape[0] * Yd[k].shape[0]),
+                        dtype=torch.float32, device=dev) for k in labels}
+    Tv = torch.full((d1, d2), 1.0 / (d1 * d2), dtype=torch.float32, device=dev)
+    cost = float("inf")
+    log_out = {"cost": []}
+    for i in range(int(niter)):
+        Tv_old, cost_old = Tv, cost
+        for k in labels:  # sample OT per label: rows of the transposed data play the role of features
+            M_k = ops.fot_cost(Xt[k], Yt[k], Tv, v1d, v2d)
+            if Clin is not None:
+                M_k = M_k + Clin
+            Ts[k] = linear_solve(Geometry(cost_matrix=M_k, epsilon=reg, scale_cost="max_cost"),
+                                 max_iterations=2000).matrix
+        M = None
+        for k in labels:  # global feature OT on the summed cost
+            Mk = ops.fot_cost(Xd[k], Yd[k], Ts[k], w1d[k], w2d[k])
+            M = Mk if M is None else M + Mk
+        Tv = linear_solve(Geometry(cost_matrix=M, epsilon=reg, scale_cost="max_cost"), max_iterations=2000).matrix
+        tot = float(Tv.double().sum())
+        if not abs(tot - 1.0) < 1e-8:
+            Tv = (Tv.double() / tot).float()
+        delta = float(torch.linalg.norm((Tv - Tv_old).double()))
+        cost = float((M.double() * Tv.double()).sum())
+        if log:
+            log_out["cost"].append(cost)
+        if verbose:
+            print(f"It {i} Delta: {delta}  Loss: {cost}")
+        if delta < 1e-16 or abs(cost_old - cost) < 1e-7:
+            if verbose:
+                print("converged at iter ", i)
+            break
+    Ts_out = {k: cv.back(Ts[k]) for k in labels}
+    if log:
+        return Ts_out, cv.back(Tv), cost, log_out
+    return Ts_out, cv.back(Tv), cost
+
+
+def get_coupling_cotl_sinkhorn(data, eps: float = 5e-3, eps2: Optional[float] = None, *, device=None):
+    """Drop-in for ``get_coupling_cotl_sinkhorn`` (perturbot/perturbot/match/cot_labels.py:283-341):
+    ``(Ts per label, log)``, or ``(-1, -1)`` on a floating-point failure like the reference (:337-338)."""
+    X_dict, Y_dict = data
+    start = time.time()
+    if eps2 is None:
+        eps2 = eps
+    try:
+        Ts, Tv, cost, log = cotl_numpy(X_dict, Y_dict, algo="sinkhorn", reg=eps, algo2="sinkhorn", reg2=eps2,
+                                       log=True, niter=2000, verbose=False, device=device)
+    except FloatingPointError:
+        return -1, -1
+    log["time"] = time.time() - start
+    return Ts, log
 
 
 def get_coupling_egw_ott_fixed(data, eps: float = 5e-3, gw_max_iterations: int = 2000,

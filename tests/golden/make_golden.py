@@ -18,7 +18,9 @@ What is executed, unmodified, from /root/reference:
     restatement of ott-jax 0.6.0 ``linear.solve`` -- so the cost construction,
     Ts normalisation, swapped marginals and BCD exit rule in the golden are the
     reference's, the inner solve is the restatement;
-  * ``mdict_to_matrix`` (``baseline_models_fusion.py:233-239``), compiled from the AST.
+  * ``mdict_to_matrix`` (``baseline_models_fusion.py:233-239``), compiled from the AST;
+  * ``cotl_numpy`` (``perturbot/perturbot/match/cot_labels.py:14-225``), compiled from the AST with the same
+    stubs as ``fot_numpy`` (``--cotl``).
 
 No reference source text is copied into this repository: the functions are
 compiled in memory from the read-only tree and only their numerical outputs are
@@ -89,9 +91,55 @@ def extras():
     print("metrics_helpers.npz written:", fos.mean(), {k: v.shape for k, v in grouped.items()})
 
 
+def cotl():
+    """Case 8: label-constrained entropic COOT, ``cotl_numpy(algo="sinkhorn", algo2="sinkhorn")``
+    (perturbot/perturbot/match/cot_labels.py:14-225, what get_coupling_cotl_sinkhorn :283-341 runs), compiled from
+    the reference's AST.  ``init_matrix_np`` is the reference's own (imported by file path); ``ott`` (not installed)
+    is bound to the oracle's restatement of ``linear.solve``, so the BCD shell -- cost construction per label, the
+    summed feature cost, the (aliased) delta, the renormalisation and the exit rule -- is the reference's and the
+    inner solves are the restatement."""
+    import contextlib
+    import io
+    ref_utils = load_ref_utils()
+
+    class _Geom:
+        def __init__(self, cost_matrix, epsilon, scale_cost):
+            self.cost_matrix, self.epsilon, self.scale_cost = cost_matrix, epsilon, scale_cost
+
+    class _Out:
+        def __init__(self, matrix):
+            self.matrix = matrix
+
+    def _solve(geom, max_iterations=2000, **kw):
+        return _Out(orc.sinkhorn_log_ott(geom.cost_matrix, geom.epsilon, max_iterations=max_iterations,
+                                         scale_cost=geom.scale_cost))
+
+    ns = {"np": np, "init_matrix_np": ref_utils.init_matrix_np, "random_gamma_init": ref_utils.random_gamma_init,
+          "linear": types.SimpleNamespace(solve=_solve), "geometry": types.SimpleNamespace(Geometry=_Geom),
+          "pot": None}
+    ref_cotl = extract_function(os.path.join(REF, "perturbot/perturbot/match/cot_labels.py"), "cotl_numpy", ns)
+    rng = np.random.default_rng(31)
+    d1, d2 = 12, 9
+    Xd, Yd = {}, {}
+    for k, (nk, mk) in {2: (14, 11), 0: (9, 9), 5: (6, 10)}.items():  # unsorted insertion order, ragged sizes
+        base = rng.standard_normal((nk, d1)) + k
+        Xd[k] = base
+        Yd[k] = (rng.standard_normal((mk, d1)) + k)[:, :d2] * 1.5
+    with contextlib.redirect_stdout(io.StringIO()):
+        Ts, Tv, cost, lg = ref_cotl(Xd, Yd, niter=2000, algo="sinkhorn", reg=5e-2, algo2="sinkhorn", reg2=5e-2,
+                                    verbose=False, log=True)
+    save = {"reg": 5e-2, "Tv": Tv, "cost": cost, "costs": np.array(lg["cost"]), "keys": np.array(list(Xd.keys()))}
+    for k in Xd:
+        save[f"X{k}"], save[f"Y{k}"], save[f"Ts{k}"] = Xd[k], Yd[k], Ts[k]
+    np.savez_compressed(os.path.join(HERE, "cotl_sinkhorn.npz"), **save)
+    print("cotl_sinkhorn.npz written: rounds", len(lg["cost"]), "cost", cost)
+
+
 def main():
     if "--extras" in sys.argv:
         return extras()
+    if "--cotl" in sys.argv:
+        return cotl()
     ref_utils = load_ref_utils()
     out = {}
 
@@ -202,6 +250,7 @@ def main():
     out["c3"] = (len(lg3["err"]), len(lg3c["err"]))
     print("golden vectors written:", out)
     extras()
+    cotl()
 
 
 if __name__ == "__main__":

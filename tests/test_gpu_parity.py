@@ -671,3 +671,29 @@ def test_entropic_gromov_wasserstein_per_label(cuda_dev):
     assert Tt[0].is_cuda and Tt[0].shape == (7, 9)
     np.testing.assert_allclose(Tt[0].double().cpu().numpy(), orc.egw_ott(Xd[1], Yd[1], eps=5e-2)[0], rtol=0,
                                atol=RTOL * float(Tt[0].max()))
+
+
+def test_label_constrained_coot_bcd_matches_reference(cuda_dev, golden_dir):
+    """cotl_numpy(algo="sinkhorn", algo2="sinkhorn") (perturbot/perturbot/match/cot_labels.py:14-225) against the
+    golden produced by the reference's own function.  The reference's exit rule (|cost_old - cost| < 1e-7 on a cost
+    of ~17) is below fp32 resolution, so the number of BCD rounds may differ by a few; costs, the feature coupling
+    and the sample couplings must agree."""
+    import b200ot
+    g = _load(golden_dir, "cotl_sinkhorn.npz")
+    keys = [int(k) for k in g["keys"]]
+    Xd = {k: g[f"X{k}"] for k in keys}
+    Yd = {k: g[f"Y{k}"] for k in keys}
+    Ts, Tv, cost, lg = b200ot.cotl_numpy(Xd, Yd, niter=2000, algo="sinkhorn", reg=float(g["reg"]), algo2="sinkhorn",
+                                         reg2=float(g["reg"]), verbose=False, log=True)
+    assert list(Ts.keys()) == keys and Tv.shape == g["Tv"].shape and Tv.dtype == np.float64
+    assert 3 <= len(lg["cost"]) <= 4 * len(g["costs"])
+    assert abs(cost - float(g["cost"])) < 1e-3 * abs(float(g["cost"]))
+    k0 = min(len(lg["cost"]), len(g["costs"]), 10)
+    np.testing.assert_allclose(lg["cost"][:k0], g["costs"][:k0], rtol=1e-4)  # the early rounds are far from the floor
+    assert _rel(Tv, g["Tv"]) < 5e-3
+    for k in keys:
+        assert _rel(Ts[k], g[f"Ts{k}"]) < 5e-3
+    Ts2, log2 = b200ot.get_coupling_cotl_sinkhorn((Xd, Yd), eps=float(g["reg"]))
+    assert set(Ts2) == set(keys) and "time" in log2 and len(log2["cost"]) == len(lg["cost"])
+    with pytest.raises(b200ot.B200OTError):
+        b200ot.cotl_numpy(Xd, Yd)  # the default 'emd' variants are POT's network simplex

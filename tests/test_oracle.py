@@ -181,3 +181,18 @@ def test_egw_oracle_recovers_an_isometric_copy_and_keeps_marginals():
     assert abs(c[-2] - c[-1]) <= 1e-8 + 1e-3 * abs(c[-1])
     Ts, log = orc.get_coupling_egw_ott_fixed(({0: X[:10], 1: X[10:25]}, {0: Y[:12], 1: Y[12:30]}))
     assert Ts[0].shape == (10, 12) and Ts[1].shape == (15, 18) and set(log) == {0, 1}
+
+
+def test_cotl_sinkhorn_matches_the_reference_function(golden_dir):
+    """BCD shell of cotl_numpy (cot_labels.py:14-225) against the golden produced by the reference's own function:
+    same number of rounds, same cost trace, same couplings."""
+    g = np.load(os.path.join(golden_dir, "cotl_sinkhorn.npz"))
+    keys = [int(k) for k in g["keys"]]
+    Xd = {k: g[f"X{k}"] for k in keys}
+    Yd = {k: g[f"Y{k}"] for k in keys}
+    Ts, Tv, cost, lg = orc.cotl_sinkhorn(Xd, Yd, reg=float(g["reg"]), niter=2000, log=True)
+    assert len(lg["cost"]) == len(g["costs"])
+    np.testing.assert_allclose(lg["cost"], g["costs"], rtol=1e-10)
+    np.testing.assert_allclose(Tv, g["Tv"], rtol=0, atol=1e-12)
+    for k in keys:
+        np.testing.assert_allclose(Ts[k], g[f"Ts{k}"], rtol=0, atol=1e-12)
