@@ -29,7 +29,8 @@
 namespace b200ot {
 
 constexpr int kResMaxStages = 16;
-constexpr size_t kResSmemMax = 113 * 1024;  // two CTAs per SM
+constexpr size_t kResSmemMax = 113 * 1024;       // two CTAs per SM (T <= 256)
+constexpr size_t kResSmemMaxWide = 232448 - 1024;  // one 512-thread CTA per SM (rows wider than 4096 columns)
 
 struct ResidentArgs {
   const float* C;
@@ -112,7 +113,7 @@ __device__ __forceinline__ float warp_sum_rows(float (&v)[R], int lane) {
 }
 
 template <int T, int NCH, int R>
-__global__ void __launch_bounds__(T, 2) resident_kernel(const ResidentArgs p) {
+__global__ void __launch_bounds__(T, (T > 256 ? 1 : 2)) resident_kernel(const ResidentArgs p) {
   constexpr int CPT = 4 * NCH;
   constexpr int W = T * CPT;  // floats per staged row
   constexpr int NW = T / 32;
@@ -494,7 +495,7 @@ static cudaError_t resident_launch(const ResidentArgs* a, int G, size_t smem, cu
   static bool attr_set = false;  // one flag per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(resident_kernel<T, NCH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kResSmemMax);
+                                         (int)(T > 256 ? kResSmemMaxWide : kResSmemMax));
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -516,6 +517,10 @@ static cudaError_t resident_launch(const ResidentArgs* a, int G, size_t smem, cu
 static cudaError_t resident_dispatch(int T, int NCH, const ResidentArgs* a, int G, size_t smem, cudaStream_t s,
                                      int* occ_out) {
   if (T == 128) return resident_launch<128, 1, 8>(a, G, smem, s, occ_out);
+  if (T == 512) {
+    if (NCH == 3) return resident_launch<512, 3, 2>(a, G, smem, s, occ_out);
+    return resident_launch<512, 4, 2>(a, G, smem, s, occ_out);
+  }
   switch (NCH) {
     case 1: return resident_launch<256, 1, 8>(a, G, smem, s, occ_out);
     case 2: return resident_launch<256, 2, 4>(a, G, smem, s, occ_out);
@@ -530,9 +535,14 @@ static cudaError_t resident_dispatch(int T, int NCH, const ResidentArgs* a, int 
 
 static bool resident_pick(int n, int m, ResCfg* c) {
   if (n < 1 || m < 4 || (m & 3) || m > kResMaxM) return false;
-  const int T = m <= 512 ? 128 : 256;
+  // rows wider than 4096 columns: one 512-thread CTA per SM keeps two rows per block barrier (16 columns per
+  // thread) where two 256-thread CTAs would be down to one (B200OT_RES_WIDE=0 restores the latter)
+  const char* ew = getenv("B200OT_RES_WIDE");
+  const bool wide = m > 4096 && !(ew && ew[0] == '0');
+  const int T = m <= 512 ? 128 : wide ? 512 : 256;
   const int NCH = (m + 4 * T - 1) / (4 * T);
   const int R = NCH == 1 ? 8 : NCH == 2 ? 4 : NCH <= 4 ? 2 : 1;
+  const size_t smem_cap = T > 256 ? kResSmemMaxWide : kResSmemMax;
   const int ngroups = (n + R - 1) / R;
   const size_t stage = (size_t)R * T * 4 * NCH * sizeof(float);
   auto fixed_for = [&](int rows_cap) {
@@ -540,11 +550,11 @@ static bool resident_pick(int n, int m, ResCfg* c) {
            3 * (size_t)rows_cap * 4 + 128;
   };
   // CTAs per SM the hardware will co-schedule for this instantiation (cached): the cooperative grid may not exceed it
-  static int occ_cache[2][9];
-  int& occ = occ_cache[T == 128 ? 0 : 1][NCH];
+  static int occ_cache[3][9];
+  int& occ = occ_cache[T == 128 ? 0 : T == 256 ? 1 : 2][NCH];
   if (occ == 0) {
     int v = 0;
-    if (resident_dispatch(T, NCH, nullptr, 0, kResSmemMax, nullptr, &v) != cudaSuccess) {
+    if (resident_dispatch(T, NCH, nullptr, 0, smem_cap, nullptr, &v) != cudaSuccess) {
       (void)cudaGetLastError();
       v = -1;
     }
@@ -558,8 +568,8 @@ static bool resident_pick(int n, int m, ResCfg* c) {
   const int cnt_max = (ngroups + G - 1) / G;
   const int rows_cap = cnt_max * R;
   const size_t fixed = fixed_for(rows_cap);
-  if (fixed + 2 * stage > kResSmemMax) return false;
-  int NG = (int)((kResSmemMax - fixed) / stage);
+  if (fixed + 2 * stage > smem_cap) return false;
+  int NG = (int)((smem_cap - fixed) / stage);
   if (NG > kResMaxStages) NG = kResMaxStages;
   if (NG > cnt_max) NG = cnt_max;
   if (NG < 2 && cnt_max > NG) return false;

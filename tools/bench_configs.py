@@ -114,8 +114,11 @@ def main():
         an = torch.full((nn,), 1.0 / nn, device=dev)
         rec = {}
         for label, env in (("resident", {"B200OT_RESIDENT": "1"}), ("resident_forward_only", {"B200OT_RESIDENT": "1", "B200OT_RES_SNAKE": "0"}),
+                           ("resident_2x256_threads", {"B200OT_RESIDENT": "1", "B200OT_RES_WIDE": "0"}),
                            ("per_sweep_launches", {"B200OT_RESIDENT": "0"})):
             if label == "resident_forward_only" and nn < 4096:
+                continue
+            if label == "resident_2x256_threads" and nn <= 4096:
                 continue
             os.environ.update(env)
             try:
