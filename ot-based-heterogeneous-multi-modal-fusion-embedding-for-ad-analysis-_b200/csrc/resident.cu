@@ -54,6 +54,7 @@ struct ResidentArgs {
   int snake;        // alternate the sweep direction when the block does not fit the ring
   int evict_first;  // L2 evict-first hint on the bulk copies
   int red_groups;   // thread groups of the slice fold (power of two)
+  int spin_ns;      // back-off between polls of a word that is not there yet
 };
 
 // ---- tagged words: the exchange between CTAs needs no barrier and no fence ------------------------------------
@@ -80,12 +81,12 @@ __device__ __forceinline__ void st_tag2(u64* p, u64 a, u64 b) {
 }
 __device__ __forceinline__ bool tag_is(u64 v, unsigned tag) { return (unsigned)(v >> 32) == tag; }
 // a producer that never shows up traps instead of hanging the GPU box
-__device__ __forceinline__ void spin_guard(long long& t0) {
+__device__ __forceinline__ void spin_guard(long long& t0, int ns) {
   if (t0 == 0)
     t0 = clock64();
   else if (clock64() - t0 > 4000000000ll)
     __trap();
-  __nanosleep(20);
+  __nanosleep(ns);
 }
 
 // Sum R per-lane values over the warp with (R - 1) + 5 - log2(R) shuffles instead of 5 R: each of the first
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(T, (T > 256 ? 1 : 2)) resident_kernel(const Re
               }
             }
             if (ok) break;
-            spin_guard(t0);
+            spin_guard(t0, p.spin_ns);
           }
 #pragma unroll
           for (int u = 0; u < kFold; ++u)
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(T, (T > 256 ? 1 : 2)) resident_kernel(const Re
           }
         }
         if (ok) break;
-        spin_guard(t0);
+        spin_guard(t0, p.spin_ns);
       }
 #pragma unroll
       for (int cc = 0; cc < kGq; ++cc) {
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(T, (T > 256 ? 1 : 2)) resident_kernel(const Re
         for (;;) {
           ld_poll2(p.err64 + 2 * (size_t)i, lo, hi);
           if (tag_is(lo, tag) && tag_is(hi, tag)) break;
-          spin_guard(t0);
+          spin_guard(t0, p.spin_ns);
         }
         ep += __longlong_as_double((long long)(((u64)(unsigned)hi << 32) | (u64)(unsigned)lo));
       }
@@ -627,6 +628,9 @@ int resident_try_enqueue(const float* C, int ldc, int n, int m, int iters, const
   const char* ee = getenv("B200OT_RES_EVICT");
   a.evict_first = (ee && ee[0] == '1') ? 1 : 0;
   a.red_groups = c.red_groups;
+  const char* ens = getenv("B200OT_RES_SPIN_NS");
+  a.spin_ns = ens ? atoi(ens) : 20;
+  if (a.spin_ns < 0) a.spin_ns = 0;
   for (int left = iters; left > 0;) {
     a.iters = left > kResMaxItersPerLaunch ? kResMaxItersPerLaunch : left;
     left -= a.iters;
