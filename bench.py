@@ -355,7 +355,7 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic(kernel_desc, n_loc, m), "peak_source": peak_src,
                      "note": "achieved = 4*n_local*m bytes per iteration / (step time / iterations); the step time "
-                             "includes the finalize kernel and, for N>1, the NCCL all-reduce"},
+                             "includes the finalize kernel and, for N>1, the exchange of the column sums (peer-memory push or NCCL)"},
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,

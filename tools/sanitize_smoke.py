@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Small invocations of every solver kernel family, meant to run under compute-sanitizer:
+"""Small invocations of every solver kernel family in one short process (a quick "does every kernel family still
+run" check, and the workload to put under compute-sanitizer where that tool is available -- it is closed on the
+round-1 GPU pool, so this script has only been run plain):
 
     compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_smoke.py
 
-Shapes are tiny (the sanitizer serialises the device), but they reach the resident kernel in both ring modes, the
+Shapes are tiny, but they reach the resident kernel in both ring modes, the
 single-sweep cluster kernel, the robust kernels, the peer-exchange kernels (peers emulated on one GPU), the batched
 and Gromov-Wasserstein one-CTA-per-problem kernels and the epilogues.
 """
