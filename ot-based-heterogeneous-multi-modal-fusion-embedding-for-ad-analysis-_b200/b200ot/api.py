@@ -312,7 +312,21 @@ def get_coupling_fot(data, Ts, eps=5e-3, *, device=None, path="auto"):
     Returns ``(Tv, log)``."""
     X_dict, Y_dict = data
     keys = list(X_dict.keys())
-    if isinstance(Ts, dict):
+    if isinstance(Ts, dict) and any(isinstance(v, torch.Tensor) and v.is_cuda for v in Ts.values()):
+        # device-resident caller: the same block-diagonal scatter (rows / columns in first-seen label order are
+        # contiguous blocks) without leaving the GPU
+        dev = next(v.device for v in Ts.values() if isinstance(v, torch.Tensor) and v.is_cuda)
+        nx = [len(X_dict[l]) for l in keys]
+        ny = [len(Y_dict[l]) for l in keys]
+        blk = torch.zeros((sum(nx), sum(ny)), dtype=torch.float64, device=dev)
+        ix = iy = 0
+        for l, a_, b_ in zip(keys, nx, ny):
+            if l in Ts:
+                blk[ix:ix + a_, iy:iy + b_] = torch.as_tensor(Ts[l], device=dev).to(torch.float64)
+            ix += a_
+            iy += b_
+        Ts = blk
+    elif isinstance(Ts, dict):
         Ts = mdict_to_matrix(
             Ts,
             np.concatenate([np.ones(len(X_dict[l])) * l for l in keys]),
@@ -473,6 +487,22 @@ def get_coupling_egw_ott_fixed(data, eps: float = 5e-3, gw_max_iterations: int =
                   "converged_outer": bool(host["converged_outer"][i]), "GW cost": float(host["GW cost"][i]),
                   "inner_iterations": int(host["inner_iterations"][i]), "time": dt, "cost_time": cost_time}
     return out_T, log
+
+
+def compute_pet_to_mri_coupling(mri_features, pet_features, labels, max_samples_per_label=None,
+                                gw_max_iterations: int = 2000, sinkhorn_max_iterations: int = 2000, *, device=None):
+    """The OT part of ``compute_pet_to_mri_coupling`` (MRI_PET_OT_OT_per_epoch_attn.py:940-960), i.e. everything
+    after ``feature_extract``: bucket both modalities by label (``max_samples_per_label`` = ``args.max_jax_samples``),
+    entropic Gromov-Wasserstein sample coupling per label (PET -> MRI), feature coupling ``get_coupling_fot`` on
+    the block-diagonal of those.  With CUDA tensors nothing leaves the device (the reference converts to NumPy,
+    solves on the CPU and copies the d x d coupling back, :943-953,1233-1236).  Returns the (d_pet, d_mri)
+    feature coupling ``T_feature_pet2mri``."""
+    grouped_mri = group_features_by_label(labels, mri_features, max_samples_per_label=max_samples_per_label)
+    grouped_pet = group_features_by_label(labels, pet_features, max_samples_per_label=max_samples_per_label)
+    T_dict, _ = get_coupling_egw_ott_fixed((grouped_pet, grouped_mri), gw_max_iterations=gw_max_iterations,
+                                           sinkhorn_max_iterations=sinkhorn_max_iterations, device=device)
+    T_feature, _ = get_coupling_fot((grouped_pet, grouped_mri), T_dict, device=device)
+    return T_feature
 
 
 def foscttm(Y_pred, Y_true, idx=None, *, device=None):

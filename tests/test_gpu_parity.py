@@ -697,3 +697,26 @@ def test_label_constrained_coot_bcd_matches_reference(cuda_dev, golden_dir):
     assert set(Ts2) == set(keys) and "time" in log2 and len(log2["cost"]) == len(lg["cost"])
     with pytest.raises(b200ot.B200OTError):
         b200ot.cotl_numpy(Xd, Yd)  # the default 'emd' variants are POT's network simplex
+
+
+def test_per_epoch_coupling_pipeline_stays_on_device(cuda_dev):
+    """compute_pet_to_mri_coupling (MRI_PET_OT_OT_per_epoch_attn.py:940-960) after feature_extract: label buckets
+    -> per-label entropic GW (PET -> MRI) -> feature coupling on the block-diagonal, with CUDA tensors end to end,
+    against the same composition of the oracle's restatements."""
+    import b200ot
+    rng = np.random.default_rng(8)
+    N, d = 150, 32
+    labels = rng.integers(0, 3, size=N)
+    mri = np.abs(rng.standard_normal((N, d))).astype(np.float32)
+    pet = np.abs(rng.standard_normal((N, d)) + 0.3 * labels[:, None]).astype(np.float32)
+    T = b200ot.compute_pet_to_mri_coupling(_dev(mri, cuda_dev), _dev(pet, cuda_dev),
+                                           torch.as_tensor(labels, device=cuda_dev), max_samples_per_label=40)
+    assert T.is_cuda and T.shape == (d, d)
+    gm = orc.group_features_by_label(labels, mri, max_samples_per_label=40)
+    gp = orc.group_features_by_label(labels, pet, max_samples_per_label=40)
+    Td, _ = orc.get_coupling_egw_ott_fixed((gp, gm))
+    Tref, _ = orc.get_coupling_fot((gp, gm), Td)
+    assert _rel(T.double().cpu().numpy(), Tref) < RTOL
+    # NumPy in -> NumPy out, like the reference
+    Tn = b200ot.compute_pet_to_mri_coupling(mri, pet, labels, max_samples_per_label=40)
+    assert isinstance(Tn, np.ndarray) and _rel(Tn, Tref) < RTOL
