@@ -288,11 +288,12 @@ class ShardedSinkhorn:
                 else:
                     self.k.run_c(step, self.comm)
                 done += step
-                ev = torch.cuda.Event()
-                ev.record()
-                self._events.append(ev)
-                if len(self._events) > self._lag:
-                    self._events.pop(0).synchronize()
+                if torch.cuda.is_available():
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    self._events.append(ev)
+                    if len(self._events) > self._lag:
+                        self._events.pop(0).synchronize()
             if self.peer is None:
                 self.allreduces += iters
             self.iterations_queued += iters

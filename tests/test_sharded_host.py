@@ -125,3 +125,111 @@ def test_two_rank_gloo_solve_matches_unsharded_oracle(tmp_path, tol):
     P = orc.plan_from_potentials(C, f, parts[0]["g"], 0.1)
     np.testing.assert_allclose(P, Pref, rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(parts[0]["errs"], lg["err"], rtol=1e-6, atol=1e-13)  # float64 noise floor
+
+
+# ---------------------------------------------------------------------------
+# peer-exchange form of the loop (no collective call per iteration)
+# ---------------------------------------------------------------------------
+class FilePeerExchange:
+    """Stand-in for sharded.PeerExchange on CPU: the ranks' exchange buffers are one shared memory-mapped file;
+    words are (value, tag) pairs, slabs [buffer owner][parity][source rank][column], like the CUDA layout."""
+
+    def __init__(self, path, world, rank, m):
+        self.world, self.rank, self.m = world, rank, m
+        self.val = np.memmap(path + ".val", dtype=np.float64, mode="r+", shape=(world, 2, world, m))
+        self.tag = np.memmap(path + ".tag", dtype=np.int64, mode="r+", shape=(world, 2, world, m))
+        self.epoch = 0
+
+    def next_epoch(self):
+        self.epoch = (self.epoch + 1) & 0xFFF
+        return self.epoch
+
+
+class NumpyPeerKernels(NumpyShardKernels):
+    """The push / finalize_peer / run_peer entry points of CudaShardKernels, restated over FilePeerExchange."""
+
+    def _x(self, is_prologue):
+        return 0 if is_prologue else self.it + 1
+
+    def push(self, peer, is_prologue):
+        if self.done:
+            return
+        s = (self.prologue() if is_prologue else self.sweep()).numpy()
+        x = self._x(is_prologue)
+        tag = (peer.epoch << 20) | (x + 1)
+        for dst in range(peer.world):
+            peer.val[dst, x & 1, peer.rank, :] = s
+            peer.tag[dst, x & 1, peer.rank, :] = tag  # value first, tag second: the tag publishes the value
+
+    def finalize_peer(self, peer, is_prologue):
+        if self.done:
+            return
+        x = self._x(is_prologue)
+        tag = (peer.epoch << 20) | (x + 1)
+        import time as _t
+        t0 = _t.time()
+        while not (peer.tag[peer.rank, x & 1] == tag).all():
+            assert _t.time() - t0 < 60, "a peer never pushed"
+            _t.sleep(0.0005)
+        tot = np.zeros(peer.m)
+        for r in range(peer.world):  # rank order: identical bits on every rank
+            tot = tot + np.array(peer.val[peer.rank, x & 1, r, :])
+        self.finalize(torch.from_numpy(tot), is_prologue)
+
+    def run_peer(self, iters, peer):
+        for _ in range(iters):
+            self.push(peer, False)
+            self.finalize_peer(peer, False)
+
+
+def _peer_worker(rank, world, port, n, m, tol, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "ot-based-heterogeneous-multi-modal-fusion-embedding-for-ad-analysis-_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from b200ot.sharded import ShardedSinkhorn, row_range
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, Y = orc.synthetic_embeddings(n, m, 16, config_index=4)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    lo, hi = row_range(n, world, rank)
+    peer = FilePeerExchange(os.path.join(out_dir, "xbuf"), world, rank, m)
+    results = []
+    for solve in range(2):  # the second solve reuses the buffers under a new epoch
+        k = NumpyPeerKernels(C[lo:hi], a[lo:hi], b, 0.1, 200, tol, 10, 0)
+        drv = ShardedSinkhorn(k, peer=peer)
+        assert drv.peer is peer and drv.c_loop
+        f, g, info = drv.solve(200, check_every=10, check_phase=0)
+        assert drv.allreduces == 0  # no collective in the loop
+        results.append((f, g, info))
+        dist.barrier()
+    assert peer.epoch == 2
+    (f, g, info), (f2, g2, info2) = results
+    assert np.array_equal(g, g2) and np.array_equal(f, f2) and info["n_iter"] == info2["n_iter"]
+    np.savez(os.path.join(out_dir, f"peer{rank}.npz"), f=f, g=g, n_iter=info["n_iter"], converged=info["converged"])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("tol", [1e-3, 0.0])
+def test_two_rank_peer_exchange_loop_matches_unsharded_oracle(tmp_path, tol):
+    """ShardedSinkhorn with a PeerExchange: start() bumps the epoch and pushes the prologue, run() queues run_peer
+    chunks, every rank folds the slabs in rank order and takes the same decisions; no all-reduce is issued."""
+    n, m, world = 50, 36, 2
+    for suffix, dt in ((".val", np.float64), (".tag", np.int64)):
+        np.memmap(str(tmp_path / ("xbuf" + suffix)), dtype=dt, mode="w+", shape=(world, 2, world, m)).flush()
+    port = 30100 + (os.getpid() % 500) + (0 if tol else 1)
+    mp.spawn(_peer_worker, args=(world, port, n, m, tol, str(tmp_path)), nprocs=world, join=True)
+    X, Y = orc.synthetic_embeddings(n, m, 16, config_index=4)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    Pref, lg = orc.sinkhorn_log(C, a, b, 0.1, max_iter=200, tol=tol, err_norm="l1", check_every=10, check_phase=0,
+                                log=True)
+    parts = [np.load(tmp_path / f"peer{r}.npz") for r in range(world)]
+    assert int(parts[0]["n_iter"]) == int(parts[1]["n_iter"]) == lg["n_iter"]
+    assert bool(parts[0]["converged"]) == lg["converged"]
+    np.testing.assert_array_equal(parts[0]["g"], parts[1]["g"])
+    f = np.concatenate([p["f"] for p in parts])
+    np.testing.assert_allclose(orc.plan_from_potentials(C, f, parts[0]["g"], 0.1), Pref, rtol=1e-9, atol=1e-15)
