@@ -135,65 +135,72 @@ __global__ void __launch_bounds__(BT) sinkhorn_batched_kernel(const BatchedArgs 
     }
     __syncthreads();
 
+    // Both mat-vecs use the same layout: thread (index, part) sums a strided slice (PARTS = BT / 64 slices for up
+    // to 64 indices, 2 for up to 128), the slices are folded through shared memory by the first threads, which also
+    // keep the previous iterate and apply POT's numerical guard.  Four block barriers per iteration.  (The first
+    // version ran the row pass one warp per row: eight serial rows per warp, each with a double-precision shuffle
+    // reduction and a division -- 5k cycles per iteration where the arithmetic needs ~300.)
+    const int cparts = BT / m > 0 ? BT / m : 1;
+    const int rparts = BT / n > 0 ? BT / n : 1;
     int cpt = 0;
     double err = 1.0;
     while (cpt < p.max_iter) {
-      // save previous iterates
-      for (int i = tid; i < n; i += BT) up[i] = u[i];
-      for (int j = tid; j < m; j += BT) vp[j] = v[j];
-      // K^T u : thread (j, part) sums a slice of rows; parts folded through shared memory
+      // ---- v = b / (K^T u) ----
       {
-        const int parts = BT / m > 0 ? BT / m : 1;  // m <= 128 -> parts >= 2
         const int j = tid % m, part = tid / m;
         double s = 0.0;
-        if (part < parts)
-          for (int i = part; i < n; i += parts) s = fma(K[i * ldk + j], u[i], s);
+        if (part < cparts)
+          for (int i = part; i < n; i += cparts) s = fma(K[i * ldk + j], u[i], s);
         scratch[tid] = s;
         __syncthreads();
         if (tid < m) {
           double t = 0.0;
-          for (int q = 0; q < parts; ++q) t += scratch[q * m + tid];
+          for (int q = 0; q < cparts; ++q) t += scratch[q * m + tid];
+          vp[tid] = v[tid];
           ktu[tid] = t;
-          v[tid] = p.b[tid] / t;
+          const double vn = (double)p.b[tid] / t;
+          v[tid] = vn;
+          if (t == 0.0 || bad_value(vn)) flag_sh = 1;
         }
         __syncthreads();
       }
-      // u = 1 / (Kp v), Kp = (1/a) K : one warp per row, lanes across columns
-      for (int i = warp; i < n; i += NW) {
-        const double ia = 1.0 / (double)p.a[i];
-        double s = 0.0;
-        for (int j = lane; j < m; j += 32) s = fma(ia * K[i * ldk + j], v[j], s);
-        s = warp_sum(s);
-        if (lane == 0) u[i] = 1.0 / s;
-      }
-      __syncthreads();
-      // numerical guard (utils.py:55-79)
+      // ---- u = 1 / (Kp v), Kp = (1/a) K ----
       {
-        int bad = 0;
-        for (int j = tid; j < m; j += BT) bad |= (ktu[j] == 0.0) || bad_value(v[j]);
-        for (int i = tid; i < n; i += BT) bad |= bad_value(u[i]);
-        if (bad) flag_sh = 1;
+        const int i = tid % n, part = tid / n;
+        double s = 0.0;
+        if (part < rparts)
+          for (int j = part; j < m; j += rparts) s = fma(K[i * ldk + j], v[j], s);
+        scratch[tid] = s;
         __syncthreads();
-        if (flag_sh) {
-          for (int i = tid; i < n; i += BT) u[i] = up[i];
-          for (int j = tid; j < m; j += BT) v[j] = vp[j];
-          __syncthreads();
-          break;
+        if (tid < n) {
+          double t = 0.0;
+          for (int q = 0; q < rparts; ++q) t += scratch[q * n + tid];
+          up[tid] = u[tid];
+          const double un = 1.0 / (t / (double)p.a[tid]);
+          u[tid] = un;
+          if (bad_value(un)) flag_sh = 1;
         }
+        __syncthreads();
+      }
+      // numerical guard (utils.py:55-79): restore the previous iterates and stop
+      if (flag_sh) {
+        for (int i = tid; i < n; i += BT) u[i] = up[i];
+        for (int j = tid; j < m; j += BT) v[j] = vp[j];
+        __syncthreads();
+        break;
       }
       if (cpt % p.check_every == ((p.check_phase + p.check_every - 1) % p.check_every)) {
         // column marginal of diag(u) K diag(v)
-        const int parts = BT / m > 0 ? BT / m : 1;
         const int j = tid % m, part = tid / m;
         double s = 0.0;
-        if (part < parts)
-          for (int i = part; i < n; i += parts) s = fma(u[i], K[i * ldk + j] * v[j], s);
+        if (part < cparts)
+          for (int i = part; i < n; i += cparts) s = fma(u[i], K[i * ldk + j] * v[j], s);
         scratch[tid] = s;
         __syncthreads();
         double e = 0.0;
         if (tid < m) {
           double t = 0.0;
-          for (int q = 0; q < parts; ++q) t += scratch[q * m + tid];
+          for (int q = 0; q < cparts; ++q) t += scratch[q * m + tid];
           const double dlt = t - (double)p.b[tid];
           e = p.err_norm == B200OT_NORM_L1 ? fabs(dlt) : dlt * dlt;
         }
