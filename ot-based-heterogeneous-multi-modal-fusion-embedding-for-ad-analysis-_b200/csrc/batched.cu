@@ -148,10 +148,18 @@ __global__ void __launch_bounds__(BT) sinkhorn_batched_kernel(const BatchedArgs 
       // ---- v = b / (K^T u) ----
       {
         const int j = tid % m, part = tid / m;
-        double s = 0.0;
-        if (part < cparts)
-          for (int i = part; i < n; i += cparts) s = fma(K[i * ldk + j], u[i], s);
-        scratch[tid] = s;
+        double s0 = 0.0, s1 = 0.0;  // two chains: the loads of one overlap the FMA latency of the other
+        if (part < cparts) {
+          const double* kp = K + part * ldk + j;
+          const int step = cparts * ldk;
+          int i = part;
+          for (; i + cparts < n; i += 2 * cparts, kp += 2 * step) {
+            s0 = fma(kp[0], u[i], s0);
+            s1 = fma(kp[step], u[i + cparts], s1);
+          }
+          if (i < n) s0 = fma(kp[0], u[i], s0);
+        }
+        scratch[tid] = s0 + s1;
         __syncthreads();
         if (tid < m) {
           double t = 0.0;
@@ -167,16 +175,23 @@ __global__ void __launch_bounds__(BT) sinkhorn_batched_kernel(const BatchedArgs 
       // ---- u = 1 / (Kp v), Kp = (1/a) K ----
       {
         const int i = tid % n, part = tid / n;
-        double s = 0.0;
-        if (part < rparts)
-          for (int j = part; j < m; j += rparts) s = fma(K[i * ldk + j], v[j], s);
-        scratch[tid] = s;
+        double s0 = 0.0, s1 = 0.0;
+        if (part < rparts) {
+          const double* kp = K + i * ldk;
+          int j = part;
+          for (; j + rparts < m; j += 2 * rparts) {
+            s0 = fma(kp[j], v[j], s0);
+            s1 = fma(kp[j + rparts], v[j + rparts], s1);
+          }
+          if (j < m) s0 = fma(kp[j], v[j], s0);
+        }
+        scratch[tid] = s0 + s1;
         __syncthreads();
         if (tid < n) {
           double t = 0.0;
           for (int q = 0; q < rparts; ++q) t += scratch[q * n + tid];
           up[tid] = u[tid];
-          const double un = 1.0 / (t / (double)p.a[tid]);
+          const double un = (double)p.a[tid] / t;  // = 1 / (Kp v)_i
           u[tid] = un;
           if (bad_value(un)) flag_sh = 1;
         }
