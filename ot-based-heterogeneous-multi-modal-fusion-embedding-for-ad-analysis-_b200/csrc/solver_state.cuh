@@ -53,7 +53,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 static_assert(sizeof(State) <= 256, "state block");
 
 struct WsLayout {
-  size_t state, gbar, err_hist, errpart, fs, gs0, gs1, a, b, log2b, snap_fs, snap_gs, part_sum, part_max,
+  size_t state, err_hist, errpart, fs, gs0, gs1, a, b, log2b, snap_fs, snap_gs, part_sum, part_max,
       res_ll, res_ll_bytes, total;
   size_t m_pad, n_pad;
 };
@@ -66,8 +66,6 @@ static inline WsLayout ws_layout(int n, int m) {
   L.n_pad = align_up((size_t)n, 64);
   size_t off = 0;
   L.state = off;
-  off += 256;
-  L.gbar = off;  // spare 256-byte line (was: grid-barrier counter of the first resident kernel)
   off += 256;
   L.err_hist = off;
   off += kErrHistCap * sizeof(float);
@@ -98,7 +96,6 @@ static inline WsLayout ws_layout(int n, int m) {
 
 struct WsPtrs {
   State* st;
-  unsigned* gbar;
   float* err_hist;
   double* errpart;
   float *fs, *gs0, *gs1, *a, *b, *log2b, *snap_fs, *snap_gs, *part_sum, *part_max;
@@ -109,7 +106,6 @@ static inline WsPtrs ws_ptrs(void* ws, const WsLayout& L) {
   char* p = static_cast<char*>(ws);
   WsPtrs w;
   w.st = reinterpret_cast<State*>(p + L.state);
-  w.gbar = reinterpret_cast<unsigned*>(p + L.gbar);
   w.err_hist = reinterpret_cast<float*>(p + L.err_hist);
   w.errpart = reinterpret_cast<double*>(p + L.errpart);
   w.fs = reinterpret_cast<float*>(p + L.fs);
