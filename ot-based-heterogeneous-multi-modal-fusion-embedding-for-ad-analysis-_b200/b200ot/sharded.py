@@ -222,7 +222,10 @@ class ShardedSinkhorn:
         self._events = []  # bounds how far the host may run ahead of the GPU (see run())
         self._win = max(1, int(os.environ.get("B200OT_SHARD_WINDOW", "10")))
         self._since_event = 0
-        self._lag = max(0, int(os.environ.get("B200OT_SHARD_LAG", "0")))  # windows the host may run ahead
+        # windows the host may run ahead of the device.  With NCCL in the loop 0 was measured best (many outstanding
+        # collectives slow NCCL's host side); the peer loop has no library call in it, so the host queues two
+        # windows ahead and the device never waits for the next chunk of launches.
+        self._lag = max(0, int(os.environ.get("B200OT_SHARD_LAG", "2" if self.peer is not None else "0")))
         self._graph, self._graph_iters = None, 0
 
     def _allreduce(self, s: torch.Tensor) -> torch.Tensor:
