@@ -72,3 +72,52 @@ def test_sass_has_bulk_copy_and_cluster_barrier(native_lib):
     assert "UBLKCP" in out.stdout
     assert "UCGABAR" in out.stdout
     assert "MUFU.EX2" in out.stdout
+
+
+def test_argument_validation_happens_before_any_device_work(native_lib):
+    """Invalid calls return their status code without touching CUDA (so this runs on a CPU-only box): null
+    pointers, non-positive sizes, shapes beyond what a kernel family covers.  No exceptions cross the ABI."""
+    from b200ot import _lib
+    lib = _lib.load()
+    E_INVALID, E_UNSUPPORTED = -1, -4
+    assert lib.b200ot_strerror(E_INVALID) == b"invalid argument"
+    assert b"unsupported" in lib.b200ot_strerror(E_UNSUPPORTED)
+    prm = _lib.Params(0.05, 10, 0.0, 10, 1, 0, 0, 0, 0)
+    # Sinkhorn life cycle: missing workspace / marginals, empty problem
+    assert lib.b200ot_sinkhorn_setup(4, 4, None, None, None, None, ctypes.byref(prm), None, 0, None) == E_INVALID
+    assert lib.b200ot_sinkhorn_enqueue(None, 4, 4, 4, 1, 0, None, None) == E_INVALID
+    assert lib.b200ot_sinkhorn_finish(0, 4, None, None, None, None, None, 0, None) == E_INVALID
+    assert lib.b200ot_sinkhorn_describe(0, 4, ctypes.create_string_buffer(64), 64) == E_INVALID
+    # batched / Gromov-Wasserstein one-CTA-per-problem kernels: size caps
+    dummy = ctypes.c_void_p(256)  # never dereferenced: validation comes first
+    assert lib.b200ot_sinkhorn_batched(dummy, None, None, 1, 129, 64, 0, dummy, dummy, ctypes.byref(prm), dummy, None,
+                                       None, None, None, None) == E_UNSUPPORTED
+    assert lib.b200ot_sinkhorn_batched(None, None, None, 1, 64, 64, 0, dummy, dummy, ctypes.byref(prm), dummy, None,
+                                       None, None, None, None) == E_INVALID
+    assert lib.b200ot_egw_batched(dummy, dummy, dummy, dummy, dummy, 1, 65, 10, 8, 8, 5e-3, 10, 5, 1e-3, 10, 10, 1e-3,
+                                  dummy, dummy, dummy, None) == E_UNSUPPORTED
+    assert lib.b200ot_egw_batched(dummy, dummy, dummy, dummy, dummy, 1, 10, 10, 8, 8, 0.0, 10, 5, 1e-3, 10, 10, 1e-3,
+                                  dummy, dummy, dummy, None) == E_INVALID
+    # peer exchange
+    assert lib.b200ot_peer_exchange_bytes(0, 64) == 0 and lib.b200ot_peer_exchange_bytes(17, 64) == 0
+    assert lib.b200ot_peer_exchange_bytes(8, 65536) == 2 * 8 * 65536 * 8
+    assert lib.b200ot_peer_exchange_bytes(3, 100) == 2 * 3 * 128 * 8  # columns padded to 64
+    assert lib.b200ot_peer_alloc(0, None, None) == E_INVALID
+    assert lib.b200ot_peer_open(None, None) == E_INVALID
+    assert lib.b200ot_sinkhorn_shard_finalize_peer(4, 4, None, None, 2, 1, 0, None) == E_INVALID
+
+
+def test_host_api_rejects_cpu_tensors_and_bad_shapes(native_lib):
+    """The Python operators fail loudly instead of falling back: CPU tensors, wrong dtypes and mismatched shapes
+    raise B200OTError before any kernel is launched."""
+    import torch
+    from b200ot import ops, B200OTError
+    x = torch.zeros(4, 8)
+    with pytest.raises(B200OTError):
+        ops.cost_matrix(x, x)
+    with pytest.raises(B200OTError):
+        ops.plan(torch.zeros(4, 4), torch.zeros(4), torch.zeros(4), 0.1)
+    with pytest.raises(B200OTError):
+        ops.egw_batched([], [])
+    with pytest.raises(B200OTError):
+        ops.egw_batched([x], [x, x])
