@@ -7,18 +7,20 @@
 // C1/C3, the reference-native 512^2 / 2048^2 feature problems of MRI_PET_OT_nojax.py:91-145): there the
 // per-iteration cost of the launch-per-sweep path is launches, ramp-up and the finalize kernel, not bytes.
 //
-//  * one CTA per SM owns a contiguous block of rows (whole rows, no cluster exchange); thread t owns the
-//    column quads t, t+T, ...: column accumulators and the scaled g live in registers for a whole sweep;
+//  * two 256-thread CTAs per SM (one 512-thread CTA for rows wider than 4096 columns) each own a contiguous block
+//    of whole rows (no cluster exchange); thread t owns the column quads t, t+T, ...: column accumulators and
+//    the scaled g live in registers for a whole sweep;
 //  * the rows sit in a shared-memory ring filled by TMA bulk copies.  When the block fits the ring
 //    (n*m*4 <= ~28 MB, e.g. 2048^2) C is read from HBM ONCE per launch and every later iteration runs out of
 //    shared memory.  Otherwise the ring is a cache of the most recent groups and sweeps alternate direction
 //    ("snake"): the tail of one sweep is the head of the next, so the ring content -- and whatever of the
 //    block is still in L2 -- is reused instead of re-fetched;
 //  * the column reduction across CTAs, the marginal error, the next g and the stopping rule run inside the
-//    kernel behind two grid barriers per iteration: partials -> barrier -> CTA c folds its slice of the
-//    columns over all CTAs in fixed order (bit-reproducible), writes g and one error partial -> barrier ->
-//    every CTA folds the same error partials and advances a private copy of the state machine, so all CTAs
-//    take identical decisions without another exchange.
+//    kernel WITHOUT a grid barrier: every value that crosses CTAs is a tagged 64-bit word that its consumers
+//    poll (see "tagged words" below).  CTA c folds its slice of the columns over all CTAs in fixed order
+//    (bit-reproducible) and publishes g and, on check iterations, one error partial; every CTA gathers g, folds
+//    the same error partials and advances a private copy of the state machine, so all CTAs take identical
+//    decisions without another exchange.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
