@@ -489,6 +489,40 @@ def get_coupling_egw_ott_fixed(data, eps: float = 5e-3, gw_max_iterations: int =
     return out_T, log
 
 
+def get_coupling_egw_ott(data, eps: float = 5e-3, *, device=None):
+    """Drop-in for ``get_coupling_egw_ott`` (perturbot/perturbot/match/ott_egwl.py:129-206; MRI_PET_OT.py:68-122):
+    the same per-label entropic Gromov-Wasserstein solve with ott's defaults spelled out there --
+    ``GromovWasserstein(epsilon=eps, max_iterations=1000)`` and the default inner ``Sinkhorn()`` (2000 iterations)."""
+    return get_coupling_egw_ott_fixed(data, eps, gw_max_iterations=1000, sinkhorn_max_iterations=2000, device=device)
+
+
+def get_coupling_eot_ott(data, eps: float = 5e-3, *, device=None):
+    """Drop-in for ``get_coupling_eot_ott`` (perturbot/perturbot/match/ott_egwl.py:299-372): ONE sample-level
+    entropic OT problem over all labels concatenated (label information is disregarded): squared-Euclidean
+    point-cloud cost divided by its maximum (``PointCloud(scale_cost="max_cost").cost_matrix``, :350), then
+    ``linear.solve(Geometry(cost_matrix, epsilon=eps))`` (:356).  The cost is built on the tcgen05 kernel and the
+    solve is the engine's ott-flavoured log-domain Sinkhorn.  Returns ``(T, log)`` with the reference's log keys
+    (``OT cost`` is the dual value ``<a, f> + <b, g>``)."""
+    X_dict, Y_dict = data
+    keys = list(X_dict.keys())
+    cv = _Conv(X_dict[keys[0]], device)
+    t0 = time.time()
+    X = torch.cat([cv.to_dev(X_dict[l]) for l in keys])
+    Y = torch.cat([cv.to_dev(Y_dict[l]) for l in keys])
+    C = ops.cost_matrix(X, Y)
+    cost_time = time.time() - t0
+    t0 = time.time()
+    out = linear_solve(Geometry(cost_matrix=C, epsilon=eps, scale_cost="max_cost"))
+    n, m = C.shape
+    f, g = torch.as_tensor(out.f).double(), torch.as_tensor(out.g).double()
+    log = {"n_iters_outer": out.n_iters, "converged": out.converged,
+           "OT cost": float(f[torch.isfinite(f)].sum() / n + g[torch.isfinite(g)].sum() / m)}
+    T = cv.back(out.matrix)
+    log["time"] = time.time() - t0
+    log["cost_time"] = cost_time
+    return T, log
+
+
 def compute_pet_to_mri_coupling(mri_features, pet_features, labels, max_samples_per_label=None,
                                 gw_max_iterations: int = 2000, sinkhorn_max_iterations: int = 2000, *, device=None):
     """The OT part of ``compute_pet_to_mri_coupling`` (MRI_PET_OT_OT_per_epoch_attn.py:940-960), i.e. everything

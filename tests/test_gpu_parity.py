@@ -720,3 +720,23 @@ def test_per_epoch_coupling_pipeline_stays_on_device(cuda_dev):
     # NumPy in -> NumPy out, like the reference
     Tn = b200ot.compute_pet_to_mri_coupling(mri, pet, labels, max_samples_per_label=40)
     assert isinstance(Tn, np.ndarray) and _rel(Tn, Tref) < RTOL
+
+
+def test_eot_and_egw_default_entry_points(cuda_dev):
+    """get_coupling_eot_ott / get_coupling_egw_ott (perturbot/perturbot/match/ott_egwl.py:129-206,299-372)."""
+    import b200ot
+    rng = np.random.default_rng(12)
+    Xd = {1: rng.standard_normal((30, 20)).astype(np.float32), 0: rng.standard_normal((45, 20)).astype(np.float32)}
+    Yd = {1: (rng.standard_normal((28, 20)) + 0.5).astype(np.float32), 0: rng.standard_normal((40, 20)).astype(np.float32)}
+    T, log = b200ot.get_coupling_eot_ott((Xd, Yd), eps=5e-2)
+    X = np.concatenate([Xd[1], Xd[0]])
+    Y = np.concatenate([Yd[1], Yd[0]])
+    C = orc.sqeuclid_cost(X, Y)
+    Pref, lg = orc.sinkhorn_log_ott(C, 5e-2, log=True)
+    assert T.shape == (75, 68) and log["n_iters_outer"] == lg["n_iter"] and log["converged"] == lg["converged"]
+    assert _rel(T, Pref) < RTOL
+    dual = float(lg["f"].mean() + lg["g"].mean())
+    assert abs(log["OT cost"] - dual) < 1e-4 * max(1.0, abs(dual))
+    Ts, lgw = b200ot.get_coupling_egw_ott(({0: Xd[1]}, {0: Yd[1]}), eps=5e-2)
+    Tr, lr = orc.egw_ott(Xd[1], Yd[1], eps=5e-2, gw_max_iterations=1000)
+    assert lgw[0]["n_iters_outer"] == lr["n_iters_outer"] and _rel(Ts[0], Tr) < RTOL
