@@ -126,56 +126,124 @@ def synthetic_rows(n_total, m, lo, hi, seed, device):
 
 
 # --------------------------------------------------------------------------------------
-# CPU arms (the oracle's restatement of the reference algorithm; bench-only use of oracle/)
+# CPU arm: the reference's own code (oracle/_ref, staged by oracle/build_ref.py) -- bench-only use of oracle/
 # --------------------------------------------------------------------------------------
-def cpu_reference_rate(n_sample, iters, n_full, repeats=1):
-    """Reference algorithm (kernel-domain Sinkhorn-Knopp in float64, MRI_PET_OT_nojax.py:143 /
-    perturbot/match/utils.py:6-115) on an n_sample^2 slice of the workload; rate scaled to the full
-    n_full^2 problem by the O(n^2) cost per iteration."""
-    import numpy as np
-    from oracle import ot_oracle as orc
-    X, Y = orc.synthetic_embeddings(n_sample, n_sample, D, config_index=3)
-    C = orc.sqeuclid_cost(X, Y)
-    a = np.ones(n_sample) / n_sample
-    best = None
-    for _ in range(repeats):
+def host_threads():
+    """Threads the CPU arm may use: the cores this process is allowed to run on."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def pin_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the reference would use every core.  Must run before numpy loads."""
+    nt = str(host_threads())
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = nt
+
+
+class CpuArm:
+    """`sinkhorn_scaling` of perturbot/perturbot/match/utils.py:6-115 -- the NumPy Sinkhorn-Knopp that
+    MRI_PET_OT_nojax.py:143's ot.sinkhorn executes arithmetically -- on the leading n_s x n_s block of the bench
+    workload (same generator, same rows), float64, K = exp(-C/eps) prepared outside the timed region.  One step =
+    one call with numItermax = iters (stopThr = 0), so the call's own set-up (Kp = K / a) and return value
+    (diag(u) K diag(v)) are inside the time, amortised over `iters` iterations instead of a solve's 200."""
+
+    def __init__(self, n_s, n_full):
+        import numpy as np
+        from oracle import build_ref
+        from oracle import ot_oracle as orc
+        self.np = np
+        self.ref = build_ref.load()
+        self.kind = "reference" if self.ref is not None else "port"
+        self.orc = orc
+        self.n_s, self.n_full = n_s, n_full
+        X, Y = synthetic_rows(n_full, n_full, 0, n_s, 20251118 + 3, None)
+        K = orc.sqeuclid_cost(X.numpy(), Y[:n_s].numpy())
+        K *= -1.0 / EPS
+        np.exp(K, out=K)
+        self.K = K
+        self.a = np.full(n_s, 1.0 / n_s)
+        try:
+            from threadpoolctl import threadpool_info
+            self.blas = [f"{d.get('internal_api')}:{d.get('num_threads')}" for d in threadpool_info()]
+        except Exception:
+            self.blas = []
+
+    def step(self, iters):
         t0 = time.perf_counter()
-        orc.sinkhorn_knopp(a, a, M=C, reg=EPS, numItermax=iters, stopThr=0.0)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    rate_sample = iters / best
-    return rate_sample * (n_sample / n_full) ** 2, rate_sample, best
+        if self.ref is not None:
+            self.ref.sinkhorn_scaling(self.a, self.a, self.K, numItermax=iters, stopThr=0.0)
+        else:
+            self.orc.sinkhorn_knopp(self.a, self.a, K=self.K, numItermax=iters, stopThr=0.0, err_norm="l2sq")
+        return time.perf_counter() - t0
+
+    def what(self):
+        return ("sinkhorn_scaling of the reference (perturbot/perturbot/match/utils.py:6-115, staged unmodified in "
+                "oracle/_ref)" if self.ref is not None else
+                "oracle port of sinkhorn_scaling (oracle/_ref not staged)")
+
+
+def cpu_sizes(requested):
+    """Largest block the host can hold: the reference needs K, Kp and two n^2 temporaries in float64 (32 n^2 B)."""
+    if requested:
+        return requested
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    return 32768 if avail > 48 * 2**30 else 16384
+
+
+def cpu_measure(args, steps, warmup, n_big):
+    """`warmup` short calls and `steps` timed calls at n = 8192, then ONE call each at n = 16384 and (when the host
+    has the memory) n = 32768.  The rate at the largest block is extrapolated to the 65536^2 problem by the O(n^2)
+    cost per iteration (x (n_big/n)^2) -- K and Kp at 65536^2 need 69 GB in float64 -- and the
+    smaller blocks show that the scaling holds."""
+    n_full = args.n
+    n_small = min(8192, n_full)
+    arm = CpuArm(n_small, n_full)
+    for _ in range(warmup):
+        arm.step(2)
+    times = [arm.step(args.cpu_iters) for _ in range(steps)]
+    rate_small = args.cpu_iters / (sum(times) / len(times))
+    kind, what, blas = arm.kind, arm.what(), arm.blas
+    del arm
+    rates = [(n_small, rate_small, sum(times) / len(times))]
+    for nb in (16384, 32768):
+        if nb <= n_small or nb > n_big or nb > n_full:
+            continue
+        big = CpuArm(nb, n_full)
+        big.step(1)  # touch the pages once
+        t = big.step(args.cpu_iters)
+        rates.append((nb, args.cpu_iters / t, t))
+        del big
+    n_used, rate_used, _ = rates[-1]
+    scaled = rate_used * (n_used / n_full) ** 2
+    per_size = "; ".join(f"n=m={nn}: {rr:.3f} it/s ({tt:.1f} s per call, x(n/{n_full})^2 -> {rr * (nn / n_full) ** 2:.4f})"
+                         for nn, rr, tt in rates)
+    sample = (f"{what}; float64; calls of {args.cpu_iters} iterations on the leading n x n block of the n=m={n_full} "
+              f"workload, {steps} timed calls at n={n_small} then one call per larger block: {per_size}; value = the "
+              f"n={n_used} rate x ({n_used}/{n_full})^2; BLAS threads {blas}")
+    return scaled, kind, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np  # noqa: F401
-    try:
-        import torch
-        cores = torch.get_num_threads()
-    except Exception:
-        cores = os.cpu_count()
-    n_full = args.n
-    n_s = args.cpu_sample
-    times = []
-    for i in range(args.warmup + args.steps):
-        scaled, raw, dt = cpu_reference_rate(n_s, args.cpu_iters, n_full)
-        if i >= args.warmup:
-            times.append((scaled, raw, dt))
-    scaled = sum(t[0] for t in times) / len(times)
-    raw = sum(t[1] for t in times) / len(times)
+    cores = host_threads()
+    scaled, kind, sample = cpu_measure(args, args.steps, args.warmup, cpu_sizes(args.cpu_sample))
     ms = 1e3 * args.iters / scaled
-    sample = (f"n=m={n_s} slice of the n=m={n_full} workload, {args.cpu_iters} iterations per step, float64 "
-              f"kernel-domain Sinkhorn-Knopp ({raw:.2f} it/s on the slice), scaled by ({n_s}/{n_full})^2")
     line = {"impl": "reference", "metric": METRIC, "value": scaled, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"log-domain/kernel-domain Sinkhorn n=m={n_full} d={D} eps={EPS}, "
-                                   f"{args.iters} iterations per solve", "n": n_full, "m": n_full, "d": D,
-                       "eps": EPS},
-            "cpu_baseline": {"value": scaled, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": f"log-domain/kernel-domain Sinkhorn n=m={args.n} d={D} eps={EPS}, "
+                                   f"{args.iters} iterations per solve (BASELINE configs[3])", "n": args.n, "m": args.n,
+                       "d": D, "eps": EPS, "iterations_per_step": args.iters},
+            "cpu_baseline": {"value": scaled, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": scaled, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -184,6 +252,58 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------
+PARITY_ROWS = 1024
+
+
+def parity_check(torch, dist, ops, world, rank, dev, Xh, Yh, Cmat, a_loc, f, g, n, m, info):
+    """Values of the TIMED solve, checked after the timed region (never inside it).
+    (1) g is replicated: every rank must hold the same bits (max and min over ranks of the int32 view agree).
+    (2) rank 0 redoes rows [0, 1024) in float64 on the host (oracle.rows_given_g: cost rows from the embeddings, the
+        f update and the plan rows that follow from the converged g) and compares the GPU's f and plan rows with it:
+        max-normalised error, elementwise relative error on entries >= 1e-6 * max, |df| in units of eps.
+    (3) the column marginals of the plan after the last f update are recomputed by an independent kernel
+        (apply_plan_t on a column of ones, all-reduced over the row shards) and compared with b in L1."""
+    out = {"g_bit_equal_across_ranks": True, "ranks": world}
+    gi = g.view(torch.int32)
+    if world > 1:
+        hi, lo = gi.clone(), gi.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        out["g_bit_equal_across_ranks"] = bool(torch.equal(hi, lo))
+    n_loc = Cmat.shape[0]
+    cols = ops.apply_plan(Cmat, f, g, EPS, torch.ones((n_loc, 1), device=dev), transpose=True).reshape(-1).double()
+    if world > 1:
+        dist.all_reduce(cols)
+    out["col_marginal_l1_recomputed"] = float((cols - 1.0 / m).abs().sum())
+    out["n_iter"] = info["n_iter"]
+    if rank != 0:
+        return None
+    import hashlib
+    import numpy as np
+    from oracle import ot_oracle as orc
+    R = min(PARITY_ROWS, n_loc)
+    g64 = g.double().cpu().numpy()
+    C_rows = orc.sqeuclid_cost(Xh[:R].numpy(), Yh.numpy())
+    f_ref, P_ref = orc.rows_given_g(C_rows, np.full(R, 1.0 / n), g64, EPS)
+    P_gpu = ops.plan(Cmat[:R], f[:R], g, EPS).double().cpu().numpy()
+    diff = np.abs(P_gpu - P_ref)
+    mx = float(P_ref.max())
+    mask = P_ref >= 1e-6 * mx
+    out.update({
+        "rows_checked": R,
+        "plan_max_norm_err": float(diff.max() / mx),
+        "plan_elementwise_rel_err_ge_1e-6max": float((diff[mask] / P_ref[mask]).max()),
+        "entries_ge_1e-6max": int(mask.sum()),
+        "f_abs_err_over_eps": float(np.abs(f[:R].double().cpu().numpy() - f_ref).max() / EPS),
+        "cost_rows_abs_err": float(np.abs(Cmat[:R].double().cpu().numpy() - C_rows).max()),
+        "tolerance": 1e-4,
+        "g_sha256_16": hashlib.sha256(g.cpu().numpy().tobytes()).hexdigest()[:16],
+        "oracle": "oracle.rows_given_g (float64) on rows [0, %d) with the GPU's converged g" % R,
+    })
+    out["ok"] = bool(out["g_bit_equal_across_ranks"] and out["plan_max_norm_err"] < 1e-4)
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -275,11 +395,15 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
     # correctness guard on the timed state: finished all iterations, finite error
     if world == 1:
-        _, _, info = stepper.finish()
+        f_fin, g_fin, info = stepper.finish()
     else:
-        _, _, info = kern.finish()
-    if not os.environ.get("B200OT_FUSED_MODE"):  # diagnostic modes do not run the real arithmetic
+        f_fin, g_fin, info = kern.finish()
+    diag = bool(os.environ.get("B200OT_FUSED_MODE"))  # diagnostic modes do not run the real arithmetic
+    if not diag:
         assert info["n_iter"] == iters and info["status"] == 0, info
+    parity = None
+    if not diag and not args.no_parity:
+        parity = parity_check(torch, dist, ops, world, rank, dev, Xh, Yh, Cmat, a_loc, f_fin, g_fin, n, m, info)
     ms_per_step = ms / args.steps
     value = iters / (ms_per_step * 1e-3)
 
@@ -315,11 +439,9 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        scaled, raw, dt = cpu_reference_rate(args.cpu_sample, args.cpu_iters, n)
-        cpu_baseline = {"value": scaled, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"n=m={args.cpu_sample} slice, {args.cpu_iters} iterations, float64 kernel-domain "
-                                  f"Sinkhorn-Knopp of the oracle ({raw:.2f} it/s, {dt:.1f} s), scaled by "
-                                  f"({args.cpu_sample}/{n})^2 to the full problem"}
+        # bounded sample (~20 s): calls at n = 8192 and one at 16384; `--impl reference` also measures n = 32768
+        scaled, kind, sample = cpu_measure(args, 2, 1, 16384)
+        cpu_baseline = {"value": scaled, "unit": UNIT, "cores": host_threads(), "kind": kind, "sample": sample}
     if rank != 0:
         if world > 1:
             _shutdown(dist)
@@ -353,7 +475,10 @@ def run_b200(args):
                    "l2": l2_note},
         "hbm_gbs": achieved * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": _traffic(kernel_desc, n_loc, m), "peak_source": peak_src,
+                     "traffic": _traffic(kernel_desc, n_loc, m),
+                     "traffic_source": "static: dram__bytes_read+write per launch from the committed ncu --set full capture "
+                                       "of this kernel configuration (profiles/r01_traffic.json); not re-measured in this run",
+                     "peak_source": peak_src,
                      "note": "achieved = 4*n_local*m bytes per iteration / (step time / iterations); the step time "
                              "includes the finalize kernel and, for N>1, the exchange of the column sums (peer-memory push or NCCL)"},
         "cpu_baseline": cpu_baseline,
@@ -362,6 +487,7 @@ def run_b200(args):
                 "note": "pinned host embeddings -> H2D -> cost construction -> solve -> potentials D2H"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
+        "parity": parity,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -395,12 +521,16 @@ def main():
                     help="N>1: how the column sums are exchanged (peer = pushed as tagged words into peer memory over "
                          "NVLink by the kernels themselves, no collective call; c = ncclAllReduce queued from C on the "
                          "compute stream; python = torch.distributed all_reduce per iteration; graph = python loop captured)")
-    ap.add_argument("--cpu-sample", type=int, default=4096)
-    ap.add_argument("--cpu-iters", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="--impl reference: side of the largest block timed on the CPU (0 = 32768 if the host has "
+                         "the memory for it, else 16384)")
+    ap.add_argument("--cpu-iters", type=int, default=10, help="reference iterations per CPU call")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run value checks")
     ap.add_argument("--no-sampler", action="store_true", help="diagnostic: do not sample clocks")
     args = ap.parse_args()
     if args.impl == "reference":
+        pin_host_threads()  # before numpy / BLAS load: torchrun exports OMP_NUM_THREADS=1
         run_reference(args)
     else:
         run_b200(args)

@@ -37,7 +37,7 @@ import numpy as np
 __all__ = [
     "synthetic_embeddings", "sqeuclid_cost", "cosine_cost", "init_matrix",
     "fot_cost_pot", "fot_cost_ott", "mdict_to_matrix", "sinkhorn_knopp",
-    "sinkhorn_log", "sinkhorn_log_ott", "plan_from_potentials", "fot_bcd_ott",
+    "sinkhorn_log", "sinkhorn_log_ott", "plan_from_potentials", "rows_given_g", "fot_bcd_ott",
     "get_feature_coupling_pot", "get_coupling_fot", "plan_guard_rownorm",
     "apply_plan_T", "barycentric", "cosine_loss", "ot_cost", "envelope_grads", "foscttm",
     "group_features_by_label", "egw_ott", "get_coupling_egw_ott_fixed", "cotl_sinkhorn",
@@ -168,7 +168,7 @@ def fot_cost_ott(X, Y, Ts):
 # Sinkhorn, kernel domain (POT / in-tree mirror semantics)
 # --------------------------------------------------------------------------
 def sinkhorn_knopp(a, b, M=None, reg=None, K=None, numItermax=1000, stopThr=1e-9,
-                   err_norm="l2", check_every=10, log=False):
+                   err_norm="l2", check_every=10, log=False, check_phase=1, u0=None, v0=None):
     """Kernel-domain Sinkhorn-Knopp.
 
     Follows ``perturbot/perturbot/match/utils.py:6-115`` line by line (init
@@ -183,6 +183,13 @@ def sinkhorn_knopp(a, b, M=None, reg=None, K=None, numItermax=1000, stopThr=1e-9
     unverifiable here).  Pass either ``K`` (mirror) or ``(M, reg)`` (POT).
     ``log["n_iter"]`` is the number of completed (v,u) updates; ``log["niter"]``
     is POT's loop index at exit.
+
+    ``check_phase`` (default 1 = the reference: ``cpt % check_every == 0`` with the
+    0-based counter) moves the check to 1-based iterations with
+    ``it % check_every == check_phase % check_every``; ``check_phase=0`` with
+    ``err_norm="l1"`` and ``u0 = v0 = 1`` is ott's rule evaluated in the kernel domain
+    (the same map as ``sinkhorn_log`` while ``K`` has not underflowed -- used for
+    problems too large for the log-domain oracle to finish in seconds).
     """
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
@@ -192,8 +199,8 @@ def sinkhorn_knopp(a, b, M=None, reg=None, K=None, numItermax=1000, stopThr=1e-9
     else:
         K = np.asarray(K, dtype=np.float64)
     n, m = len(a), len(b)
-    u = np.ones(n) / n
-    v = np.ones(m) / m
+    u = np.ones(n) / n if u0 is None else np.asarray(u0, dtype=np.float64).copy()
+    v = np.ones(m) / m if v0 is None else np.asarray(v0, dtype=np.float64).copy()
     Kp = (1.0 / a).reshape(-1, 1) * K
     errs = []
     err = 1.0
@@ -210,7 +217,7 @@ def sinkhorn_knopp(a, b, M=None, reg=None, K=None, numItermax=1000, stopThr=1e-9
             u, v = uprev, vprev
             flag = 1  # "numerical errors": previous iterate returned
             break
-        if cpt % check_every == 0:
+        if (cpt + 1) % check_every == check_phase % check_every:
             # column marginal of diag(u) K diag(v), same op order as utils.py:88
             col = np.sum(u.reshape(-1, 1) * (K * v), axis=0)
             if err_norm == "l2sq":
@@ -294,6 +301,17 @@ def sinkhorn_log(C, a, b, eps, max_iter=1000, tol=1e-9, err_norm="l2", check_eve
     if log:
         return P, {"err": errs, "f": f, "g": g, "n_iter": it, "converged": converged}
     return P
+
+
+def rows_given_g(C_rows, a_rows, g, eps):
+    """The f update and plan rows that follow from a given column potential g (float64): after any completed
+    iteration f_i = eps log a_i - eps LSE_j((g_j - C_ij)/eps) and P_ij = exp((f_i + g_j - C_ij)/eps).  bench.py
+    uses it to check rows of a 65536-column solve that no CPU can iterate itself: the converged g comes from the
+    GPU, the row arithmetic (cost rows, logsumexp, plan entries) is redone here in float64."""
+    C_rows = np.asarray(C_rows, dtype=np.float64)
+    g = np.asarray(g, dtype=np.float64)
+    f = eps * np.log(np.asarray(a_rows, dtype=np.float64)) - eps * _lse((g[None, :] - C_rows) / eps, axis=1)
+    return f, np.exp((f[:, None] + g[None, :] - C_rows) / eps)
 
 
 def sinkhorn_log_ott(M, eps, a=None, b=None, max_iterations=2000, threshold=1e-3,

@@ -1287,6 +1287,13 @@ static bool vec_eligible(const float* C, int ldc, int m) {
   return (ldc % 4 == 0) && (m % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 }
 
+// stream C through L2 with an evict-first policy once it cannot stay resident (B200OT_FUSED_EVICT overrides)
+static int sweep_evict_first(int n, int m) {
+  const char* ev = getenv("B200OT_FUSED_EVICT");
+  if (ev) return atoi(ev) ? 1 : 0;
+  return ((double)n * (double)m * 4.0 > 100e6) ? 1 : 0;
+}
+
 static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtrs& w, int* np_out,
                               cudaStream_t s) {
   // B200OT_FUSED_VARIANT: "lite" = 256-thread CTAs, two per SM; "pipe" = 512-thread software-pipelined
@@ -1313,9 +1320,7 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
   a.part = w.part_sum;
   a.stride = w.m_pad;
   a.ng = cfg.NG;
-  a.evict_first = ((double)n * (double)m * 4.0 > 100e6) ? 1 : 0;
-  const char* ev = getenv("B200OT_FUSED_EVICT");
-  if (ev) a.evict_first = atoi(ev);
+  a.evict_first = sweep_evict_first(n, m);
   a.wq = cfg.wq;
   const char* em = getenv("B200OT_FUSED_MODE");
   a.mode = em ? atoi(em) : 0;
@@ -1578,10 +1583,11 @@ int b200ot_sinkhorn_describe(int n, int m, char* buf, int buf_len) {
   if (rc) return rc;
   snprintf(buf, buf_len,
            "%s: cluster=%d CTAs x %d threads, %d clusters (%d CTAs), %d cols/CTA, %d cols/thread, "
-           "%d row(s)/group, TMA ring %d x %zu B, smem %zu B/CTA",
+           "%d row(s)/group, TMA ring %d x %zu B, smem %zu B/CTA, L2 %s",
            lite ? "sweep_lite_kernel (2 CTAs/SM)" : "sweep_fused_kernel (pipelined, 1 CTA/SM)", cfg.Q,
            lite ? kLiteThreads : kSweepThreads, cfg.NC, cfg.NC * cfg.Q, cfg.wq, 4 * cfg.NCH, cfg.R, cfg.NG,
-           (size_t)cfg.R * (lite ? kLiteThreads : kSweepThreads) * 4 * cfg.NCH * 4, cfg.smem);
+           (size_t)cfg.R * (lite ? kLiteThreads : kSweepThreads) * 4 * cfg.NCH * 4, cfg.smem,
+           sweep_evict_first(n, m) ? "evict-first" : "default policy");
   return 0;
 }
 

@@ -9,6 +9,10 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+for p in (os.path.join(ROOT, "tests"),):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -34,3 +38,17 @@ def cuda_dev(native_lib):
     import torch
     assert torch.cuda.is_available(), "GPU tests were selected (-m gpu) but no CUDA device is visible"
     return torch.device("cuda", 0)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Write the measured plan-parity figures (tests/_parity.py) where gpurun brings them back."""
+    try:
+        import json
+        import _parity
+        if _parity.REPORT:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_report.json"), "w") as fh:
+                json.dump(_parity.REPORT, fh, indent=1)
+    except Exception:  # reporting must never turn a green run red
+        pass

@@ -13,6 +13,8 @@ import torch
 
 from oracle import ot_oracle as orc
 
+import _parity
+
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4
@@ -24,9 +26,11 @@ def _load(golden_dir, name):
     return np.load(os.path.join(golden_dir, name))
 
 
-def _rel(P, Pref):
-    P = np.asarray(P, dtype=np.float64)
-    return float(np.abs(P - Pref).max() / np.abs(Pref).max())
+def _rel(P, Pref, elem_rtol=_parity.ELEM_RTOL):
+    """max-normalised plan error; the elementwise error on entries >= 1e-6 * max is asserted (and both are
+    recorded for gpurun_out/parity_report.json) inside tests/_parity.py"""
+    import inspect
+    return _parity.rel(P, Pref, what=inspect.stack()[1].function, elem_rtol=elem_rtol)
 
 
 def _dev(x, dev, dtype=torch.float32):
@@ -244,7 +248,7 @@ def test_small_eps_falls_back_and_stays_finite(cuda_dev):
     P = ops.plan(Cd, f, g, eps).cpu().numpy()
     assert np.isfinite(P).all() and info["n_iter"] == 40
     np.testing.assert_allclose(P.sum(1), a, rtol=1e-3)
-    assert _rel(P, Pref) < 2e-2  # exponents ~1e3: fp32 resolves the plan to ~1e-3 here
+    assert _rel(P, Pref, elem_rtol=None) < 2e-2  # exponents ~1e3: fp32 resolves the plan to ~1e-3 here
 
 
 def test_warm_start_and_stepper(cuda_dev):
@@ -690,9 +694,9 @@ def test_label_constrained_coot_bcd_matches_reference(cuda_dev, golden_dir):
     assert abs(cost - float(g["cost"])) < 1e-3 * abs(float(g["cost"]))
     k0 = min(len(lg["cost"]), len(g["costs"]), 10)
     np.testing.assert_allclose(lg["cost"][:k0], g["costs"][:k0], rtol=1e-4)  # the early rounds are far from the floor
-    assert _rel(Tv, g["Tv"]) < 5e-3
+    assert _rel(Tv, g["Tv"], elem_rtol=None) < 5e-3
     for k in keys:
-        assert _rel(Ts[k], g[f"Ts{k}"]) < 5e-3
+        assert _rel(Ts[k], g[f"Ts{k}"], elem_rtol=None) < 5e-3
     Ts2, log2 = b200ot.get_coupling_cotl_sinkhorn((Xd, Yd), eps=float(g["reg"]))
     assert set(Ts2) == set(keys) and "time" in log2 and len(log2["cost"]) == len(lg["cost"])
     with pytest.raises(b200ot.B200OTError):
