@@ -255,6 +255,148 @@ def run_reference(args):
 PARITY_ROWS = 1024
 
 
+def _event_ms(torch, fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def extras(torch, dist, ops, world, rank, dev, args):
+    """The other BASELINE configs, measured in the same run so that the driver sees them:
+    C2  4096 independent 64 x 64 problems from embeddings (d = 512), float64 POT arithmetic, 200 iterations each,
+        the batch split over the ranks with no communication -> problems/s of the whole job;
+    C3  n = m = 4096 cohort: iterations/s of the resident kernel (C lives in L2), and the end-to-end time of
+        pinned embeddings -> cost -> 200 iterations -> fused embedding -> envelope backward -> fused embedding D2H;
+    online  the cost-free solver at n = m = 65536 (C rebuilt on tcgen05 every iteration, never in HBM).
+    C3 and online run on rank 0 at N = 1 only (they do not shard; "replicas only")."""
+    import b200ot
+    out = {}
+    # ---- C2: batched minibatch OT, batch split across the ranks
+    B, nb, d = 4096, 64, D
+    B_loc = B // world + (1 if rank < B % world else 0)
+    gen = torch.Generator(device="cpu").manual_seed(20251118 + 1 + 7919 * rank)
+    Xb = torch.randn(B_loc, nb, d, generator=gen)
+    Yb = torch.randn(B_loc, nb, d, generator=gen) + 0.5 * torch.randn(B_loc, 1, d, generator=gen)
+    Xb = (Xb / Xb.norm(dim=2, keepdim=True)).to(dev)
+    Yb = (Yb / Yb.norm(dim=2, keepdim=True)).to(dev)
+    ab = torch.full((nb,), 1.0 / nb, device=dev)
+    its = 200
+    holder = {}
+
+    def run_c2():
+        holder["r"] = ops.sinkhorn_batched(ab, ab, EPS, X=Xb, Y=Yb, max_iter=its, tol=0.0)
+    if world > 1:
+        dist.barrier()
+    ms = _event_ms(torch, run_c2, reps=5)
+    n_it = holder["r"][1]["n_iter"]
+    assert int(n_it.min()) == its and int(n_it.max()) == its
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    out["c2_batched"] = {
+        "workload": f"{B} independent {nb}x{nb} problems, d={d}, eps={EPS}, {its} iterations each (BASELINE configs[1]), "
+                    f"float64 POT arithmetic, Gibbs kernel in registers, one problem per CTA, two CTAs per SM",
+        "problems_per_s": B / (ms * 1e-3), "ms": ms, "n_gpus": world, "problems_per_gpu": B_loc,
+        "split": "batch dimension over the ranks, no communication",
+        "problem_iterations_per_s": B * its / (ms * 1e-3),
+        "sm_ns_per_problem_iteration": ms * 1e6 * sm * world / (B * its),
+        "hbm_bytes_per_problem": 4 * (2 * nb * d + nb * nb)}
+    del Xb, Yb, holder
+    if rank != 0 or world != 1:
+        return out
+    # ---- C3: cohort problem, n = m = 4096
+    n3 = 4096
+    X3h, Y3h = synthetic_rows(n3, n3, 0, n3, 20251118 + 2, None)
+    X3p, Y3p = X3h.pin_memory(), Y3h.pin_memory()
+    x3, y3 = X3p.to(dev), Y3p.to(dev)
+    C3 = ops.cost_matrix(x3, y3)
+    a3 = torch.full((n3,), 1.0 / n3, device=dev)
+    st3 = ops.SinkhornStepper(C3, a3, a3, EPS, max_iter=its, tol=0.0)
+
+    def run_c3():
+        st3.reset()
+        st3.run(its)
+    ms3 = _event_ms(torch, run_c3, reps=5)
+    f3, g3, inf3 = st3.finish()
+    assert inf3["n_iter"] == its
+    ms_apply = _event_ms(torch, lambda: ops.apply_plan(C3, f3, g3, EPS, y3, normalise=True), reps=11)
+    ms_bwd = _event_ms(torch, lambda: ops.envelope_bwd(C3, f3, g3, EPS, x3, y3), reps=11)
+    fused3 = torch.empty((n3, D), dtype=torch.float32).pin_memory()
+
+    def e2e_c3():
+        o = b200ot.sinkhorn_from_embeddings(X3p, Y3p, reg=EPS, numItermax=its, stopThr=0.0, V=Y3p, fused_out=fused3)
+        xd, yd = X3p.to(dev, non_blocking=True), Y3p.to(dev, non_blocking=True)
+        Cx = ops.cost_matrix(xd, yd)
+        ff = torch.as_tensor(o["f"]).to(dev)
+        gg = torch.as_tensor(o["g"]).to(dev)
+        dx, dy = ops.envelope_bwd(Cx, ff, gg, EPS, xd, yd)
+        dx.cpu()
+    e2e_c3()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        e2e_c3()
+    torch.cuda.synchronize()
+    e2e3 = (time.perf_counter() - t0) / 3
+    out["c3_cohort"] = {
+        "workload": f"n=m={n3}, d={D}, eps={EPS}, {its} iterations (BASELINE configs[2]); C = 64 MiB lives in L2",
+        "kernel": ops.describe_kernel(n3, n3), "iterations_per_s": its / (ms3 * 1e-3), "us_per_iteration": 1e3 * ms3 / its,
+        "l2_gbs": 4.0 * n3 * n3 * its / (ms3 * 1e-3) / 1e9,
+        "fused_embedding_ms": ms_apply, "envelope_backward_ms": ms_bwd,
+        "fused_embedding_alg_tflops": 2.0 * n3 * n3 * D / ms_apply / 1e9,
+        "e2e_ms": 1e3 * e2e3,
+        "e2e_note": "pinned embeddings -> H2D -> cost -> 200 iterations -> fused embedding (tcgen05) -> D2H, then "
+                    "cost + envelope backward (one tcgen05 launch for dX and dY) -> dX D2H"}
+    del C3, st3
+    # ---- online (cost-free) solver at the headline shape
+    if not args.no_online:
+        from b200ot.online import OnlineSinkhorn
+        n = m = args.n
+        Xh, Yh = synthetic_rows(n, m, 0, n, 20251118 + 3, None)
+        xo, yo = Xh.to(dev), Yh.to(dev)
+        ao = torch.full((n,), 1.0 / n, device=dev)
+        bo = torch.full((m,), 1.0 / m, device=dev)
+        k_it = 4
+        sol = OnlineSinkhorn(xo, yo, ao, bo, EPS, max_iter=10 ** 6, tol=0.0)
+        sol.start()
+        sol.run(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sol.run(k_it)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_o = e0.elapsed_time(e1) / k_it
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                tf_peak = float(json.load(fh)["bf16_tflops_sustained"])
+        except Exception:
+            tf_peak = 1400.0
+        executed = sol.tensor_flops_per_iteration / ms_o / 1e9
+        out["online_c4"] = {
+            "workload": f"cost-free Sinkhorn n=m={n} d={D}: C rebuilt per iteration on tcgen05 in {sol.panel_rows}-row panels "
+                        f"({sol.panel.numel() * 4 >> 20} MiB scratch, 6-term bf16 split), consumed by the single-sweep "
+                        f"kernel; the n x m matrix is never materialised",
+            "iterations_per_s": 1e3 / ms_o, "ms_per_iteration": ms_o,
+            "tensor_tflops_executed": executed, "tensor_tflops_algorithmic": executed / sol.terms,
+            "tensor_frac_of_sustained_bf16_peak": executed / tf_peak, "tensor_peak_tflops": tf_peak,
+            "streaming_is_faster_by": None}
+    return out
+
+
+
+
 def parity_check(torch, dist, ops, world, rank, dev, Xh, Yh, Cmat, a_loc, f, g, n, m, info):
     """Values of the TIMED solve, checked after the timed region (never inside it).
     (1) g is replicated: every rank must hold the same bits (max and min over ranks of the int32 view agree).
@@ -407,17 +549,26 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     value = iters / (ms_per_step * 1e-3)
 
-    # ---- end to end through the public API: pinned host embeddings -> potentials on the host
+    # ---- end to end through the public API: pinned host embeddings -> potentials AND the fused embedding
+    # (barycentric projection of the PET embeddings through the plan, single-pass tcgen05 kernel) on the host
+    fused_host = torch.empty((n_loc, D), dtype=torch.float32).pin_memory()
+    fg_host = torch.empty(n_loc + m, dtype=torch.float32).pin_memory()
+
     def step_e2e():
         if world == 1:
-            out = b200ot.sinkhorn_from_embeddings(Xp, Yp, reg=EPS, numItermax=iters, stopThr=0.0, path=args.path)
+            out = b200ot.sinkhorn_from_embeddings(Xp, Yp, reg=EPS, numItermax=iters, stopThr=0.0, path=args.path,
+                                                  V=Yp, fused_out=fused_host)
             return out["err"]
         xd = Xp.to(dev, non_blocking=True)
         yd = Yp.to(dev, non_blocking=True)
         ops.cost_matrix(xd, yd, out=Cmat)
         f, g, inf = sharded.solve_sharded(Cmat, a_loc, b, EPS, max_iter=iters, tol=0.0, path=args.path, comm=comm,
                                           peer=peer)
-        f.cpu(), g.cpu()
+        fused = ops.apply_plan(Cmat, f, g, EPS, yd, normalise=True)  # rows are local: no communication
+        fused_host.copy_(fused, non_blocking=True)
+        fg_host[:n_loc].copy_(f, non_blocking=True)
+        fg_host[n_loc:].copy_(g, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
         return inf["err"]
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -435,13 +586,19 @@ def run_b200(args):
         e2e_s = float(t.item())
     e2e_value = iters / e2e_s
     h2d = (Xp.numel() + Yp.numel()) * 4
-    d2h = (n_loc + m) * 4 + 32
+    d2h = (n_loc + m) * 4 + 32 + n_loc * D * 4  # potentials, result block, fused embedding (n_loc x 512 fp32)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         # bounded sample (~20 s): calls at n = 8192 and one at 16384; `--impl reference` also measures n = 32768
         scaled, kind, sample = cpu_measure(args, 2, 1, 16384)
         cpu_baseline = {"value": scaled, "unit": UNIT, "cores": host_threads(), "kind": kind, "sample": sample}
+    extra = None
+    if not diag and not args.no_extras:
+        stepper = None  # release the workspace
+        extra = extras(torch, dist, ops, world, rank, dev, args)
+        if extra.get("online_c4"):
+            extra["online_c4"]["streaming_is_faster_by"] = value / extra["online_c4"]["iterations_per_s"]
     if rank != 0:
         if world > 1:
             _shutdown(dist)
@@ -484,10 +641,12 @@ def run_b200(args):
         "cpu_baseline": cpu_baseline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps,
-                "note": "pinned host embeddings -> H2D -> cost construction -> solve -> potentials D2H"},
+                "note": "pinned host embeddings -> H2D -> cost construction (tcgen05) -> solve -> fused embedding "
+                        "diag(1/P1) P Y (tcgen05, one pass over C) -> potentials and fused embedding D2H (pinned)"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "parity": parity,
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -527,6 +686,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=10, help="reference iterations per CPU call")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run value checks")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2 / C3 / online measurements")
+    ap.add_argument("--no-online", action="store_true", help="skip the online (cost-free) measurement")
     ap.add_argument("--no-sampler", action="store_true", help="diagnostic: do not sample clocks")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -249,18 +249,48 @@ int b200ot_sinkhorn_batched(const float* C, const float* X, const float* Y, int 
  *            perturbot/perturbot/eval/match.py:202-206 and, with V = pet^T, the
  *            reference's `pet @ T.t()` (MRI_PET_OT_OT_per_epoch_attn.py:728).
  * apply_t    Z = P^T U (U n x du, Z m x du), same options.
- * envelope   dX = 2 (diag(P1) X - P Y), dY = 2 (diag(P^T 1) Y - P^T X) scaled by `scale`:
- *            gradient of <P, C(X,Y)> at fixed P (new capability).  */
+ * These four are the generic SIMT kernels (any shape and alignment); large problems use the tensor-core forms
+ * b200ot_apply_plan_tc / b200ot_envelope_bwd declared below.                                     */
 int b200ot_plan(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
                 float* P, int ldp, void* stream);
+/* ot_cost: `out` must hold B200OT_OT_COST_DOUBLES doubles; out[0] is <P, C>, the rest is scratch for the
+ * fixed-order two-stage fold (the value is bit-reproducible: no floating-point atomics).        */
+#define B200OT_OT_COST_DOUBLES (1 + 148 * 8 + 1)
 int b200ot_ot_cost(const float* C, int ldc, int n, int m, const float* f, const float* g,
                    float eps, double* out, void* stream);
+/* Per-step plan guard of the reference (MRI_PET_OT_nojax.py:704-715): NaN -> 1e-8, then every row divided by its
+ * sum, zero sums replaced by 1e-8.  T == NULL: the plan of (C, f, g, eps) is evaluated on the fly and written
+ * normalised; T != NULL (n x m, ldt): an already materialised plan is sanitised (C, f, g ignored).   */
+int b200ot_plan_guard_rownorm(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                              const float* T, int ldt, float* P, int ldp, void* stream);
 int b200ot_apply_plan(const float* C, int ldc, int n, int m, const float* f, const float* g,
                       float eps, const float* V, int ldv, int dv, int normalise, float* Z,
                       int ldz, void* stream);
 int b200ot_apply_plan_t(const float* C, int ldc, int n, int m, const float* f, const float* g,
                         float eps, const float* U, int ldu, int du, int normalise, float* Z,
                         int ldz, void* stream);
+/* Tensor-core form of apply / apply_t (csrc/apply_tc.cu): ONE pass over C whatever dv <= 512 is.  The plan entries
+ * are evaluated once, split into two bf16 parts and fed to tcgen05.mma as the A operand against the pre-split
+ * right-hand side (3-term product p1.v2 + p2.v1 + p1.v1, fp32 accumulators in TMEM, error ~2^-16 per product);
+ * row sums of P come out of the same registers in fp32.  transpose = 0: Z (n x dv) = P V, V is m x dv;
+ * transpose = 1: Z (m x dv) = P^T V, V is n x dv.  normalise = 1 divides every row of Z by the row sum of P
+ * (0 -> 1e-30, perturbot/perturbot/eval/match.py:203-204).  rowsum_out (may be NULL) receives those row sums
+ * (P 1, or P^T 1 in the transposed form).  ws: 1024-byte aligned, b200ot_apply_plan_tc_workspace_bytes bytes
+ * (the pre-tiled bf16 parts of V and, for short outputs whose K range is split over several CTAs, the partial
+ * accumulators).                                                                                          */
+size_t b200ot_apply_plan_tc_workspace_bytes(int n, int m, int dv, int transpose);
+int b200ot_apply_plan_tc(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                         const float* V, int ldv, int dv, int transpose, int normalise, float* Z, int ldz,
+                         float* rowsum_out, void* ws, size_t ws_bytes, void* stream);
+/* Envelope gradient of <P, C(X, Y)> for the squared-Euclidean cost at fixed P (new capability; the reference never
+ * differentiates through OT, MRI_PET_OT_nojax.py:683-684), both halves in ONE launch of the same kernel:
+ *   dX = scale (diag(P 1) X - P Y)   (n x d),   dY = scale (diag(P^T 1) Y - P^T X)   (m x d),  scale = 2 for <P, C>.
+ * rowsum_out (n) / colsum_out (m) may be NULL.                                                              */
+size_t b200ot_envelope_bwd_workspace_bytes(int n, int m, int d);
+int b200ot_envelope_bwd(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                        const float* X, int ldx, const float* Y, int ldy, int d, float scale, float* dX, int lddx,
+                        float* dY, int lddy, float* rowsum_out, float* colsum_out, void* ws, size_t ws_bytes,
+                        void* stream);
 /* fused fusion loss of the reference forward: 1 - mean_i cos(A_i, B_i)
  * (MRI_PET_OT_nojax.py:552-560); out is one float.                                  */
 int b200ot_cosine_loss(const float* A, int lda, const float* B, int ldb, int rows, int d,

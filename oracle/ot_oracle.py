@@ -40,7 +40,8 @@ __all__ = [
     "sinkhorn_log", "sinkhorn_log_ott", "plan_from_potentials", "rows_given_g", "fot_bcd_ott",
     "get_feature_coupling_pot", "get_coupling_fot", "plan_guard_rownorm",
     "apply_plan_T", "barycentric", "cosine_loss", "ot_cost", "envelope_grads", "foscttm",
-    "group_features_by_label", "egw_ott", "get_coupling_egw_ott_fixed", "cotl_sinkhorn",
+    "group_features_by_label", "egw_ott", "get_coupling_egw_ott_fixed", "cotl_sinkhorn", "block_diag_mask",
+    "get_coupling_egw_all_ott", "get_coupling_egw_labels_ott", "get_coupling_leot_ott",
 ]
 
 
@@ -255,7 +256,7 @@ def plan_from_potentials(C, f, g, eps):
 
 
 def sinkhorn_log(C, a, b, eps, max_iter=1000, tol=1e-9, err_norm="l2", check_every=10,
-                 check_phase=1, stop_inclusive=False, f0=None, g0=None, log=False):
+                 check_phase=1, stop_inclusive=False, f0=None, g0=None, log=False, mask=None):
     """Log-domain Sinkhorn with a pluggable stopping rule.
 
     One iteration = ``g <- eps log b - eps LSE_i((f_i - C_ij)/eps)`` then
@@ -268,6 +269,8 @@ def sinkhorn_log(C, a, b, eps, max_iter=1000, tol=1e-9, err_norm="l2", check_eve
     0-based counter), ``check_phase=0`` reproduces ott's ``inner_iterations``.
     """
     C = np.asarray(C, dtype=np.float64)
+    if mask is not None:  # plan restricted to the support of `mask`: no mass where it is 0
+        C = np.where(np.asarray(mask) > 0, C, np.inf)
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     n, m = C.shape
@@ -297,7 +300,8 @@ def sinkhorn_log(C, a, b, eps, max_iter=1000, tol=1e-9, err_norm="l2", check_eve
             if (err <= tol) if stop_inclusive else (err < tol):
                 converged = True
                 break
-    P = plan_from_potentials(C, f, g, eps)
+    with np.errstate(invalid="ignore"):
+        P = plan_from_potentials(C, f, g, eps)
     if log:
         return P, {"err": errs, "f": f, "g": g, "n_iter": it, "converged": converged}
     return P
@@ -315,7 +319,7 @@ def rows_given_g(C_rows, a_rows, g, eps):
 
 
 def sinkhorn_log_ott(M, eps, a=None, b=None, max_iterations=2000, threshold=1e-3,
-                     inner_iterations=10, scale_cost="max_cost", log=False):
+                     inner_iterations=10, scale_cost="max_cost", log=False, mask=None):
     """ott-jax 0.6.0 ``linear.solve(Geometry(cost_matrix=M, epsilon=eps,
     scale_cost="max_cost"), max_iterations=N).matrix`` as called at
     ``perturbot/perturbot/match/fot.py:129-134`` (upstream, unverifiable here):
@@ -334,7 +338,7 @@ def sinkhorn_log_ott(M, eps, a=None, b=None, max_iterations=2000, threshold=1e-3
     else:
         raise ValueError(scale_cost)
     P, lg = sinkhorn_log(C, a, b, eps, max_iter=max_iterations, tol=threshold, err_norm="l1",
-                         check_every=inner_iterations, check_phase=0, log=True)
+                         check_every=inner_iterations, check_phase=0, log=True, mask=mask)
     lg["scaled_cost"] = C
     return (P, lg) if log else P
 
@@ -457,7 +461,7 @@ def cotl_sinkhorn(X_dict, Y_dict, reg=5e-3, niter=2000, log=False):
 # entropic Gromov-Wasserstein sample couplings
 # --------------------------------------------------------------------------
 def egw_ott(X, Y, eps=5e-3, gw_max_iterations=2000, sinkhorn_max_iterations=2000, gw_threshold=1e-3,
-            gw_min_iterations=5, sk_threshold=1e-3, sk_check_every=10):
+            gw_min_iterations=5, sk_threshold=1e-3, sk_check_every=10, mask=None):
     """ott-jax 0.6.0 ``GromovWasserstein(epsilon=eps, max_iterations=..., linear_solver=Sinkhorn(max_iterations=...))``
     on ``QuadraticProblem(PointCloud(x, x, scale_cost="max_cost"), PointCloud(y, y, scale_cost="max_cost"))``
     (``MRI_PET_OT_OT_per_epoch_attn.py:155-175``).  PARITY UNPINNED: ott is not in the tree; this restates its
@@ -467,7 +471,13 @@ def egw_ott(X, Y, eps=5e-3, gw_max_iterations=2000, sinkhorn_max_iterations=2000
     problem with the log-domain Sinkhorn of ``sinkhorn_log_ott`` (absolute epsilon, L1 error of the b-marginal
     every 10 iterations, threshold 1e-3) warm-started from the previous potentials, and records
     ``cost = <a, f> + <b, g>``; it stops once ``iteration >= min_iterations`` and
-    ``isclose(costs[i - 2], costs[i - 1], rtol=threshold)``.  Returns ``(T, log)``."""
+    ``isclose(costs[i - 2], costs[i - 1], rtol=threshold)``.  Returns ``(T, log)``.
+
+    ``mask`` (n x m of 0/1, optional): the label-aware form called at ``perturbot/perturbot/match/ott_egwl.py:77-105``
+    (``QuadraticProblem(..., labels_a, labels_b, n_labels, block_diag_mat)`` of a modified OTT that is NOT in the
+    tree, version unknown).  Restated from that function's docstring (``T_ij > 0 => l_{x_i} = l_{y_j}``, :37): the
+    coupling is restricted to the support of ``mask`` -- start coupling ``(a b^T) * mask``, every linearised cost
+    infinite outside it -- with the global uniform marginals kept.  PARITY UNPINNED."""
     X = np.asarray(X, dtype=np.float64)
     Y = np.asarray(Y, dtype=np.float64)
     n, m = X.shape[0], Y.shape[0]
@@ -479,6 +489,9 @@ def egw_ott(X, Y, eps=5e-3, gw_max_iterations=2000, sinkhorn_max_iterations=2000
     b = np.full(m, 1.0 / m)
     la, lb = np.log(a), np.log(b)
     T = np.outer(a, b)
+    if mask is not None:
+        mask = np.asarray(mask) > 0
+        T = T * mask
     f = np.zeros(n)
     g = np.zeros(m)
     costs = []
@@ -487,6 +500,8 @@ def egw_ott(X, Y, eps=5e-3, gw_max_iterations=2000, sinkhorn_max_iterations=2000
     outer_conv = False
     while len(costs) < gw_max_iterations:
         M = ((C1 * C1) @ T.sum(1))[:, None] + ((C2 * C2) @ T.sum(0))[None, :] - 2.0 * C1 @ T @ C2
+        if mask is not None:
+            M = np.where(mask, M, np.inf)
         it = 0
         inner_conv = False
         while it < sinkhorn_max_iterations:
@@ -501,6 +516,8 @@ def egw_ott(X, Y, eps=5e-3, gw_max_iterations=2000, sinkhorn_max_iterations=2000
         inner_total += it
         T = np.exp((f[:, None] + g[None, :] - M) / eps)
         costs.append(float(a @ f + b @ g))
+        if not np.isfinite(costs[-1]):
+            break
         k = len(costs)
         if k >= 2:
             outer_conv = bool(abs(costs[-2] - costs[-1]) <= 1e-8 + gw_threshold * abs(costs[-1]))
@@ -521,6 +538,53 @@ def get_coupling_egw_ott_fixed(data, eps=5e-3, gw_max_iterations=2000, sinkhorn_
         Ts[l] = T
         log[l] = lg
     return Ts, log
+
+
+def _concat_with_labels(X_dict, Y_dict):
+    keys = list(X_dict.keys())
+    Xs = np.concatenate([np.asarray(X_dict[l], dtype=np.float64) for l in keys], axis=0)
+    Xt = np.concatenate([np.asarray(Y_dict[l], dtype=np.float64) for l in keys], axis=0)
+    sl = np.concatenate([np.repeat(l, np.asarray(X_dict[l]).shape[0]) for l in keys])
+    tl = np.concatenate([np.repeat(l, np.asarray(Y_dict[l]).shape[0]) for l in keys])
+    return Xs, Xt, sl, tl
+
+
+def block_diag_mask(labels_a, labels_b):
+    """``create_block_diag_mat`` (``perturbot/perturbot/match/ott_egwl.py:16-22``): 1 where the labels agree."""
+    labels_a, labels_b = np.asarray(labels_a), np.asarray(labels_b)
+    out = np.zeros((len(labels_a), len(labels_b)))
+    for l in np.unique(labels_a):
+        out[np.ix_(np.where(labels_a == l)[0], np.where(labels_b == l)[0])] = 1.0
+    return out
+
+
+def get_coupling_egw_all_ott(data, eps=5e-3):
+    """``perturbot/perturbot/match/ott_egwl.py:209-297``: ONE entropic GW problem over all samples (labels
+    disregarded), ``GromovWasserstein(epsilon=eps, max_iterations=1000)`` with the default inner ``Sinkhorn``."""
+    Xs, Xt, _, _ = _concat_with_labels(*data)
+    T, lg = egw_ott(Xs, Xt, eps, gw_max_iterations=1000, sinkhorn_max_iterations=2000)
+    return T, lg
+
+
+def get_coupling_egw_labels_ott(data, eps=5e-3):
+    """``perturbot/perturbot/match/ott_egwl.py:25-127``: the label-constrained entropic GW (block-diagonal support,
+    see ``egw_ott(mask=...)``), ``max_iterations=2000`` outer and inner; returns the per-label diagonal blocks."""
+    Xs, Xt, sl, tl = _concat_with_labels(*data)
+    T, lg = egw_ott(Xs, Xt, eps, gw_max_iterations=2000, sinkhorn_max_iterations=2000,
+                    mask=block_diag_mask(sl, tl))
+    return {l: T[sl == l, :][:, tl == l] for l in np.unique(sl)}, lg
+
+
+def get_coupling_leot_ott(data, eps=5e-3):
+    """``perturbot/perturbot/match/ott_egwl.py:375-454``: label-constrained entropic OT.  Squared-Euclidean cost over
+    all samples divided by its maximum (``PointCloud(scale_cost="max_cost").cost_matrix``, :426-427), then ott
+    ``Sinkhorn()`` on ``LinearProblem(geom, labels_a, labels_b)`` of the modified OTT (not in the tree): restated as
+    the plan restricted to matching labels with the global uniform marginals kept.  PARITY UNPINNED."""
+    Xs, Xt, sl, tl = _concat_with_labels(*data)
+    C = sqeuclid_cost(Xs, Xt)
+    C = C / C.max()
+    T, lg = sinkhorn_log_ott(C, eps, scale_cost=None, mask=block_diag_mask(sl, tl), log=True)
+    return {l: T[sl == l, :][:, tl == l] for l in np.unique(sl)}, lg
 
 
 # --------------------------------------------------------------------------

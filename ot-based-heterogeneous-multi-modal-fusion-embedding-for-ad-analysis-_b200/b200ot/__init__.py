@@ -9,7 +9,8 @@ operators; ``b200ot.torch_ops`` the ``torch.library`` custom ops and the autogra
 from ._lib import B200OTError, LIB_PATH  # noqa: F401
 from . import ops  # noqa: F401
 from .api import (Geometry, SinkhornOutput, dist, unif, foscttm, get_FOSCTTM, group_features_by_label, fot_numpy, get_coupling_fot, get_feature_coupling_pot,  # noqa: F401
-                  get_coupling_egw_ott_fixed, get_coupling_egw_ott, get_coupling_eot_ott, cotl_numpy, get_coupling_cotl_sinkhorn, compute_pet_to_mri_coupling,
+                  get_coupling_egw_ott_fixed, get_coupling_egw_ott, get_coupling_eot_ott, get_coupling_egw_all_ott,
+                  get_coupling_egw_labels_ott, get_coupling_leot_ott, per_step_feature_plan, cotl_numpy, get_coupling_cotl_sinkhorn, compute_pet_to_mri_coupling,
                   init_matrix_np, linear_solve, mdict_to_matrix, sinkhorn, sinkhorn_from_embeddings,
                   sinkhorn_scaling)
 

@@ -17,6 +17,7 @@ OK, E_INVALID, E_WORKSPACE, E_LAUNCH, E_UNSUPPORTED, E_NUMERIC = 0, -1, -2, -3, 
 NORM_L2, NORM_L2SQ, NORM_L1 = 0, 1, 2
 PATH_AUTO, PATH_FUSED, PATH_ROBUST = 0, 1, 2
 COST_SQEUCLIDEAN, COST_COSINE = 0, 1
+OT_COST_DOUBLES = 1 + 148 * 8 + 1  # B200OT_OT_COST_DOUBLES
 NORMS = {"l2": NORM_L2, "l2sq": NORM_L2SQ, "l1": NORM_L1}
 PATHS = {"auto": PATH_AUTO, "fused": PATH_FUSED, "robust": PATH_ROBUST}
 COSTS = {"sqeuclidean": COST_SQEUCLIDEAN, "cosine": COST_COSINE}
@@ -89,8 +90,13 @@ SIGNATURES = {
                                      _p, _p, _p]),
     "b200ot_plan": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _p]),
     "b200ot_ot_cost": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _p]),
+    "b200ot_plan_guard_rownorm": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _p, _i, _p]),
     "b200ot_apply_plan": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _i, _i, _p, _i, _p]),
     "b200ot_apply_plan_t": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _i, _i, _p, _i, _p]),
+    "b200ot_apply_plan_tc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b200ot_apply_plan_tc": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p]),
+    "b200ot_envelope_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "b200ot_envelope_bwd": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _p, _i, _i, _f, _p, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "b200ot_cosine_loss": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),
     "b200ot_foscttm": (_i, [_p, _i, _i, _p, _p]),
     "b200ot_egw_batched": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _i, _f, _i, _i, _f, _p, _p, _p, _p]),

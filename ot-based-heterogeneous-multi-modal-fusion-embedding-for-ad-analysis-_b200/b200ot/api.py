@@ -69,6 +69,9 @@ class _Conv:
         return t.to(device=self.home, dtype=self.torch_dtype)
 
 
+_MASKED_COST = 1e30  # cost of a forbidden pair: exp(-1e30 / eps) is exactly 0 in fp32, and k * 1e30 stays finite
+
+
 def _uniform(n, device):
     return torch.full((n,), 1.0 / n, dtype=torch.float32, device=device)
 
@@ -188,7 +191,8 @@ class SinkhornOutput:
 
 
 def linear_solve(geom: Geometry, a=None, b=None, max_iterations=2000, threshold=1e-3,
-                 inner_iterations=10, *, path="auto", device=None, **kwargs) -> SinkhornOutput:
+                 inner_iterations=10, *, path="auto", device=None, f0=None, g0=None, mask=None, _device_out=False,
+                 **kwargs) -> SinkhornOutput:
     """Drop-in for ``ott.solvers.linear.solve(geom, max_iterations=N)`` (fot.py:129-134):
     cost divided by its max (``scale_cost="max_cost"``), eps absolute on the scaled cost,
     zero start potentials, g-then-f updates, L1 error of the b-marginal every
@@ -202,14 +206,18 @@ def linear_solve(geom: Geometry, a=None, b=None, max_iterations=2000, threshold=
         ops.scale_by_inv_(Cs, ops.matrix_max(Cs))
     elif geom.scale_cost not in (None, 1.0, 1, "none"):
         raise B200OTError(f"scale_cost={geom.scale_cost!r} is not used by the reference")
+    if mask is not None:  # plan restricted to the support of `mask` (label-aware solves): no mass elsewhere
+        Cs.masked_fill_(~cv.to_dev(mask, dtype=torch.bool), _MASKED_COST)
     ad = _uniform(n, cv.device) if a is None else cv.to_dev(a)
     bd = _uniform(m, cv.device) if b is None else cv.to_dev(b)
     f, g, info = ops.sinkhorn_potentials(Cs, ad, bd, geom.epsilon, max_iter=int(max_iterations),
                                          tol=float(threshold), check_every=int(inner_iterations),
-                                         check_phase=0, err_norm="l1", stop_inclusive=False, path=path)
+                                         check_phase=0, err_norm="l1", stop_inclusive=False, path=path,
+                                         f0=None if f0 is None else cv.to_dev(f0),
+                                         g0=None if g0 is None else cv.to_dev(g0))
     P = ops.plan(Cs, f, g, geom.epsilon)
-    return SinkhornOutput(cv.back(P), cv.back(f), cv.back(g), info["n_iter"], info["converged"],
-                          cv.back(info["errs"]))
+    back = (lambda t: t) if _device_out else cv.back
+    return SinkhornOutput(back(P), back(f), back(g), info["n_iter"], info["converged"], back(info["errs"]))
 
 
 # ---------------------------------------------------------------------------
@@ -283,27 +291,77 @@ def get_feature_coupling_pot(data, Ts, eps=5e-3, *, numItermax=2000, stopThr=1e-
     return cv.back(Tv), {}
 
 
-def fot_numpy(X1, X2, Ts, reg, reg2, eps=1e-7, niter=2000, C1=None, C2=None, log=False,
-              verbose=False, *, device=None, path="auto"):
-    """Drop-in for ``fot_numpy`` (perturbot/perturbot/match/fot.py:14-152) with ``Ts`` fixed:
-    ``Ts /= Ts.sum()``, ``w1 = Ts.sum(0)``, ``w2 = Ts.sum(1)`` (the reference's swapped axes),
-    cost ``constC - hC1 Ts hC2^T``, inner solve = ott ``linear.solve`` semantics.  Because ``Ts``
-    never changes the reference's second BCD round repeats the first solve bit for bit and
-    exits on ``delta < 1e-16`` (:145); that repeat is not re-run here."""
+def per_step_feature_plan(mri_feat, pet_feat, eps=1e-2, *, numItermax=2000, stopThr=1e-9, err_norm="l2",
+                          stop_inclusive=False, device=None):
+    """The per-step OT block of ``MultimodalMRI_PET_OT.forward`` (MRI_PET_OT_nojax.py:679-715) without the
+    device -> host -> device round trip: identity sample coupling ``Ts = I / B`` (:687), ``get_feature_coupling_pot
+    (({0: mri}, {0: pet}), {0: Ts}, eps=1e-2)`` (:694-698), then the guard ``NaN -> 1e-8`` and the row
+    normalisation with zero sums replaced by 1e-8 (:704-715) fused into the kernel that writes the plan
+    (``b200ot_plan_guard_rownorm``: the unnormalised plan is never stored).  Returns the (d_mri, d_pet) fp32
+    coupling the forward applies as ``pet @ T.t()`` (:718); CUDA tensors in -> CUDA tensor out."""
+    cv = _Conv(mri_feat, device)
+    Xd, Yd = cv.to_dev(mri_feat).detach(), cv.to_dev(pet_feat).detach()
+    B = Xd.shape[0]
+    if Yd.shape[0] != B:
+        raise B200OTError("per_step_feature_plan: one PET row per MRI row (identity sample coupling)")
+    Ts = torch.eye(B, dtype=torch.float32, device=cv.device) / B
+    w = torch.full((B,), 1.0 / B, dtype=torch.float32, device=cv.device)
+    M = ops.fot_cost(Xd, Yd, Ts, w, w)
+    d1, d2 = M.shape
+    f0 = torch.full((d1,), float(eps) * math.log(1.0 / d1), dtype=torch.float32, device=cv.device)
+    g0 = torch.full((d2,), float(eps) * math.log(1.0 / d2), dtype=torch.float32, device=cv.device)
+    f, g, _ = ops.sinkhorn_potentials(M, _uniform(d1, cv.device), _uniform(d2, cv.device), float(eps),
+                                      max_iter=int(numItermax), tol=float(stopThr), check_every=10, check_phase=1,
+                                      err_norm=err_norm, stop_inclusive=stop_inclusive, f0=f0, g0=g0, floor_patience=3)
+    T = ops.plan_guard_rownorm(M, f, g, float(eps))
+    return T if not cv.is_numpy else cv.back(T)
+
+
+def fot_numpy(X1, X2, Ts, v1=None, v2=None, niter=10, algo="emd", reg=0, algo2="emd", reg2=0, verbose=True,
+              log=False, random_init=False, C_lin=None, *, device=None, path="auto", warm_start=None):
+    """Drop-in for ``fot_numpy`` (perturbot/perturbot/match/fot.py:14-152), same positional order and defaults.
+    With ``Ts`` fixed: ``Ts /= Ts.sum()``, ``w1 = Ts.sum(0)``, ``w2 = Ts.sum(1)`` (the reference's swapped axes,
+    :109-110), cost ``constC - hC1 Ts hC2^T`` (:128), inner solve = ott ``linear.solve(Geometry(cost_matrix=M,
+    epsilon=reg2, scale_cost="max_cost"), max_iterations=2000)`` (:129-134), ``cost = sum(M * Tv)`` (:137).
+
+    As in the reference, ``v1``, ``v2``, ``algo``, ``algo2``, ``reg`` and ``C_lin`` do not enter the result (the
+    feature solve is always the entropic ott solve with ``reg2``; ``v1``/``v2`` only seed ``random_init``).
+    ``random_init=True`` needs scipy's sparse gamma initialisation of the reference and is rejected; ``reg2`` must be
+    positive (the reference's default 0 makes ott's epsilon 0).  Because ``Ts`` never changes, the reference's
+    second BCD round repeats the first solve bit for bit and exits on ``delta < 1e-16`` (:145): that repeat is not
+    re-run, its cost is logged twice.  Returns ``(Tv, cost)`` or ``(Tv, cost, log)`` like the reference.
+
+    ``warm_start=(f0, g0)`` (opt-in, not in the reference): start the solve from the potentials of a previous
+    call (``log["potentials"]``), e.g. the previous epoch's; changes the iteration count, not the fixed point."""
+    if random_init:
+        raise B200OTError("fot_numpy: random_init needs scipy's sparse gamma initialisation and is not served")
+    if not (reg2 > 0):
+        raise B200OTError("fot_numpy: reg2 must be > 0 (it is ott's epsilon for the feature solve, fot.py:131)")
     cv = _Conv(X1, device)
     Xd, Yd = cv.to_dev(X1), cv.to_dev(X2)
     Td = cv.to_dev(Ts, dtype=torch.float64)
     Td = (Td / Td.sum()).to(torch.float32)
     M = ops.fot_cost(Xd, Yd, Td, Td.sum(dim=0), Td.sum(dim=1))
-    cost_unscaled = M.clone() if log else None
+    cost_unscaled = M.clone()
     t0 = time.time()
-    out = linear_solve(Geometry(cost_matrix=M, epsilon=reg2, scale_cost="max_cost"), max_iterations=niter,
-                       path=path)
+    f0 = g0 = None
+    if warm_start is not None:
+        f0, g0 = (None if w is None else cv.to_dev(w) for w in warm_start)
+    out = linear_solve(Geometry(cost_matrix=M, epsilon=reg2, scale_cost="max_cost"), max_iterations=2000,
+                       path=path, f0=f0, g0=g0, _device_out=True)
     Tv_d = out.matrix
+    cost = float((cost_unscaled.double() * Tv_d.double()).sum())
+    rounds = [cost] if int(niter) <= 1 else [cost, cost]
+    if verbose:
+        for i, c in enumerate(rounds):
+            print("Delta: {0}  Loss: {1}".format(0.0 if i else float(torch.linalg.norm(
+                (Tv_d - 1.0 / Tv_d.numel()).double())), c))
+        if len(rounds) > 1:
+            print("converged at iter ", 1)
     if log:
-        cost = float((cost_unscaled.double() * Tv_d.double()).sum())
-        return cv.back(Tv_d), cost, {"cost": [cost, cost], "time": time.time() - t0, "n_iters": out.n_iters}
-    return cv.back(Tv_d), float("nan")
+        return cv.back(Tv_d), cost, {"cost": rounds, "time": time.time() - t0, "n_iters": out.n_iters,
+                                     "potentials": (out.f, out.g)}
+    return cv.back(Tv_d), cost
 
 
 def get_coupling_fot(data, Ts, eps=5e-3, *, device=None, path="auto"):
@@ -334,7 +392,8 @@ def get_coupling_fot(data, Ts, eps=5e-3, *, device=None, path="auto"):
     X = _concat(X_dict, keys)
     Y = _concat(Y_dict, keys)
     t0 = time.time()
-    Tv, cost, lg = fot_numpy(X, Y, Ts, eps, eps, niter=2000, log=True, device=device, path=path)
+    Tv, cost, lg = fot_numpy(X, Y, Ts, reg=eps, reg2=eps, niter=2000, log=True, verbose=False, device=device,
+                             path=path)
     lg["time"] = time.time() - t0
     return Tv, lg
 
@@ -364,7 +423,7 @@ def group_features_by_label(y, p, max_samples_per_label=None):
 
 
 def cotl_numpy(X_dict, Y_dict, w1=None, w2=None, v1=None, v2=None, niter=100, algo="emd", reg=0.2, algo2="emd",
-               reg2=0.2, verbose=True, log=False, random_init=False, C_lin=None, *, device=None):
+               reg2=0.2, verbose=True, log=False, random_init=False, C_lin=None, *, device=None, warm_start=False):
     """Drop-in for ``cotl_numpy`` (perturbot/perturbot/match/cot_labels.py:14-225) in its entropic form
     (``algo="sinkhorn", algo2="sinkhorn"``, what ``get_coupling_cotl_sinkhorn`` runs): label-constrained COOT by block
     coordinate descent.  Per label a sample coupling on ``constC_s - hC1_s Tv hC2_s^T`` (:172), then one feature
@@ -372,7 +431,12 @@ def cotl_numpy(X_dict, Y_dict, w1=None, w2=None, v1=None, v2=None, niter=100, al
     (``b200ot_fot_cost``) and every solve is the engine's ott-flavoured ``linear_solve``; couplings stay on the
     device between rounds.  Reference quirks kept: the feature solve uses ``reg`` (``reg2`` is never read, :201);
     ``Tsold = Ts`` aliases the dict so ``delta`` only sees ``Tv`` (:162,209-211); exit on ``delta < 1e-16`` or
-    ``|cost_old - cost| < 1e-7`` (:219).  The ``"emd"`` variants are POT's network simplex and are not served."""
+    ``|cost_old - cost| < 1e-7`` (:219).  The ``"emd"`` variants are POT's network simplex and are not served.
+
+    ``warm_start=True`` (opt-in, not in the reference): every solve of BCD round r + 1 starts from the
+    potentials its counterpart reached in round r instead of from zero.  The costs change little between rounds, so
+    the inner solves converge in a fraction of the iterations (``log["inner_iterations"]`` records the total); the
+    fixed point of each solve is the same, the iterates (and so the last digits of the couplings) are not."""
     if algo != "sinkhorn" or algo2 != "sinkhorn":
         raise B200OTError("cotl_numpy: only algo='sinkhorn', algo2='sinkhorn' run on the B200 engine "
                           "('emd' is POT's network-simplex solver)")
@@ -405,20 +469,28 @@ def cotl_numpy(X_dict, Y_dict, w1=None, w2=None, v1=None, v2=None, niter=100, al
                         dtype=torch.float32, device=dev) for k in labels}
     Tv = torch.full((d1, d2), 1.0 / (d1 * d2), dtype=torch.float32, device=dev)
     cost = float("inf")
-    log_out = {"cost": []}
+    log_out = {"cost": [], "inner_iterations": 0}
+    pot = {}  # potentials of the previous round's solves (warm_start)
     for i in range(int(niter)):
         Tv_old, cost_old = Tv, cost
         for k in labels:  # sample OT per label: rows of the transposed data play the role of features
             M_k = ops.fot_cost(Xt[k], Yt[k], Tv, v1d, v2d)
             if Clin is not None:
                 M_k = M_k + Clin
-            Ts[k] = linear_solve(Geometry(cost_matrix=M_k, epsilon=reg, scale_cost="max_cost"),
-                                 max_iterations=2000).matrix
+            f0, g0 = pot.get(k, (None, None)) if warm_start else (None, None)
+            out_k = linear_solve(Geometry(cost_matrix=M_k, epsilon=reg, scale_cost="max_cost"),
+                                 max_iterations=2000, f0=f0, g0=g0, _device_out=True)
+            Ts[k], pot[k] = out_k.matrix, (out_k.f, out_k.g)
+            log_out["inner_iterations"] += out_k.n_iters
         M = None
         for k in labels:  # global feature OT on the summed cost
             Mk = ops.fot_cost(Xd[k], Yd[k], Ts[k], w1d[k], w2d[k])
             M = Mk if M is None else M + Mk
-        Tv = linear_solve(Geometry(cost_matrix=M, epsilon=reg, scale_cost="max_cost"), max_iterations=2000).matrix
+        f0, g0 = pot.get("_features", (None, None)) if warm_start else (None, None)
+        out_v = linear_solve(Geometry(cost_matrix=M, epsilon=reg, scale_cost="max_cost"), max_iterations=2000,
+                             f0=f0, g0=g0, _device_out=True)
+        Tv, pot["_features"] = out_v.matrix, (out_v.f, out_v.g)
+        log_out["inner_iterations"] += out_v.n_iters
         tot = float(Tv.double().sum())
         if not abs(tot - 1.0) < 1e-8:
             Tv = (Tv.double() / tot).float()
@@ -461,7 +533,9 @@ def get_coupling_egw_ott_fixed(data, eps: float = 5e-3, gw_max_iterations: int =
     the MRI and PET embeddings of that label, on max-scaled squared-Euclidean point-cloud geometries.  All labels
     are solved by ONE kernel launch, one CTA per label.  ``data = (X_dict, Y_dict)`` with NumPy arrays (as in the
     reference: results come back as NumPy) or torch tensors (CUDA: couplings stay on the device).  Returns
-    ``(Ts, log)`` with the reference's log keys; NaN features are mapped to 0 with a message (:148-151)."""
+    ``(Ts, log)`` with the reference's log keys; NaN features are mapped to 0 with a message (:148-151).
+    Labels with more than 64 samples on either side (``max_samples_per_label=None``; ``--max-jax-samples 128``) do
+    not fit the shared-memory kernel and are solved one at a time on the dense path (``_egw_dense``, fp32)."""
     X_dict, Y_dict = data
     labels = list(X_dict.keys())
     conv = _Conv(X_dict[labels[0]], device)
@@ -477,16 +551,167 @@ def get_coupling_egw_ott_fixed(data, eps: float = 5e-3, gw_max_iterations: int =
         Ys.append(y)
     cost_time = time.time() - t0
     t0 = time.time()
-    Ts, info = ops.egw_batched(Xs, Ys, eps, gw_max_iterations, sinkhorn_max_iterations)
-    host = {k: v.cpu() for k, v in info.items()}
-    dt = time.time() - t0
+    # labels of at most 64 x 64 samples: ONE launch, one CTA per label, everything in shared memory (float64);
+    # larger labels (max_samples_per_label=None, or args.max_jax_samples = 128) take the dense path, one at a time
+    small = [i for i in range(len(labels)) if Xs[i].shape[0] <= _EGW_SMEM_MAX and Ys[i].shape[0] <= _EGW_SMEM_MAX]
     out_T, log = {}, {}
-    for i, l in enumerate(labels):
-        out_T[l] = conv.back(Ts[i])
-        log[l] = {"n_iters_outer": int(host["n_iters_outer"][i]), "converged_inner": bool(host["converged_inner"][i]),
-                  "converged_outer": bool(host["converged_outer"][i]), "GW cost": float(host["GW cost"][i]),
-                  "inner_iterations": int(host["inner_iterations"][i]), "time": dt, "cost_time": cost_time}
-    return out_T, log
+    if small:
+        Ts, info = ops.egw_batched([Xs[i] for i in small], [Ys[i] for i in small], eps, gw_max_iterations,
+                                   sinkhorn_max_iterations)
+        host = {k: v.cpu() for k, v in info.items()}
+        for j, i in enumerate(small):
+            out_T[labels[i]] = conv.back(Ts[j])
+            log[labels[i]] = {"n_iters_outer": int(host["n_iters_outer"][j]),
+                              "converged_inner": bool(host["converged_inner"][j]),
+                              "converged_outer": bool(host["converged_outer"][j]), "GW cost": float(host["GW cost"][j]),
+                              "inner_iterations": int(host["inner_iterations"][j])}
+    for i in range(len(labels)):
+        if i in small:
+            continue
+        T, lg = _egw_dense(Xs[i], Ys[i], eps, gw_max_iterations, sinkhorn_max_iterations)
+        out_T[labels[i]] = conv.back(T)
+        log[labels[i]] = lg
+    dt = time.time() - t0
+    out_T = {l: out_T[l] for l in labels}  # the reference's key order
+    for l in labels:
+        log[l]["time"], log[l]["cost_time"] = dt, cost_time
+    return out_T, {l: log[l] for l in labels}
+
+
+_EGW_SMEM_MAX = 64  # kEgwMax of csrc/egw.cu: samples per side the one-CTA-per-label kernel holds in shared memory
+
+
+def _egw_dense(X, Y, eps, gw_max_iterations=2000, sinkhorn_max_iterations=2000, mask=None, gw_threshold=1e-3,
+               gw_min_iterations=5, sk_threshold=1e-3, sk_check_every=10):
+    """Entropic Gromov-Wasserstein of ANY size on device tensors: ott ``GromovWasserstein`` semantics as in
+    ``get_coupling_egw_ott_fixed`` (squared-Euclidean geometries divided by their maximum, square loss, uniform
+    marginals, warm-started inner log-domain Sinkhorn, outer stop on ``isclose(cost[-2], cost[-1], rtol=1e-3)`` after
+    5 iterations), with the per-iteration work on the engine's kernels: the linearised cost
+    ``(C1^2) T1 (+) (C2^2) T^T 1 - 2 C1 T C2`` is ``b200ot_fot_cost``, the inner solve ``b200ot_sinkhorn_solve``
+    (resident kernel for these sizes), the coupling ``b200ot_plan``.  ``mask`` restricts the coupling to its
+    support (label-aware form).  fp32, unlike the float64 shared-memory kernel for labels of <= 64 samples."""
+    dev = X.device
+    n, m = X.shape[0], Y.shape[0]
+    C1 = ops.cost_matrix(X, X, impl="simt" if n < 512 else "auto")
+    C2 = ops.cost_matrix(Y, Y, impl="simt" if m < 512 else "auto")
+    C1.clamp_(min=0.0)  # |x_i - x_i|^2 is 0, not -1e-7
+    C2.clamp_(min=0.0)
+    ops.scale_by_inv_(C1, ops.matrix_max(C1))
+    ops.scale_by_inv_(C2, ops.matrix_max(C2))
+    a, b = _uniform(n, dev), _uniform(m, dev)
+    T = torch.outer(a, b)
+    if mask is not None:
+        mask = mask.to(device=dev, dtype=torch.bool)
+        T = T * mask
+    f = torch.zeros(n, dtype=torch.float32, device=dev)
+    g = torch.zeros(m, dtype=torch.float32, device=dev)
+    costs, inner_total, inner_conv, outer_conv = [], 0, False, False
+    while len(costs) < int(gw_max_iterations):
+        M = ops.fot_cost(C1, C2, T, T.sum(dim=1), T.sum(dim=0))
+        if mask is not None:
+            M.masked_fill_(~mask, _MASKED_COST)
+        f, g, info = ops.sinkhorn_potentials(M, a, b, float(eps), max_iter=int(sinkhorn_max_iterations),
+                                             tol=float(sk_threshold), check_every=int(sk_check_every), check_phase=0,
+                                             err_norm="l1", f0=f, g0=g)
+        inner_total += info["n_iter"]
+        inner_conv = bool(info["converged"])
+        T = ops.plan(M, f, g, float(eps))
+        ff, gg = f.double(), g.double()
+        costs.append(float(ff[torch.isfinite(ff)].sum() / n + gg[torch.isfinite(gg)].sum() / m))
+        if not math.isfinite(costs[-1]):
+            break
+        k = len(costs)
+        if k >= 2:
+            outer_conv = abs(costs[-2] - costs[-1]) <= 1e-8 + gw_threshold * abs(costs[-1])
+            if outer_conv and k >= gw_min_iterations:
+                break
+    return T, {"n_iters_outer": len(costs), "converged_inner": inner_conv, "converged_outer": bool(outer_conv),
+               "GW cost": costs[-1], "inner_iterations": inner_total}
+
+
+def _concat_with_labels(data, cv):
+    """Concatenate both sides in first-seen label order with their label vectors (ott_egwl.py:66-75)."""
+    X_dict, Y_dict = data
+    keys = list(X_dict.keys())
+    X = torch.cat([cv.to_dev(X_dict[l]) for l in keys])
+    Y = torch.cat([cv.to_dev(Y_dict[l]) for l in keys])
+    sl = np.concatenate([np.repeat(l, len(X_dict[l])) for l in keys])
+    tl = np.concatenate([np.repeat(l, len(Y_dict[l])) for l in keys])
+    return X, Y, sl, tl
+
+
+def _label_mask(sl, tl, device):
+    """``create_block_diag_mat`` (ott_egwl.py:16-22) as a boolean device tensor: True where the labels agree."""
+    s_t = torch.as_tensor(np.unique(sl, return_inverse=True)[1], device=device)
+    uniq = {v: i for i, v in enumerate(np.unique(sl))}
+    t_t = torch.as_tensor(np.array([uniq.get(v, -1) for v in tl]), device=device)
+    return s_t[:, None] == t_t[None, :]
+
+
+def _blocks_by_label(T, sl, tl, cv):
+    dev = T.device
+    out = {}
+    for l in np.unique(sl):
+        ri = torch.as_tensor(np.where(sl == l)[0], device=dev)
+        ci = torch.as_tensor(np.where(tl == l)[0], device=dev)
+        out[l] = cv.back(T.index_select(0, ri).index_select(1, ci))
+    return out
+
+
+def get_coupling_egw_all_ott(data, eps: float = 5e-3, *, device=None):
+    """Drop-in for ``get_coupling_egw_all_ott`` (perturbot/perturbot/match/ott_egwl.py:209-297): ONE entropic
+    Gromov-Wasserstein problem over all samples of all labels (labels disregarded), ``GromovWasserstein(epsilon=eps,
+    max_iterations=1000)`` with the default inner ``Sinkhorn``.  Returns ``(T, log)`` with the full (n, m) coupling."""
+    cv = _Conv(next(iter(data[0].values())), device)
+    t0 = time.time()
+    X, Y, _, _ = _concat_with_labels(data, cv)
+    cost_time = time.time() - t0
+    t0 = time.time()
+    T, log = _egw_dense(X, Y, eps, gw_max_iterations=1000, sinkhorn_max_iterations=2000)
+    log["time"], log["cost_time"] = time.time() - t0, cost_time
+    return cv.back(T), log
+
+
+def get_coupling_egw_labels_ott(data, eps: float = 5e-3, *, device=None):
+    """Drop-in for ``get_coupling_egw_labels_ott`` (perturbot/perturbot/match/ott_egwl.py:25-127): entropic
+    Gromov-Wasserstein over all samples with the coupling restricted to pairs of equal label
+    (``T_ij > 0 => l_{x_i} = l_{y_j}``, :37; ``block_diag_mat``, :16-22,84), ``max_iterations=2000`` outer and inner.
+    The reference calls a modified OTT (``labels_a / labels_b / n_labels / block_diag_mat`` on ``QuadraticProblem``)
+    that is not in its tree; the constraint is served as a support mask on the start coupling and on every
+    linearised cost, global uniform marginals kept.  Returns ``(T_dict, log)``: the diagonal blocks keyed by label
+    in ``np.unique`` order, like the reference (:124-127)."""
+    cv = _Conv(next(iter(data[0].values())), device)
+    t0 = time.time()
+    X, Y, sl, tl = _concat_with_labels(data, cv)
+    mask = _label_mask(sl, tl, X.device)
+    cost_time = time.time() - t0
+    t0 = time.time()
+    T, log = _egw_dense(X, Y, eps, gw_max_iterations=2000, sinkhorn_max_iterations=2000, mask=mask)
+    log["time"], log["cost_time"] = time.time() - t0, cost_time
+    return _blocks_by_label(T, sl, tl, cv), log
+
+
+def get_coupling_leot_ott(data, eps: float = 5e-3, *, device=None):
+    """Drop-in for ``get_coupling_leot_ott`` (perturbot/perturbot/match/ott_egwl.py:375-454): label-constrained
+    entropic OT.  Squared-Euclidean cost over all samples divided by its maximum
+    (``PointCloud(scale_cost="max_cost").cost_matrix``, :426-427; built on tcgen05 for large inputs), then ott
+    ``Sinkhorn()`` on ``LinearProblem(geom, labels_a, labels_b)`` of the modified OTT: served as the engine's
+    ott-flavoured solve with the plan restricted to pairs of equal label.  Returns ``(T_dict, log)`` with the
+    reference's log keys (``OT cost`` = dual value)."""
+    cv = _Conv(next(iter(data[0].values())), device)
+    t0 = time.time()
+    X, Y, sl, tl = _concat_with_labels(data, cv)
+    C = ops.cost_matrix(X, Y)
+    mask = _label_mask(sl, tl, X.device)
+    cost_time = time.time() - t0
+    t0 = time.time()
+    out = linear_solve(Geometry(cost_matrix=C, epsilon=eps, scale_cost="max_cost"), mask=mask, _device_out=True)
+    n, m = C.shape
+    f, g = out.f.double(), out.g.double()
+    log = {"n_iters_outer": out.n_iters, "converged": out.converged,
+           "OT cost": float(f[torch.isfinite(f)].sum() / n + g[torch.isfinite(g)].sum() / m)}
+    log["time"], log["cost_time"] = time.time() - t0, cost_time
+    return _blocks_by_label(out.matrix, sl, tl, cv), log
 
 
 def get_coupling_egw_ott(data, eps: float = 5e-3, *, device=None):
@@ -572,10 +797,11 @@ def get_FOSCTTM(T, Xs_true, Xt_true, use_barycenter=True, use_agg="mean", *, dev
 # ---------------------------------------------------------------------------
 def sinkhorn_from_embeddings(x, y, a=None, b=None, reg=0.05, numItermax=1000, stopThr=1e-9,
                              cost="sqeuclidean", check_every=10, err_norm="l2", path="auto",
-                             return_plan=False, V=None, device=None):
+                             return_plan=False, V=None, device=None, fused_out=None):
     """Embeddings (host or device) -> cost on the GPU -> Sinkhorn -> potentials, OT cost and,
-    if ``V`` is given, the barycentric projection ``diag(1/P1) P V``; the plan itself is only
-    materialised when ``return_plan`` is set.  Returns a dict."""
+    if ``V`` is given, the barycentric projection ``diag(1/P1) P V`` (the fused embedding; single-pass
+    tcgen05 kernel); the plan itself is only materialised when ``return_plan`` is set.  ``fused_out``: optional
+    preallocated (e.g. pinned host) tensor that receives the fused embedding.  Returns a dict."""
     cv = _Conv(x, device)
     xd, yd = cv.to_dev(x), cv.to_dev(y)
     n, m = xd.shape[0], yd.shape[0]
@@ -589,7 +815,13 @@ def sinkhorn_from_embeddings(x, y, a=None, b=None, reg=0.05, numItermax=1000, st
     out = {"f": cv.back(f), "g": cv.back(g), "n_iter": info["n_iter"], "converged": info["converged"],
            "err": info["err"], "ot_cost": float(ops.ot_cost(Cm, f, g, float(reg)).item())}
     if V is not None:
-        out["fused"] = cv.back(ops.apply_plan(Cm, f, g, float(reg), cv.to_dev(V), normalise=True))
+        fused = ops.apply_plan(Cm, f, g, float(reg), cv.to_dev(V), normalise=True)
+        if fused_out is not None:
+            fused_out.copy_(fused, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            out["fused"] = fused_out
+        else:
+            out["fused"] = cv.back(fused)
     if return_plan:
         out["plan"] = cv.back(ops.plan(Cm, f, g, float(reg)))
     return out

@@ -1,10 +1,11 @@
 """Online (cost-free) Sinkhorn: C = |x|^2 + |y|^2 - 2 x.y is never materialised in HBM.
 
 The embeddings are split into bf16 parts once; every iteration rebuilds C one row panel at a time on the
-tensor cores (``b200ot_cost_gemm``) into a panel buffer small enough to stay in the 126 MB L2, and the same
-single-sweep kernel that streams a materialised C consumes the panel from L2
-(``b200ot_sinkhorn_panel_sweep``), adding the panel's column sums into one vector; ``finalize`` then runs once
-per iteration exactly as in the streaming solver, so stopping rule, error history and results are the same.
+tensor cores (``b200ot_cost_gemm``) into a panel buffer (default 2 GiB: a few thousand rows -- the whole matrix is
+never materialised; ``panel_bytes=48 << 20`` keeps the panel inside the 126 MB L2 instead), and the same
+single-sweep kernel that streams a materialised C consumes the panel (``b200ot_sinkhorn_panel_sweep``), adding the
+panel's column sums into one vector; ``finalize`` then runs once per iteration exactly as in the streaming solver,
+so stopping rule, error history and results are the same.
 
 When to use it: an iteration costs 2*n*m*d*terms tensor flops instead of 4*n*m bytes
 of HBM traffic.  At d = 512 and fp32-grade terms = 6 that is ~21 ms against ~3 ms per iteration at
@@ -26,7 +27,7 @@ class OnlineSinkhorn:
     def __init__(self, x: torch.Tensor, y: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float,
                  max_iter: int = 1000, tol: float = 1e-9, check_every: int = 10, check_phase: int = 1,
                  err_norm: str = "l2", stop_inclusive: bool = False, cost: str = "sqeuclidean", terms: int = 6,
-                 panel_bytes: int = 48 << 20, f0: Optional[torch.Tensor] = None, g0: Optional[torch.Tensor] = None):
+                 panel_bytes: int = 2 << 30, f0: Optional[torch.Tensor] = None, g0: Optional[torch.Tensor] = None):
         self.lib = _lib.load()
         x, self.ldx = ops._matrix(x, "x")
         y, self.ldy = ops._matrix(y, "y")
@@ -44,7 +45,11 @@ class OnlineSinkhorn:
         self.eps, self.kind, self.terms = float(eps), _lib.COSTS[cost], int(terms)
         self.prm = ops.make_params(eps, max_iter, tol, check_every, check_phase, err_norm, stop_inclusive, "auto")
         self.max_iter, self.ce, self.cp = int(max_iter), max(1, int(check_every)), int(check_phase)
-        # panel height: a multiple of the 128-row GEMM tile, small enough for the panel to live in L2
+        # panel height: a multiple of the 128-row GEMM tile.  Measured at n = m = 65536 (bench.py extra.online_c4):
+        # L2-sized panels (48 MB = 128 rows) make every iteration 512 GEMM launches of 1.7 waves plus 512 sweeps of
+        # 4 rows per cluster -- 49 ms per iteration, 39 % of the bf16 peak; panels of a few thousand rows (2 GiB of
+        # HBM scratch, ~1 % of the matrix that is never materialised) give the GEMM full waves and the sweep the
+        # same shape as an 8-GPU shard
         rows = max(128, (int(panel_bytes) // (4 * self.m)) // 128 * 128)
         self.panel_rows = min(rows, (self.n + 127) // 128 * 128)
         self.panel = ops.empty_matrix(self.panel_rows, self.m, dev)

@@ -19,6 +19,37 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _cuda_tensors(obj):
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            yield obj
+    elif isinstance(obj, (list, tuple)):
+        for o in obj:
+            yield from _cuda_tensors(o)
+
+
+def on_device(fn):
+    """Run an operator on the device its tensors live on: every CUDA operand must share ONE device, and the call
+    (stream lookup, kernel launches, per-device function attributes inside the library) happens with that device
+    current -- tensors on cuda:1 while cuda:0 is current would otherwise be launched on the wrong device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for t in _cuda_tensors(list(args) + list(kwargs.values())):
+            if dev is None:
+                dev = t.device
+            elif t.device != dev:
+                raise B200OTError(f"{fn.__name__}: operands live on different devices ({dev} and {t.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -71,6 +102,7 @@ def aligned_copy(Cm: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # cost construction
 # ---------------------------------------------------------------------------
+@on_device
 def cost_matrix(x: torch.Tensor, y: torch.Tensor, kind: str = "sqeuclidean",
                 out: Optional[torch.Tensor] = None, impl: str = "auto", terms: int = 6) -> torch.Tensor:
     """C_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  or  1 - cos(x_i, y_j).
@@ -104,6 +136,7 @@ def cost_matrix(x: torch.Tensor, y: torch.Tensor, kind: str = "sqeuclidean",
     return out
 
 
+@on_device
 def fot_cost(A: torch.Tensor, B: torch.Tensor, Ts: torch.Tensor, w1: torch.Tensor,
              w2: torch.Tensor) -> torch.Tensor:
     """M = (A.^2)^T w1 (+) (B.^2)^T w2 - 2 A^T Ts B (b200ot_fot_cost)."""
@@ -124,6 +157,7 @@ def fot_cost(A: torch.Tensor, B: torch.Tensor, Ts: torch.Tensor, w1: torch.Tenso
     return M
 
 
+@on_device
 def matrix_max(Cm: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     Cm, ldc = _matrix(Cm, "C")
@@ -133,6 +167,7 @@ def matrix_max(Cm: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_device
 def scale_by_inv_(Cm: torch.Tensor, denom: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     if Cm.stride(1) != 1:
@@ -180,6 +215,7 @@ def make_params(eps, max_iter, tol, check_every=10, check_phase=1, err_norm="l2"
                   _lib.NORMS[err_norm], int(bool(stop_inclusive)), _lib.PATHS[path], int(floor_patience))
 
 
+@on_device
 def sinkhorn_potentials(Cm: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps: float,
                         max_iter: int = 1000, tol: float = 1e-9, check_every: int = 10,
                         check_phase: int = 1, err_norm: str = "l2", stop_inclusive: bool = False,
@@ -215,6 +251,21 @@ def sinkhorn_potentials(Cm: torch.Tensor, a: torch.Tensor, b: torch.Tensor, eps:
     return f, g, info
 
 
+def _on_self_device(method):
+    """Method form of on_device for objects that own their matrix (``self.C``)."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        dev = self.C.device
+        if dev.index == torch.cuda.current_device():
+            return method(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return method(self, *args, **kwargs)
+
+    return wrapper
+
+
 class SinkhornStepper:
     """Asynchronous life cycle (init / enqueue / finish) for callers that drive the
     iteration themselves: bench loops, CUDA-graph capture, the row-sharded solver."""
@@ -235,17 +286,20 @@ class SinkhornStepper:
         self.g0 = None if g0 is None else _vector(g0, "g0", self.m)
         self.reset()
 
+    @_on_self_device
     def reset(self):
         check(self.lib.b200ot_sinkhorn_init(_ptr(self.C), self.ldc, self.n, self.m, _ptr(self.a),
                                             _ptr(self.b), _ptr(self.f0), _ptr(self.g0),
                                             C.byref(self.prm), _ws_ptr(self.ws), self.ws.numel() - 256,
                                             _stream()), "b200ot_sinkhorn_init")
 
+    @_on_self_device
     def enqueue(self, iters: int):
         check(self.lib.b200ot_sinkhorn_enqueue(_ptr(self.C), self.ldc, self.n, self.m, int(iters),
                                                self.path, _ws_ptr(self.ws), _stream()),
               "b200ot_sinkhorn_enqueue")
 
+    @_on_self_device
     def build_graph(self, iters_per_replay: int = 10):
         """Capture `iters_per_replay` iterations into a CUDA graph (launch-bound small problems: two kernel
         launches per iteration become one graph replay per `iters_per_replay`).  Kernels no-op once the
@@ -265,6 +319,7 @@ class SinkhornStepper:
         self.reset()
         return self._graph
 
+    @_on_self_device
     def run(self, iters: int):
         """enqueue() through the captured graph where whole replays fit, eagerly for the remainder."""
         g = getattr(self, "_graph", None)
@@ -275,12 +330,14 @@ class SinkhornStepper:
         if iters > 0:
             self.enqueue(iters)
 
+    @_on_self_device
     def flags(self) -> dict:
         out = torch.empty(8, dtype=torch.int32, device=self.C.device)
         check(self.lib.b200ot_sinkhorn_peek(_ws_ptr(self.ws), _ptr(out), _stream()), "b200ot_sinkhorn_peek")
         v = out.cpu().tolist()
         return {"it": v[0], "done": v[1], "converged": v[2], "cur": v[3], "bad": v[4], "n_err": v[5]}
 
+    @_on_self_device
     def finish(self, err_hist_cap: int = 512):
         f = torch.empty(self.n, dtype=torch.float32, device=self.C.device)
         g = torch.empty(self.m, dtype=torch.float32, device=self.C.device)
@@ -295,6 +352,7 @@ class SinkhornStepper:
         return f, g, info
 
 
+@on_device
 def sinkhorn_batched(a: torch.Tensor, b: torch.Tensor, eps: float, *, C3: Optional[torch.Tensor] = None,
                      X: Optional[torch.Tensor] = None, Y: Optional[torch.Tensor] = None,
                      max_iter: int = 1000, tol: float = 1e-9, check_every: int = 10, check_phase: int = 1,
@@ -335,6 +393,7 @@ def sinkhorn_batched(a: torch.Tensor, b: torch.Tensor, eps: float, *, C3: Option
 # ---------------------------------------------------------------------------
 # epilogues
 # ---------------------------------------------------------------------------
+@on_device
 def plan(Cm, f, g, eps, out=None):
     lib = _lib.load()
     Cm, ldc = _matrix(Cm, "C")
@@ -349,18 +408,62 @@ def plan(Cm, f, g, eps, out=None):
     return out
 
 
+@on_device
 def ot_cost(Cm, f, g, eps):
     lib = _lib.load()
     Cm, ldc = _matrix(Cm, "C")
     n, m = Cm.shape
-    out = torch.empty(1, dtype=torch.float64, device=Cm.device)
+    out = torch.empty(_lib.OT_COST_DOUBLES, dtype=torch.float64, device=Cm.device)
     check(lib.b200ot_ot_cost(_ptr(Cm), ldc, n, m, _ptr(_vector(f, "f", n)), _ptr(_vector(g, "g", m)),
                              float(eps), _ptr(out), _stream()), "b200ot_ot_cost")
+    return out[:1]
+
+
+@on_device
+def plan_guard_rownorm(Cm=None, f=None, g=None, eps=None, T=None, out=None):
+    """The per-step plan guard of the reference (MRI_PET_OT_nojax.py:704-715) in one kernel: NaN -> 1e-8, rows
+    divided by their sums (0 -> 1e-8).  Either ``(Cm, f, g, eps)`` (plan evaluated on the fly) or a dense ``T``."""
+    lib = _lib.load()
+    if T is not None:
+        T, ldt = _matrix(T, "T")
+        n, m = T.shape
+        if out is None:
+            out = torch.empty((n, m), dtype=torch.float32, device=T.device)
+        out, ldp = _matrix(out, "out")
+        check(lib.b200ot_plan_guard_rownorm(None, 0, n, m, None, None, 1.0, _ptr(T), ldt, _ptr(out), ldp, _stream()),
+              "b200ot_plan_guard_rownorm")
+        return out
+    Cm, ldc = _matrix(Cm, "C")
+    n, m = Cm.shape
+    if out is None:
+        out = torch.empty((n, m), dtype=torch.float32, device=Cm.device)
+    out, ldp = _matrix(out, "out")
+    check(lib.b200ot_plan_guard_rownorm(_ptr(Cm), ldc, n, m, _ptr(_vector(f, "f", n)), _ptr(_vector(g, "g", m)),
+                                        float(eps), None, 0, _ptr(out), ldp, _stream()), "b200ot_plan_guard_rownorm")
     return out
 
 
-def apply_plan(Cm, f, g, eps, V, normalise=False, transpose=False):
-    """Z = P V (or P^T V with transpose=True), optionally row-normalised, without forming P."""
+_TC_MAX_DV = 512
+
+
+def _tc_ws(nbytes: int, device) -> tuple:
+    """1024-byte aligned scratch of `nbytes` for the tensor-core epilogues (torch owns the memory)."""
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    return buf, C.c_void_p((buf.data_ptr() + 1023) // 1024 * 1024)
+
+
+def _apply_wants_tc(n: int, m: int, dv: int) -> bool:
+    # the tcgen05 kernel pads dv to 16 and works on 128-row blocks: tiny problems stay on the SIMT kernel
+    return n * m >= (1 << 18) and dv >= 16
+
+
+@on_device
+def apply_plan(Cm, f, g, eps, V, normalise=False, transpose=False, impl="auto", return_rowsum=False):
+    """Z = P V (or P^T V with transpose=True), optionally row-normalised, without forming P.
+
+    impl="tc": single-pass tcgen05 kernel (b200ot_apply_plan_tc; dv is processed in slabs of 512 columns);
+    impl="simt": the generic fp32 kernel (any shape / alignment); "auto" picks by size.  With
+    ``return_rowsum`` the row sums of P (P^T when transposed) come back as well."""
     lib = _lib.load()
     Cm, ldc = _matrix(Cm, "C")
     n, m = Cm.shape
@@ -369,13 +472,67 @@ def apply_plan(Cm, f, g, eps, V, normalise=False, transpose=False):
     if V.shape[0] != rows_in:
         raise B200OTError(f"V must have {rows_in} rows")
     dv = V.shape[1]
+    fv, gv = _vector(f, "f", n), _vector(g, "g", m)
     Z = torch.empty((rows_out, dv), dtype=torch.float32, device=Cm.device)
+    if impl == "auto":
+        impl = "tc" if _apply_wants_tc(n, m, dv) else "simt"
+    if impl == "tc":
+        rs = torch.empty(rows_out, dtype=torch.float32, device=Cm.device) if return_rowsum else None
+        for c0 in range(0, dv, _TC_MAX_DV):
+            dvc = min(_TC_MAX_DV, dv - c0)
+            need = lib.b200ot_apply_plan_tc_workspace_bytes(n, m, dvc, int(bool(transpose)))
+            buf, wsp = _tc_ws(need, Cm.device)
+            Vc, Zc = V[:, c0:c0 + dvc], Z[:, c0:c0 + dvc]
+            check(lib.b200ot_apply_plan_tc(_ptr(Cm), ldc, n, m, _ptr(fv), _ptr(gv), float(eps), _ptr(Vc), ldv, dvc,
+                                           int(bool(transpose)), int(bool(normalise)), _ptr(Zc), Z.stride(0),
+                                           _ptr(rs) if c0 == 0 else None, wsp, need, _stream()),
+                  "b200ot_apply_plan_tc")
+        return (Z, rs) if return_rowsum else Z
+    if impl != "simt":
+        raise B200OTError(f"unknown apply_plan impl {impl!r}")
     fn = lib.b200ot_apply_plan_t if transpose else lib.b200ot_apply_plan
-    check(fn(_ptr(Cm), ldc, n, m, _ptr(_vector(f, "f", n)), _ptr(_vector(g, "g", m)), float(eps), _ptr(V),
+    check(fn(_ptr(Cm), ldc, n, m, _ptr(fv), _ptr(gv), float(eps), _ptr(V),
              ldv, dv, int(bool(normalise)), _ptr(Z), Z.stride(0), _stream()), "b200ot_apply_plan")
+    if return_rowsum:
+        ones = torch.ones((rows_in, 1), dtype=torch.float32, device=Cm.device)
+        rs = torch.empty((rows_out, 1), dtype=torch.float32, device=Cm.device)
+        check(fn(_ptr(Cm), ldc, n, m, _ptr(fv), _ptr(gv), float(eps), _ptr(ones), 1, 1, 0, _ptr(rs), 1, _stream()),
+              "b200ot_apply_plan")
+        return Z, rs.reshape(-1)
     return Z
 
 
+@on_device
+def envelope_bwd(Cm, f, g, eps, x, y, scale: float = 2.0, impl="auto"):
+    """dX = scale (diag(P1) x - P y), dY = scale (diag(P^T 1) y - P^T x): the gradient of <P, C(x, y)> for the
+    squared-Euclidean cost with the plan held fixed.  impl="tc": both halves in ONE launch of the tcgen05 kernel
+    (b200ot_envelope_bwd); "simt": two plan-free products on the generic kernel."""
+    lib = _lib.load()
+    Cm, ldc = _matrix(Cm, "C")
+    n, m = Cm.shape
+    x, ldx = _matrix(x, "x")
+    y, ldy = _matrix(y, "y")
+    d = x.shape[1]
+    if x.shape[0] != n or y.shape[0] != m or y.shape[1] != d:
+        raise B200OTError("envelope_bwd: x must be n x d and y m x d")
+    fv, gv = _vector(f, "f", n), _vector(g, "g", m)
+    if impl == "auto":
+        impl = "tc" if (_apply_wants_tc(n, m, d) and d <= _TC_MAX_DV) else "simt"
+    if impl == "tc":
+        dx = torch.empty((n, d), dtype=torch.float32, device=Cm.device)
+        dy = torch.empty((m, d), dtype=torch.float32, device=Cm.device)
+        need = lib.b200ot_envelope_bwd_workspace_bytes(n, m, d)
+        buf, wsp = _tc_ws(need, Cm.device)
+        check(lib.b200ot_envelope_bwd(_ptr(Cm), ldc, n, m, _ptr(fv), _ptr(gv), float(eps), _ptr(x), ldx, _ptr(y), ldy,
+                                      d, float(scale), _ptr(dx), d, _ptr(dy), d, None, None, wsp, need, _stream()),
+              "b200ot_envelope_bwd")
+        return dx, dy
+    Py, r = apply_plan(Cm, fv, gv, eps, y, impl="simt", return_rowsum=True)
+    Ptx, c = apply_plan(Cm, fv, gv, eps, x, transpose=True, impl="simt", return_rowsum=True)
+    return scale * (r[:, None] * x - Py), scale * (c[:, None] * y - Ptx)
+
+
+@on_device
 def cosine_loss(A, B):
     lib = _lib.load()
     A, lda = _matrix(A, "A")
@@ -388,6 +545,7 @@ def cosine_loss(A, B):
     return out
 
 
+@on_device
 def foscttm(pred: torch.Tensor, true: torch.Tensor) -> torch.Tensor:
     """Fraction of samples closer than the true match, per sample (b200ot_cost + b200ot_foscttm)."""
     lib = _lib.load()
@@ -399,6 +557,7 @@ def foscttm(pred: torch.Tensor, true: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@on_device
 def egw_batched(Xs, Ys, eps: float = 5e-3, gw_max_iter: int = 2000, sk_max_iter: int = 2000, gw_threshold: float = 1e-3,
                 gw_min_iter: int = 5, sk_threshold: float = 1e-3, sk_check_every: int = 10):
     """Entropic Gromov-Wasserstein couplings for a list of independent small problems (one per label), one CTA

@@ -100,7 +100,7 @@ class PeerExchange:
 
     def next_epoch(self) -> int:
         """A new solve on the same buffers: the same sequence of values on every rank."""
-        self.epoch = (self.epoch + 1) & 0xFFF
+        self.epoch = (self.epoch + 1) & 0x7FF
         return self.epoch
 
     def close(self):
@@ -130,35 +130,41 @@ class CudaShardKernels:
                               dtype=torch.uint8, device=dev)
         self.s = torch.zeros(self.m, dtype=torch.float32, device=dev)
 
+    @ops._on_self_device
     def setup(self):
         check(self.lib.b200ot_sinkhorn_setup(self.n, self.m, ops._ptr(self.a), ops._ptr(self.b),
                                              ops._ptr(self.f0), ops._ptr(self.g0), C.byref(self.prm),
                                              ops._ws_ptr(self.ws), self.ws.numel() - 256, ops._stream()),
               "b200ot_sinkhorn_setup")
 
+    @ops._on_self_device
     def prologue(self) -> torch.Tensor:
         check(self.lib.b200ot_sinkhorn_shard_prologue(ops._ptr(self.C), self.ldc, self.n, self.m,
                                                       ops._ws_ptr(self.ws), ops._ptr(self.s), ops._stream()),
               "b200ot_sinkhorn_shard_prologue")
         return self.s
 
+    @ops._on_self_device
     def sweep(self) -> torch.Tensor:
         check(self.lib.b200ot_sinkhorn_shard_sweep(ops._ptr(self.C), self.ldc, self.n, self.m, self.path,
                                                    ops._ws_ptr(self.ws), ops._ptr(self.s), ops._stream()),
               "b200ot_sinkhorn_shard_sweep")
         return self.s
 
+    @ops._on_self_device
     def finalize(self, s_total: torch.Tensor, is_prologue: bool):
         check(self.lib.b200ot_sinkhorn_shard_finalize(self.n, self.m, ops._ws_ptr(self.ws), ops._ptr(s_total),
                                                       int(is_prologue), ops._stream()),
               "b200ot_sinkhorn_shard_finalize")
 
     # -- C-driven loop: everything, including the all-reduce, is queued by one call on the compute stream
+    @ops._on_self_device
     def start_c(self, comm: Optional["NcclComm"]):
         check(self.lib.b200ot_sinkhorn_shard_start(ops._ptr(self.C), self.ldc, self.n, self.m, ops._ws_ptr(self.ws),
                                                    ops._ptr(self.s), comm.handle if comm else None, ops._stream()),
               "b200ot_sinkhorn_shard_start")
 
+    @ops._on_self_device
     def run_c(self, iters: int, comm: Optional["NcclComm"]):
         check(self.lib.b200ot_sinkhorn_shard_run(ops._ptr(self.C), self.ldc, self.n, self.m, int(iters), self.path,
                                                  ops._ws_ptr(self.ws), ops._ptr(self.s),
@@ -166,23 +172,40 @@ class CudaShardKernels:
               "b200ot_sinkhorn_shard_run")
 
     # -- peer-memory loop: no collective call, the column sums travel as tagged words over NVLink
+    @ops._on_self_device
     def push(self, peer: "PeerExchange", is_prologue: bool):
         check(self.lib.b200ot_sinkhorn_shard_push(ops._ptr(self.C), self.ldc, self.n, self.m, self.path,
                                                   ops._ws_ptr(self.ws), peer.ptrs, peer.world, peer.rank, peer.epoch,
                                                   int(is_prologue), ops._stream()), "b200ot_sinkhorn_shard_push")
 
+    @ops._on_self_device
     def finalize_peer(self, peer: "PeerExchange", is_prologue: bool):
         check(self.lib.b200ot_sinkhorn_shard_finalize_peer(self.n, self.m, ops._ws_ptr(self.ws),
                                                            peer.ptrs[peer.rank], peer.world, peer.epoch,
                                                            int(is_prologue), ops._stream()),
               "b200ot_sinkhorn_shard_finalize_peer")
 
+    @ops._on_self_device
     def run_peer(self, iters: int, peer: "PeerExchange"):
         check(self.lib.b200ot_sinkhorn_shard_run_peer(ops._ptr(self.C), self.ldc, self.n, self.m, int(iters),
                                                       self.path, ops._ws_ptr(self.ws), peer.ptrs, peer.world,
                                                       peer.rank, peer.epoch, ops._stream()),
               "b200ot_sinkhorn_shard_run_peer")
 
+    @ops._on_self_device
+    def snapshot(self):
+        check(self.lib.b200ot_sinkhorn_snapshot(self.n, self.m, ops._ws_ptr(self.ws), ops._stream()),
+              "b200ot_sinkhorn_snapshot")
+
+    @ops._on_self_device
+    def rewind(self):
+        check(self.lib.b200ot_sinkhorn_rewind(self.n, self.m, ops._ws_ptr(self.ws), ops._stream()),
+              "b200ot_sinkhorn_rewind")
+
+    def use_robust_path(self):
+        self.path = _lib.PATH_ROBUST
+
+    @ops._on_self_device
     def flags(self) -> dict:
         out = torch.empty(8, dtype=torch.int32, device=self.C.device)
         check(self.lib.b200ot_sinkhorn_peek(ops._ws_ptr(self.ws), ops._ptr(out), ops._stream()),
@@ -190,6 +213,7 @@ class CudaShardKernels:
         v = out.cpu().tolist()
         return {"it": v[0], "done": v[1], "converged": v[2], "bad": v[4], "n_err": v[5]}
 
+    @ops._on_self_device
     def finish(self):
         f = torch.empty(self.n, dtype=torch.float32, device=self.C.device)
         g = torch.empty(self.m, dtype=torch.float32, device=self.C.device)
@@ -323,16 +347,36 @@ class ShardedSinkhorn:
         self.iterations_queued += iters
 
     def solve(self, max_iter: int, check_every: int = 10, check_phase: int = 1):
-        """Blocking solve: chunks that end on check iterations, flags read after each chunk."""
+        """Blocking solve: chunks that end on check iterations, flags read after each chunk.  A chunk whose fast
+        path lost a row or column sum (``bad``: raised on one rank, carried to every rank as NaN column sums, so
+        all ranks stop in the same iteration) is rewound to its snapshot and replayed on the robust two-sweep
+        kernels -- the same recovery the single-GPU driver ``b200ot_sinkhorn_solve`` performs."""
         self.start()
         done = 0
         ce = max(1, int(check_every))
+        robust = False
+        can_recover = all(hasattr(self.k, nm) for nm in ("snapshot", "rewind", "use_robust_path"))
         while done < max_iter:
             ln = ((check_phase - done - 1) % ce) + 1
             ln = min(ln, max_iter - done)
+            if can_recover:
+                self.k.snapshot()
             self.run(ln)
-            done += ln
             fl = self.k.flags()
+            if fl.get("bad") and can_recover and not robust:
+                robust = True
+                if self.peer is not None:
+                    # the aborted exchanges left words with this epoch's tags in the slabs: new epoch, and no rank
+                    # may still be polling when the replay starts to push
+                    if self.world > 1 and dist.is_initialized() and torch.cuda.is_available():
+                        torch.cuda.current_stream().synchronize()
+                        dist.barrier(group=self.group)
+                    self.peer.next_epoch()
+                self.k.rewind()
+                self.k.use_robust_path()
+                done = self.k.flags()["it"]
+                continue
+            done += ln
             if fl["done"]:
                 break
         return self.k.finish()

@@ -76,16 +76,9 @@ def _(C, f, g, eps, V, normalise, transpose):
 @torch.library.custom_op("b200ot::sinkhorn_bwd_envelope", mutates_args=())
 def sinkhorn_bwd_envelope(C: Tensor, f: Tensor, g: Tensor, eps: float, x: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
     """Envelope gradients of <P, C(x, y)> for the squared-Euclidean cost at fixed P:
-    dx = 2 (diag(P1) x - P y), dy = 2 (diag(P^T 1) y - P^T x).  The row / column sums come out of the
-    same plan-free kernel by appending a column of ones to the right-hand side."""
-    n, m = C.shape
-    ones_m = torch.ones((m, 1), dtype=torch.float32, device=C.device)
-    ones_n = torch.ones((n, 1), dtype=torch.float32, device=C.device)
-    Py = ops.apply_plan(C, f, g, eps, torch.cat([y, ones_m], dim=1))
-    Ptx = ops.apply_plan(C, f, g, eps, torch.cat([x, ones_n], dim=1), transpose=True)
-    dx = 2.0 * (Py[:, -1:] * x - Py[:, :-1])
-    dy = 2.0 * (Ptx[:, -1:] * y - Ptx[:, :-1])
-    return dx, dy
+    dx = 2 (diag(P1) x - P y), dy = 2 (diag(P^T 1) y - P^T x): one launch of the tcgen05 plan-application
+    kernel computes both products, the row / column sums of P and the combination (b200ot_envelope_bwd)."""
+    return ops.envelope_bwd(C, f, g, eps, x.contiguous(), y.contiguous(), scale=2.0)
 
 
 @sinkhorn_bwd_envelope.register_fake
@@ -139,21 +132,20 @@ class ApplyPlan(torch.autograd.Function):
     @staticmethod
     def forward(ctx, C, f, g, eps, V, normalise):
         Vd = V.detach().float().contiguous()
-        Z = ops.apply_plan(C, f, g, eps, Vd, normalise=normalise)
-        ctx.save_for_backward(C, f, g)
+        Z, rs = ops.apply_plan(C, f, g, eps, Vd, normalise=normalise, return_rowsum=True)
+        ctx.save_for_backward(C, f, g, rs)
         ctx.eps, ctx.normalise = eps, normalise
         return Z.to(V.dtype)
 
     @staticmethod
     def backward(ctx, dZ):
-        C, f, g = ctx.saved_tensors
+        C, f, g, rs = ctx.saved_tensors
+        dtype = dZ.dtype
         dZ = dZ.float().contiguous()
         if ctx.normalise:
-            ones = torch.ones((C.shape[1], 1), dtype=torch.float32, device=C.device)
-            rs = ops.apply_plan(C, f, g, ctx.eps, ones)
-            dZ = dZ / torch.where(rs == 0, torch.full_like(rs, 1e-30), rs)
+            dZ = dZ / torch.where(rs == 0, torch.full_like(rs, 1e-30), rs)[:, None]
         dV = ops.apply_plan(C, f, g, ctx.eps, dZ, transpose=True)
-        return None, None, None, None, dV, None
+        return None, None, None, None, dV.to(dtype), None
 
 
 def apply_plan(C, f, g, eps, V, normalise=False):

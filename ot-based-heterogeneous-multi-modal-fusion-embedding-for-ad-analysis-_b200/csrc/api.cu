@@ -13,13 +13,20 @@ void set_last_cuda_error(cudaError_t e, const char* where) {
            cudaGetErrorString(e), cudaGetErrorName(e));
 }
 
+int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  return dev < 0 ? 0 : dev % kMaxDeviceSlots;
+}
+
 int sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
+  static int cached[kMaxDeviceSlots] = {};
+  const int slot = device_slot();
+  if (cached[slot]) return cached[slot];
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  cached[slot] = n;
   return n;
 }
 

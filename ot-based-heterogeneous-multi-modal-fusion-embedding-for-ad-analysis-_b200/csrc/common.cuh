@@ -33,7 +33,22 @@ void set_last_cuda_error(cudaError_t e, const char* where);
     }                                                   \
   } while (0)
 
-int sm_count();
+int sm_count();      // SMs of the CURRENT device (cached per device)
+int device_slot();   // current device ordinal folded into [0, kMaxDeviceSlots)
+constexpr int kMaxDeviceSlots = 32;
+
+// Per-(call site, device) one-time work: function attributes (cudaFuncSetAttribute) belong to a device, so a
+// process that touches a second GPU must set them again there.  `static PerDeviceOnce once; if (once.first()) ...`
+struct PerDeviceOnce {
+  bool done[kMaxDeviceSlots] = {};
+  bool first() {
+    const int d = device_slot();
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+  void undo() { done[device_slot()] = false; }
+};
 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;

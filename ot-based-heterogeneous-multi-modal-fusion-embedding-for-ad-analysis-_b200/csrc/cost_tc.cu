@@ -24,6 +24,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace b200ot {
 
@@ -35,48 +36,6 @@ constexpr int TC_THREADS = 192;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KiB
 constexpr int TC_GROUP_N = 16;  // n-blocks per raster group (keeps a 12 MiB slab of B' hot in L2)
-
-// ---- tcgen05 wrappers -----------------------------------------------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = byte step between the two K chunks of
-// one MMA, SBO = byte step between 8-row groups (both in 16-byte units in the descriptor).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
-  return d;                // base offset 0, layout type 0 = SWIZZLE_NONE
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- pre-pass: fp32 rows -> two bf16 parts in tiled UMMA layout + row norms ---------------------
 // One warp per (padded) row.  x = p1 + p2 + p3 (bf16 parts, 8 + 8 + 8 significand bits).
@@ -377,10 +336,9 @@ int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, 
   B200OT_LAUNCH_OK();
   split_tiles_kernel<<<(w.m_pad * 32 + 255) / 256, 256, 0, s>>>(Y, ldy, m, d, TC_BN, w.kblocks, w.m_pad, cosine, nparts, Bp, yn);
   B200OT_LAUNCH_OK();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;  // function attributes are per device
+  if (attr_once.first()) {
     B200OT_CUDA_OK(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    attr_set = true;
   }
   CostTcArgs a;
   a.A = Ap;
@@ -436,10 +394,9 @@ int b200ot_cost_gemm(const void* partsA, const float* normsA, int row_tile0, int
   if (!partsA || !normsA || !partsB || !normsB || !C || n <= 0 || m <= 0 || d <= 0 || ldc < m || row_tile0 < 0)
     return B200OT_E_INVALID;
   if (terms != 1 && terms != 3 && terms != 6) return B200OT_E_INVALID;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;  // function attributes are per device
+  if (attr_once.first()) {
     B200OT_CUDA_OK(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-    attr_set = true;
   }
   const int nparts = terms == 1 ? 1 : terms == 3 ? 2 : 3;
   const int kblocks = (d + TC_BK - 1) / TC_BK;

@@ -269,10 +269,9 @@ int b200ot_egw_batched(const float* X, const float* Y, const int* xoff, const in
   p.info = info4;
   p.cost = cost;
   const size_t smem = ((size_t)5 * kEgwMax * kEgwLd + 6 * kEgwMax + ET / 32) * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;  // function attributes are per device
+  if (attr_once.first()) {
     B200OT_CUDA_OK(cudaFuncSetAttribute(egw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   egw_kernel<<<nprob, ET, smem, static_cast<cudaStream_t>(stream)>>>(p);
   B200OT_LAUNCH_OK();

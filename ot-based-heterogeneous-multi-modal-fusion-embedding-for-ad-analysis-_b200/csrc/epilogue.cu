@@ -25,6 +25,10 @@ __global__ void __launch_bounds__(256) plan_kernel(const float* __restrict__ C, 
   }
 }
 
+// <P, C> without materialising P.  Every block leaves ONE double (its rows in fixed order, fixed reduction tree)
+// in out[1 + block]; the last block to finish (ticket in out[1 + kOtCostBlocks]) adds the partials in block order,
+// so the value is bit-reproducible run to run -- no floating-point atomics.
+constexpr int kOtCostBlocks = 148 * 8;
 __global__ void __launch_bounds__(256) ot_cost_kernel(const float* __restrict__ C, long long ldc, int n,
                                                       int m, const float* __restrict__ f,
                                                       const float* __restrict__ g, float k,
@@ -41,12 +45,63 @@ __global__ void __launch_bounds__(256) ot_cost_kernel(const float* __restrict__ 
   }
   acc = warp_sum(acc);
   __shared__ double sh[8];
+  __shared__ int is_last;
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += sh[w];
-    atomicAdd(out, t);
+    out[1 + blockIdx.x] = t;
+    __threadfence();
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(out + 1 + kOtCostBlocks);
+    is_last = (atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double part = 0.0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) part += ((volatile double*)out)[1 + i];
+  part = warp_sum(part);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    out[0] = t;
+  }
+}
+
+// The per-step plan guard of the reference (MRI_PET_OT_nojax.py:704-715): NaN -> 1e-8, then every row divided by
+// its sum with zero sums replaced by 1e-8.  The plan comes either from potentials (T == nullptr: entries are
+// re-evaluated, never stored unnormalised) or from a materialised matrix T.  One block per row, two passes.
+__global__ void __launch_bounds__(256) plan_guard_rownorm_kernel(const float* __restrict__ C, long long ldc, int n,
+                                                                 int m, const float* __restrict__ f,
+                                                                 const float* __restrict__ g, float k,
+                                                                 const float* __restrict__ T, long long ldt,
+                                                                 float* __restrict__ P, long long ldp) {
+  __shared__ float sh[8];
+  __shared__ float s_inv;
+  for (long long r = blockIdx.x; r < n; r += gridDim.x) {
+    const float fi = T ? 0.f : f[r] * k;
+    auto entry = [&](int j) {
+      float v = T ? T[r * ldt + j] : exp2f(fmaf(C[r * ldc + j], -k, fmaf(g[j], k, fi)));
+      return (v != v) ? 1e-8f : v;
+    };
+    float part = 0.f;
+    for (int j = threadIdx.x; j < m; j += 256) part += entry(j);
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += sh[w];
+      s_inv = 1.f / (t == 0.f ? 1e-8f : t);
+    }
+    __syncthreads();
+    const float inv = s_inv;
+    for (int j = threadIdx.x; j < m; j += 256) P[r * ldp + j] = entry(j) * inv;
+    __syncthreads();
   }
 }
 
@@ -212,9 +267,24 @@ int b200ot_ot_cost(const float* C, int ldc, int n, int m, const float* f, const 
                    float eps, double* out, void* stream) {
   if (!C || !f || !g || !out || n <= 0 || m <= 0 || ldc < m || !(eps > 0.f)) return B200OT_E_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  B200OT_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), s));
-  const int grid = n < 148 * 8 ? n : 148 * 8;
+  B200OT_CUDA_OK(cudaMemsetAsync(out, 0, B200OT_OT_COST_DOUBLES * sizeof(double), s));
+  const int grid = n < kOtCostBlocks ? n : kOtCostBlocks;
   ot_cost_kernel<<<grid, 256, 0, s>>>(C, ldc, n, m, f, g, kLog2e / eps, out);
+  B200OT_LAUNCH_OK();
+  return 0;
+}
+
+int b200ot_plan_guard_rownorm(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                              const float* T, int ldt, float* P, int ldp, void* stream) {
+  if (!P || n <= 0 || m <= 0 || ldp < m) return B200OT_E_INVALID;
+  if (T) {
+    if (ldt < m) return B200OT_E_INVALID;
+  } else if (!C || !f || !g || ldc < m || !(eps > 0.f)) {
+    return B200OT_E_INVALID;
+  }
+  const int grid = n < 148 * 8 ? n : 148 * 8;
+  plan_guard_rownorm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      C, ldc, n, m, f, g, T ? 0.f : kLog2e / eps, T, ldt, P, ldp);
   B200OT_LAUNCH_OK();
   return 0;
 }

@@ -495,12 +495,14 @@ struct ResCfg {
 
 template <int T, int NCH, int R>
 static cudaError_t resident_launch(const ResidentArgs* a, int G, size_t smem, cudaStream_t s, int* occ_out) {
-  static bool attr_set = false;  // one flag per instantiation
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;  // one per instantiation and device
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(resident_kernel<T, NCH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(T > 256 ? kResSmemMaxWide : kResSmemMax));
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (e != cudaSuccess) {
+      attr_once.undo();
+      return e;
+    }
   }
   if (!a) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, resident_kernel<T, NCH, R>, T, smem);
   cudaLaunchConfig_t cfg;

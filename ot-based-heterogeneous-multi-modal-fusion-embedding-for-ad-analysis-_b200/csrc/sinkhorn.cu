@@ -113,20 +113,47 @@ __global__ void __launch_bounds__(256) init_kernel(State* st, float eps, int n, 
 // the loop, see reduce_push_kernel): a 64-bit access is single-copy atomic, so the tag of exchange x carries the
 // value of exchange x.  Exchange index x = 0 for the prologue, it + 1 for the iteration that follows `it` completed
 // ones; slabs are double-buffered by the parity of x.
-__device__ __forceinline__ unsigned peer_tag(unsigned epoch, int x) { return (epoch << 20) | ((unsigned)(x + 1) & 0xfffffu); }
-__device__ __forceinline__ float peer_poll(const unsigned long long* p, unsigned tag) {
+// Bit 31 of the tag marks a LOG-DOMAIN word: the value is log2 of the rank's column sum instead of the sum.  The
+// first g update and the robust two-sweep iterations use it, because their column sums (unbalanced potentials,
+// extreme eps) can lie far outside the fp32 range while their logarithms are ordinary numbers.
+constexpr unsigned kPeerLogBit = 0x80000000u;
+__device__ __forceinline__ unsigned peer_tag(unsigned epoch, int x) {
+  return ((epoch & 0x7ffu) << 20) | ((unsigned)(x + 1) & 0xfffffu);
+}
+// A peer that never pushes (a rank that died, a host stalled for seconds) must not hang or kill this rank:
+// after ~4 s the poll gives up and returns NaN, which poisons the error partial, so the state machine stops the
+// solve with bad = 1 and the host reads B200OT_E_NUMERIC instead of a dead CUDA context.
+__device__ __forceinline__ float peer_poll(const unsigned long long* p, unsigned tag, bool* is_log = nullptr) {
   unsigned long long v;
   long long t0 = 0;
   for (;;) {
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    if ((unsigned)(v >> 32) == tag) break;
+    if (((unsigned)(v >> 32) & ~kPeerLogBit) == tag) {
+      if (is_log) *is_log = ((unsigned)(v >> 32) & kPeerLogBit) != 0;
+      break;
+    }
     if (t0 == 0)
       t0 = clock64();
     else if (clock64() - t0 > 8000000000ll)
-      __trap();  // a peer that never pushes traps this rank instead of hanging the box
+      return __int_as_float(0x7fc00000);
     __nanosleep(40);
   }
   return __uint_as_float((unsigned)v);
+}
+
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+  unsigned long long* buf[kMaxPeers];
+};
+
+// One column of the finalize step: marginal-error term and the next g from the column sum s of the new plan.
+__device__ __forceinline__ double finalize_column(float s, float l2s, float bj, float log2bj, float gcur_j, int norm,
+                                                  float* gnext_j, int* bad) {
+  const double d = (double)s - (double)bj;
+  const float gn = bj > 0.f ? gcur_j + (log2bj - l2s) : -INFINITY;  // b_j = 0: no mass, v_j = 0
+  *gnext_j = gn;
+  if (bj > 0.f && !(fabsf(gn) < INFINITY)) *bad = 1;
+  return (norm == B200OT_NORM_L1) ? fabs(d) : d * d;
 }
 
 __global__ void __launch_bounds__(kFinalizeThreads)
@@ -161,8 +188,36 @@ __global__ void __launch_bounds__(kFinalizeThreads)
           const float pm = part_max[(size_t)p * stride + j];
           if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm - M);
         }
-      } else if (tagged) {
-        for (int p = grp; p < np; p += groups) acc += peer_poll(tagged + (size_t)p * stride + j, tag);
+      } else if (tagged) {  // groups == 1: one thread gathers the world's words of its column, rank order
+        float v[kMaxPeers];
+        bool any_log = false, any_nan = false;
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p) {
+          v[p] = -INFINITY;
+          if (p < np) {
+            bool lg = false;
+            v[p] = peer_poll(tagged + (size_t)p * stride + j, tag, &lg);
+            any_log |= lg;
+            any_nan |= (v[p] != v[p]);  // a rank that lost a sum, or never answered
+          }
+        }
+        if (any_nan) {
+          acc = M = __int_as_float(0x7fc00000);
+        } else if (any_log) {  // values are log2 of the ranks' sums: log-sum-exp over the ranks, rank order
+          float Mx = -INFINITY;
+#pragma unroll
+          for (int p = 0; p < kMaxPeers; ++p) Mx = fmaxf(Mx, v[p]);
+#pragma unroll
+          for (int p = 0; p < kMaxPeers; ++p)
+            if (v[p] > -INFINITY) acc += exp2f(v[p] - Mx);
+          M = Mx > -INFINITY ? Mx + log2f(acc) : -INFINITY;
+          acc = exp2f(M);
+        } else {
+#pragma unroll
+          for (int p = 0; p < kMaxPeers; ++p)
+            if (p < np) acc += v[p];
+          M = log2f(acc);
+        }
       } else {
         for (int p = grp; p < np; p += groups) acc += part_sum[(size_t)p * stride + j];
       }
@@ -175,7 +230,10 @@ __global__ void __launch_bounds__(kFinalizeThreads)
   int bad = 0;
   if (j < m && grp == 0) {
     float s, l2s;
-    if (part_max) {
+    if (tagged) {
+      s = sh_s[c];
+      l2s = sh_m[c];
+    } else if (part_max) {
       float M = -INFINITY;
       for (int g2 = 0; g2 < groups; ++g2) M = fmaxf(M, sh_m[g2 * CB + c]);
       float acc = 0.f;
@@ -266,6 +324,19 @@ struct SweepArgs {
   int evict_first; // stream C through L2 with an evict-first policy
   int wq;          // columns per CTA (multiple of 4, <= 2048*NCH): an even split of m over the cluster
   int mode;        // 0 = normal; 1 = stream only (diagnostic: TMA ring without the arithmetic)
+  // fused iteration (sweep_lite_kernel only): after the sweep the SAME launch folds the cluster partials, exchanges
+  // the column sums with the peer ranks (world > 1), applies the finalize step and advances the state machine
+  int fuse;
+  float* gs0w;
+  float* gs1w;
+  const float* b;
+  const float* log2b;
+  double* errpart;
+  float* err_hist;
+  PeerPtrs peers;
+  int world, rank;
+  size_t xstride;
+  unsigned epoch;
 };
 
 constexpr int kSweepThreads = 512;
@@ -571,18 +642,138 @@ __global__ void __launch_bounds__(kSweepThreads, 1) sweep_fused_kernel(const Swe
   cluster_wait();
 }
 
+constexpr int kLiteThreads = 256;
+constexpr int kLiteWarps = kLiteThreads / 32;
+constexpr size_t kLiteSmemMax = 113 * 1024;
+
+// =============================================================================
+// Fused iteration tail: fold -> (peer exchange) -> finalize -> state machine, inside the sweep's own launch
+// =============================================================================
+// Runs after every CTA of the (cooperative, fully co-resident) grid has written its cluster's column partials.
+// One grid barrier makes the slabs visible; then column j is owned by thread (j mod G*T): it folds the NC slabs in
+// fixed order, (world > 1) stores the rank's sum as a tagged word into slab [parity][rank] of every peer's exchange
+// buffer over NVLink and polls the world slabs of its own buffer, adds them in rank order (identical bits on every
+// rank), and applies the finalize step.  The last CTA to finish (ticket) folds the error partials in fixed order and
+// advances the state machine -- exactly what finalize_kernel does, minus two kernel launches and their gaps.
+// `scratch`: >= 128 bytes of the kernel's DYNAMIC shared memory (the TMA ring is idle by now).  Static shared memory
+// would add to the 113 KB the kernel is sized for and cost the second CTA per SM.
+__device__ __noinline__ void sweep_fused_tail(const SweepArgs& p, State* st, int cur, int it0, int NC,
+                                              unsigned char* scratch) {
+  const int tid = threadIdx.x;
+  const unsigned G = gridDim.x;
+  double* sh_e = reinterpret_cast<double*>(scratch);  // [kLiteThreads / 32]
+  int& sh_bad = *reinterpret_cast<int*>(scratch + 64);
+  int& sh_last = *reinterpret_cast<int*>(scratch + 68);
+  __syncthreads();
+  if (tid == 0) {
+    sh_bad = 0;
+    unsigned gen;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&st->gbar_gen) : "memory");
+    __threadfence();
+    const unsigned t = atomicAdd(&st->gbar_count, 1u);
+    if (t == G - 1) {
+      st->gbar_count = 0;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->gbar_gen), "r"(gen + 1) : "memory");
+    } else {
+      unsigned now;
+      long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(&st->gbar_gen) : "memory");
+        if (now == gen) {
+          __nanosleep(64);
+          if (clock64() - t0 > 8000000000ll) {  // a lost CTA must not hang the box: poison the solve instead
+            atomicExch(&st->bad, 1);
+            break;
+          }
+        }
+      } while (now == gen);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+
+  const float* gcur = cur ? p.gs1w : p.gs0w;
+  float* gnext = cur ? p.gs0w : p.gs1w;
+  const int norm = st->err_norm;
+  // a row sum that vanished on THIS rank (bad raised by the sweep) must stop every rank in the same iteration:
+  // the rank's column sums travel as NaN, every rank's error becomes NaN and all state machines stop with bad = 1
+  const bool lbad = ((volatile int*)&st->bad)[0] != 0;
+  const int x = it0 + 1;  // exchange index of this iteration
+  const unsigned tag = peer_tag(p.epoch, x);
+  const unsigned long long word_hi = (unsigned long long)tag << 32;
+  const size_t slab0 = (size_t)(x & 1) * p.world * p.xstride;
+  double e = 0.0;
+  int bad = 0;
+  for (int j = (int)blockIdx.x * kLiteThreads + tid; j < p.m; j += (int)G * kLiteThreads) {
+    float s = 0.f;
+    for (int c = 0; c < NC; ++c) s += __ldcg(p.part + (size_t)c * p.stride + j);  // written by other SMs: L2
+    if (lbad) s = __int_as_float(0x7fc00000);
+    if (p.world > 1) {
+      const unsigned long long word = word_hi | (unsigned long long)__float_as_uint(s);
+      const size_t off = slab0 + (size_t)p.rank * p.xstride + j;
+      for (int r = 0; r < p.world; ++r) {
+        const int dst = (p.rank + r) % p.world;  // everyone starts with itself: spreads the ranks over the links
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p.peers.buf[dst] + off), "l"(word) : "memory");
+      }
+      const unsigned long long* mine = p.peers.buf[p.rank] + slab0 + j;
+      s = 0.f;
+      for (int r = 0; r < p.world; ++r) s += peer_poll(mine + (size_t)r * p.xstride, tag);
+    }
+    float gn;
+    e += finalize_column(s, log2f(s), p.b[j], p.log2b[j], gcur[j], norm, &gn, &bad);
+    gnext[j] = gn;
+  }
+  e = warp_sum(e);
+  if ((tid & 31) == 0) sh_e[tid >> 5] = e;
+  if (bad) sh_bad = 1;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < kLiteThreads / 32; ++w) tot += sh_e[w];
+    p.errpart[blockIdx.x] = tot;
+    if (sh_bad) atomicExch(&st->bad, 1);
+    __threadfence();
+    const int t = atomicAdd(&st->ticket, 1);
+    sh_last = (t == (int)G - 1);
+  }
+  __syncthreads();
+  if (!sh_last) return;
+  __threadfence();
+  {
+    double part = 0.0;
+    for (unsigned i = tid; i < G; i += kLiteThreads) part += ((volatile double*)p.errpart)[i];
+    part = warp_sum(part);
+    __syncthreads();
+    if ((tid & 31) == 0) sh_e[tid >> 5] = part;
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  double tot = 0.0;
+  for (int w = 0; w < kLiteThreads / 32; ++w) tot += sh_e[w];
+  // NaN error (a vanished column sum, a peer that never answered): stop with bad = 1
+  const float err = (norm == B200OT_NORM_L2) ? (float)sqrt(tot) : (float)tot;
+  st->ticket = 0;
+  if (!(tot == tot)) atomicExch(&st->bad, 1);
+  __threadfence();
+  if (((volatile int*)&st->bad)[0]) {
+    st->done = 1;
+    return;
+  }
+  State ls = *st;
+  advance_state(ls, err, false, p.err_hist);
+  *st = ls;
+}
+
 // =============================================================================
 // FUSED single-sweep kernel, "lite" form: 256-thread CTAs, two per SM
 // =============================================================================
 // Same mathematics and data path as sweep_fused_kernel, but latency is hidden by occupancy instead of by
 // software pipelining: each CTA keeps ONE register set of exponentials (32 per thread), so two CTAs of
 // different clusters share an SM and one computes while the other sits in its reduction / DSMEM exchange.
-constexpr int kLiteThreads = 256;
-constexpr int kLiteWarps = kLiteThreads / 32;
-constexpr size_t kLiteSmemMax = 113 * 1024;
 
 template <int NCH>
-__global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const SweepArgs p) {
+__global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __grid_constant__ SweepArgs p) {
   constexpr int CPT = 4 * NCH;
   constexpr int W = kLiteThreads * CPT;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -764,6 +955,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const Sweep
       *reinterpret_cast<float4*>(p.part + (size_t)cid * p.stride + col0 + col) =
           make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
   }
+  if (p.fuse) sweep_fused_tail(p, st, cur, it0, NC, smem);  // every row of the ring has been consumed
   cluster_arrive();
   cluster_wait();
 }
@@ -790,10 +982,6 @@ __global__ void reduce_parts_kernel(const State* st, const float* __restrict__ p
 // Row-sharded solve without NCCL in the loop: fold this rank's cluster partials and PUSH the result, as tagged
 // words, into slab [parity][rank] of every peer's exchange buffer (peer memory mapped over NVLink / NVSwitch with
 // CUDA IPC; stores are posted, nobody waits).  The finalize kernel of each rank then polls its own buffer.
-constexpr int kMaxPeers = 16;
-struct PeerPtrs {
-  unsigned long long* buf[kMaxPeers];
-};
 __global__ void __launch_bounds__(256)
     reduce_push_kernel(const State* st, const float* __restrict__ part_sum, const float* __restrict__ part_max, int np,
                        size_t stride, int m, PeerPtrs peers, int world, int rank, size_t xstride, unsigned epoch,
@@ -802,16 +990,23 @@ __global__ void __launch_bounds__(256)
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= m) return;
   float acc = 0.f;
-  if (part_max) {
+  unsigned flag = 0;
+  if (part_max) {  // running-max partials (first g update, robust iterations): send log2 of the rank's sum
+    float Mx = -INFINITY;
+    for (int p = 0; p < np; ++p) Mx = fmaxf(Mx, part_max[(size_t)p * stride + j]);
     for (int p = 0; p < np; ++p) {
       const float pm = part_max[(size_t)p * stride + j];
-      if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm);
+      if (pm > -INFINITY) acc += part_sum[(size_t)p * stride + j] * exp2f(pm - Mx);
     }
+    acc = Mx > -INFINITY ? Mx + log2f(acc) : -INFINITY;
+    flag = kPeerLogBit;
   } else {
     for (int p = 0; p < np; ++p) acc += part_sum[(size_t)p * stride + j];
   }
+  if (st->bad) acc = __int_as_float(0x7fc00000);  // a lost sum on this rank stops every rank (NaN error on all of them)
   const int x = is_prologue ? 0 : st->it + 1;
-  const unsigned long long word = ((unsigned long long)peer_tag(epoch, x) << 32) | (unsigned long long)__float_as_uint(acc);
+  const unsigned long long word =
+      ((unsigned long long)(peer_tag(epoch, x) | flag) << 32) | (unsigned long long)__float_as_uint(acc);
   const size_t off = ((size_t)(x & 1) * world + rank) * xstride + j;
   for (int r = 0; r < world; ++r) {
     const int dst = (rank + r) % world;  // spread the ranks over the links: everyone starts with itself
@@ -1023,11 +1218,11 @@ struct FusedCfg {
 
 template <int NCH, int R>
 static cudaError_t fused_set_attr() {
-  static bool attr_set = false;  // one flag per instantiation
-  if (attr_set) return cudaSuccess;
+  static PerDeviceOnce attr_once;  // one per instantiation and device
+  if (!attr_once.first()) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(sweep_fused_kernel<NCH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(232448 - 1024));
-  if (e == cudaSuccess) attr_set = true;
+  if (e != cudaSuccess) attr_once.undo();
   return e;
 }
 
@@ -1185,11 +1380,11 @@ constexpr int kLiteMaxNch = 8;
 
 template <int NCH>
 static cudaError_t lite_set_attr() {
-  static bool done = false;
-  if (done) return cudaSuccess;
+  static PerDeviceOnce attr_once;  // one per instantiation and device
+  if (!attr_once.first()) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(sweep_lite_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kLiteSmemMax);
-  if (e == cudaSuccess) done = true;
+  if (e != cudaSuccess) attr_once.undo();
   return e;
 }
 
@@ -1203,7 +1398,7 @@ static cudaError_t lite_launch_or_query(const SweepArgs* a, int Q, int NC, size_
   cfg.blockDim = dim3(kLiteThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)Q;
   at[0].val.clusterDim.y = 1;
@@ -1211,6 +1406,11 @@ static cudaError_t lite_launch_or_query(const SweepArgs* a, int Q, int NC, size_
   cfg.attrs = at;
   cfg.numAttrs = 1;
   if (!a) return cudaOccupancyMaxActiveClusters(nc_out, sweep_lite_kernel<NCH>, &cfg);
+  if (a->fuse) {  // the fused tail holds a grid barrier: every CTA must be co-resident, or the launch fails
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, sweep_lite_kernel<NCH>, *a);
 }
 
@@ -1294,8 +1494,28 @@ static int sweep_evict_first(int n, int m) {
   return ((double)n * (double)m * 4.0 > 100e6) ? 1 : 0;
 }
 
+// Peer context of a fused iteration (world = 1: no exchange).  B200OT_FUSE=0 keeps sweep and finalize as separate
+// launches (the form the one-GPU emulation of several ranks needs: kernels of different ranks must not wait for
+// one another on one device).
+struct FuseCtx {
+  PeerPtrs peers;
+  int world, rank;
+  size_t xstride;
+  unsigned epoch;
+};
+static bool g_fuse_broken = false;  // a failed cooperative cluster launch disables the fused form for the process
+static bool fuse_wanted() {
+  static int want = -1;
+  if (want < 0) {
+    const char* e = getenv("B200OT_FUSE");
+    want = (e && e[0] == '0') ? 0 : 1;
+  }
+  return want == 1 && !g_fuse_broken;
+}
+
 static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtrs& w, int* np_out,
-                              cudaStream_t s) {
+                              cudaStream_t s, const FuseCtx* fc = nullptr, bool* fused_out = nullptr) {
+  if (fused_out) *fused_out = false;
   // B200OT_FUSED_VARIANT: "lite" = 256-thread CTAs, two per SM; "pipe" = 512-thread software-pipelined
   static int variant = -1;
   if (variant < 0) {
@@ -1324,9 +1544,34 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
   a.wq = cfg.wq;
   const char* em = getenv("B200OT_FUSED_MODE");
   a.mode = em ? atoi(em) : 0;
+  a.fuse = 0;
   cudaError_t e = cudaSuccess;
   if (lite && cfg.R == 1 && cfg.smem <= kLiteSmemMax && cfg.NCH <= kLiteMaxNch && cfg.wq <= 1024 * cfg.NCH) {
-    e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
+    if (fc && fused_out && fuse_wanted() && a.mode == 0) {
+      a.fuse = 1;
+      a.gs0w = w.gs0;
+      a.gs1w = w.gs1;
+      a.b = w.b;
+      a.log2b = w.log2b;
+      a.errpart = w.errpart;
+      a.err_hist = w.err_hist;
+      a.peers = fc->peers;
+      a.world = fc->world;
+      a.rank = fc->rank;
+      a.xstride = fc->xstride;
+      a.epoch = fc->epoch;
+      e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
+      if (e == cudaSuccess) {
+        *fused_out = true;
+      } else {  // e.g. cooperative + cluster launch refused: fall back to separate launches, for good
+        (void)cudaGetLastError();
+        g_fuse_broken = true;
+        a.fuse = 0;
+        e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
+      }
+    } else {
+      e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
+    }
   } else {
 #define B200OT_L(NCH_, R_) e = launch_fused<NCH_, R_>(a, cfg.Q, cfg.NC, cfg.smem, s)
     B200OT_DISPATCH_NCH(cfg.NCH, B200OT_L)
@@ -1377,6 +1622,7 @@ static int launch_finalize(int m, const WsPtrs& w, const float* psum, const floa
                            size_t stride, int is_prologue, cudaStream_t s,
                            const unsigned long long* tagged = nullptr, unsigned epoch = 0) {
   int groups = np >= 32 ? 8 : np >= 16 ? 4 : np >= 8 ? 2 : 1;
+  if (tagged) groups = 1;  // the world's words of a column are gathered by one thread (log-domain combine)
   while (groups > 1 && (long long)(m + kFinalizeThreads / groups - 1) / (kFinalizeThreads / groups) > 4096) groups >>= 1;
   const int cb = kFinalizeThreads / groups;
   const int grid = (m + cb - 1) / cb;
@@ -1485,12 +1731,16 @@ int b200ot_sinkhorn_enqueue(const float* C, int ldc, int n, int m, int iters, in
     rc = resident_try_enqueue(C, ldc, n, m, iters, w, s);
     if (rc <= 0) return rc;
   }
+  FuseCtx solo;
+  memset(&solo, 0, sizeof(solo));
+  solo.world = 1;
   for (int i = 0; i < iters; ++i) {
     int np = 0;
     if (path == B200OT_PATH_FUSED) {
-      rc = launch_sweep_fused(C, ldc, n, m, w, &np, s);
+      bool fused = false;
+      rc = launch_sweep_fused(C, ldc, n, m, w, &np, s, &solo, &fused);
       if (rc) return rc;
-      rc = launch_finalize(m, w, w.part_sum, nullptr, np, w.m_pad, 0, s);
+      if (!fused) rc = launch_finalize(m, w, w.part_sum, nullptr, np, w.m_pad, 0, s);
     } else {
       rc = launch_rowpass(C, ldc, n, m, w, s);
       if (rc) return rc;
@@ -1606,13 +1856,18 @@ int b200ot_sinkhorn_solve(const float* C, int ldc, int n, int m, const float* a,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int rc = b200ot_sinkhorn_init(C, ldc, n, m, a, b, f0, g0, prm, ws, ws_bytes, stream);
   if (rc) return rc;
-  static thread_local int* pinned = nullptr;  // 2 slots x 8 ints + result block
-  static thread_local cudaEvent_t ev[2];
-  if (!pinned) {
-    B200OT_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&pinned), 64 * sizeof(int), cudaHostAllocDefault));
-    B200OT_CUDA_OK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    B200OT_CUDA_OK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  // events (and the pinned flag block they guard) belong to the device that was current when they were made:
+  // one set per host thread AND device
+  static thread_local int* pinned_dev[kMaxDeviceSlots] = {};  // 2 slots x 8 ints + result block
+  static thread_local cudaEvent_t ev_dev[kMaxDeviceSlots][2];
+  const int slot = device_slot();
+  if (!pinned_dev[slot]) {
+    B200OT_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&pinned_dev[slot]), 64 * sizeof(int), cudaHostAllocPortable));
+    B200OT_CUDA_OK(cudaEventCreateWithFlags(&ev_dev[slot][0], cudaEventDisableTiming));
+    B200OT_CUDA_OK(cudaEventCreateWithFlags(&ev_dev[slot][1], cudaEventDisableTiming));
   }
+  int* pinned = pinned_dev[slot];
+  cudaEvent_t* ev = ev_dev[slot];
   int path = resolve_path(prm->path, C, ldc, n, m);
   const int ce = prm->check_every > 0 ? prm->check_every : 1;
   const int phase = ((prm->check_phase % ce) + ce) % ce;
@@ -1752,7 +2007,7 @@ int b200ot_sinkhorn_shard_push(const float* C, int ldc, int n_local, int m, int 
   }
   if (rc) return rc;
   reduce_push_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, pmax, np, w.m_pad, m, pp, world, rank,
-                                                     align_up((size_t)m, 64), epoch & 0xfffu, is_prologue);
+                                                     align_up((size_t)m, 64), epoch & 0x7ffu, is_prologue);
   B200OT_LAUNCH_OK();
   return 0;
 }
@@ -1763,14 +2018,45 @@ int b200ot_sinkhorn_shard_finalize_peer(int n_local, int m, void* ws, const void
   const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
   return launch_finalize(m, w, nullptr, nullptr, world, align_up((size_t)m, 64), is_prologue,
                          static_cast<cudaStream_t>(stream), static_cast<const unsigned long long*>(my_buf),
-                         epoch & 0xfffu);
+                         epoch & 0x7ffu);
 }
 
 int b200ot_sinkhorn_shard_run_peer(const float* C, int ldc, int n_local, int m, int iters, int path, void* ws,
                                    void* const* peer_bufs, int world, int rank, unsigned epoch, void* stream) {
-  if (iters < 0 || !peer_bufs || rank < 0 || rank >= world) return B200OT_E_INVALID;
+  if (iters < 0 || !peer_bufs || rank < 0 || rank >= world || world > kMaxPeers) return B200OT_E_INVALID;
+  int rc = check_problem(C, ldc, n_local, m, ws);
+  if (rc) return rc;
+  const bool can_fuse = resolve_path(path, C, ldc, n_local, m) == B200OT_PATH_FUSED && fuse_wanted();
+  const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
+  FuseCtx fc;
+  memset(&fc, 0, sizeof(fc));
+  for (int r = 0; r < world; ++r) {
+    if (!peer_bufs[r]) return B200OT_E_INVALID;
+    fc.peers.buf[r] = static_cast<unsigned long long*>(peer_bufs[r]);
+  }
+  fc.world = world;
+  fc.rank = rank;
+  fc.xstride = align_up((size_t)m, 64);
+  fc.epoch = epoch & 0x7ffu;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (int i = 0; i < iters; ++i) {
-    int rc = b200ot_sinkhorn_shard_push(C, ldc, n_local, m, path, ws, peer_bufs, world, rank, epoch, 0, stream);
+    bool fused = false;
+    if (can_fuse && !g_fuse_broken) {
+      // ONE launch per iteration: sweep + fold + push to the peers + poll + finalize + state machine
+      int np = 0;
+      rc = launch_sweep_fused(C, ldc, n_local, m, w, &np, s, &fc, &fused);
+      if (rc) return rc;
+      if (!fused) {  // the pipelined kernel ran instead (no fused tail): finish the iteration the unfused way
+        PeerPtrs pp = fc.peers;
+        reduce_push_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, nullptr, np, w.m_pad, m, pp, world, rank,
+                                                           fc.xstride, fc.epoch, 0);
+        B200OT_LAUNCH_OK();
+        rc = b200ot_sinkhorn_shard_finalize_peer(n_local, m, ws, peer_bufs[rank], world, epoch, 0, stream);
+        if (rc) return rc;
+      }
+      continue;
+    }
+    rc = b200ot_sinkhorn_shard_push(C, ldc, n_local, m, path, ws, peer_bufs, world, rank, epoch, 0, stream);
     if (rc) return rc;
     rc = b200ot_sinkhorn_shard_finalize_peer(n_local, m, ws, peer_bufs[rank], world, epoch, 0, stream);
     if (rc) return rc;

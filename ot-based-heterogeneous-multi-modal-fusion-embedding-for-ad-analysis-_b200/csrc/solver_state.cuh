@@ -22,7 +22,8 @@ struct State {
   float err, kscale, eps, tol;
   int max_iter, check_every, check_phase, err_norm;
   int stop_inclusive, path, snap_it, snap_cur;
-  int snap_n_err, res_epoch, pad1, pad2;  // res_epoch: launches of the resident kernel on this workspace
+  int snap_n_err, res_epoch;  // res_epoch: launches of the resident kernel on this workspace
+  unsigned gbar_count, gbar_gen;  // grid barrier of the fused-iteration sweep (count returns to 0 after every use)
   float snap_err, pad3, pad4, pad5;
   // range of the scaled row potentials fs; slot [it & 1] is valid when `it` iterations are complete,
   // the sweep of iteration it+1 fills slot [(it+1) & 1].  lo > hi means "unknown".

@@ -135,11 +135,116 @@ def cotl():
     print("cotl_sinkhorn.npz written: rounds", len(lg["cost"]), "cost", cost)
 
 
+def ott_labels():
+    """Case 9: the label-aware / all-to-all ott call sites of perturbot/perturbot/match/ott_egwl.py --
+    ``get_coupling_egw_labels_ott`` (:25-127), ``get_coupling_egw_all_ott`` (:209-297) and ``get_coupling_leot_ott``
+    (:375-454) -- compiled from the reference's AST together with ``create_block_diag_mat`` (:16-22).  ``jax`` /
+    ``ott`` (and the modified OTT with ``labels_a / labels_b / block_diag_mat`` the first and third expect) are not
+    installable, so they are bound to stubs that forward to the oracle's restatements: the SHELL (concatenation in
+    first-seen label order, label arrays, the block-diagonal matrix, solver parameters, the per-label slicing of
+    the result, the log keys) is the reference's own code, the inner solves are the restatement."""
+    import contextlib
+    import io
+    import time as _time
+
+    class _PC:
+        def __init__(self, x, y, scale_cost=None, **kw):
+            self.x, self.y, self.scale_cost = np.asarray(x), np.asarray(y), scale_cost
+
+        @property
+        def cost_matrix(self):
+            C = orc.sqeuclid_cost(self.x, self.y)
+            return C / C.max() if self.scale_cost == "max_cost" else C
+
+    class _Geom:
+        def __init__(self, cost_matrix, epsilon=None, **kw):
+            self.cost_matrix, self.epsilon = np.asarray(cost_matrix), epsilon
+
+    class _LP:
+        def __init__(self, geom, labels_a=None, labels_b=None, **kw):
+            self.geom, self.labels_a, self.labels_b = geom, labels_a, labels_b
+
+    class _Res:
+        pass
+
+    class _SK:
+        def __init__(self, **kw):
+            self.kw = kw
+
+        def __call__(self, prob):
+            mask = None
+            if prob.labels_a is not None:
+                mask = orc.block_diag_mask(np.asarray(prob.labels_a), np.asarray(prob.labels_b))
+            P, lg = orc.sinkhorn_log_ott(prob.geom.cost_matrix, prob.geom.epsilon, scale_cost=None, mask=mask, log=True)
+            r = _Res()
+            r.n_iters, r.converged, r.matrix = lg["n_iter"], lg["converged"], P
+            n, m = P.shape
+            fin_f, fin_g = lg["f"][np.isfinite(lg["f"])], lg["g"][np.isfinite(lg["g"])]
+            r.reg_ot_cost = float(fin_f.sum() / n + fin_g.sum() / m)
+            return r
+
+    class _QP:
+        def __init__(self, geom_xx, geom_yy, labels_a=None, labels_b=None, n_labels=None, block_diag_mat=None, **kw):
+            self.geom_xx, self.geom_yy, self.bdm = geom_xx, geom_yy, block_diag_mat
+
+    class _GW:
+        def __init__(self, epsilon=None, store_inner_errors=False, max_iterations=50, kwargs_sinkhorn=None, **kw):
+            self.eps, self.max_it = epsilon, max_iterations
+            self.sk_it = (kwargs_sinkhorn or {}).get("max_iterations", 2000)
+
+        def __call__(self, prob):
+            T, lg = orc.egw_ott(prob.geom_xx.x, prob.geom_yy.x, self.eps, gw_max_iterations=self.max_it,
+                                sinkhorn_max_iterations=self.sk_it,
+                                mask=None if prob.bdm is None else np.asarray(prob.bdm))
+            r = _Res()
+            r.n_iters, r.converged, r.reg_gw_cost, r.matrix = lg["n_iters_outer"], lg["converged_outer"], lg["GW cost"], T
+            r.linear_convergence = np.array([True] * (lg["n_iters_outer"] - 1) + [lg["converged_inner"]])
+            r.inner_iterations = lg["inner_iterations"]
+            return r
+
+    ns = {"np": np, "jnp": types.SimpleNamespace(array=np.asarray), "time": _time,
+          "pointcloud": types.SimpleNamespace(PointCloud=_PC), "geometry": types.SimpleNamespace(Geometry=_Geom),
+          "linear_problem": types.SimpleNamespace(LinearProblem=_LP),
+          "quadratic_problem": types.SimpleNamespace(QuadraticProblem=_QP),
+          "gromov_wasserstein": types.SimpleNamespace(GromovWasserstein=_GW),
+          "sinkhorn": types.SimpleNamespace(Sinkhorn=_SK)}
+    path = os.path.join(REF, "perturbot/perturbot/match/ott_egwl.py")
+    extract_function(path, "create_block_diag_mat", ns)
+    ref_egwl = extract_function(path, "get_coupling_egw_labels_ott", ns)
+    ref_egwa = extract_function(path, "get_coupling_egw_all_ott", ns)
+    ref_leot = extract_function(path, "get_coupling_leot_ott", ns)
+    rng = np.random.default_rng(41)
+    Xd, Yd = {}, {}
+    for k, (nk, mk) in {3: (10, 10), 0: (14, 14), 7: (8, 8)}.items():  # unsorted insertion order
+        base = rng.standard_normal((nk, 6)) + 0.6 * k
+        Xd[k] = base.astype(np.float32)
+        Q, _ = np.linalg.qr(rng.standard_normal((6, 6)))
+        Yd[k] = ((base @ Q)[rng.permutation(nk)][:mk] + 0.05 * rng.standard_normal((mk, 6))).astype(np.float32)
+    save = {"eps": 5e-2, "keys": np.array(list(Xd.keys()))}
+    for k in Xd:
+        save[f"X{k}"], save[f"Y{k}"] = Xd[k], Yd[k]
+    with contextlib.redirect_stdout(io.StringIO()):
+        Tl, lgl = ref_egwl((Xd, Yd), 5e-2)
+        Ta, lga = ref_egwa((Xd, Yd), 5e-2)
+        To, lgo = ref_leot((Xd, Yd), 5e-2)
+    for k in Xd:
+        save[f"egwl_T{k}"], save[f"leot_T{k}"] = Tl[k], To[k]
+    save["egwa_T"] = Ta
+    save["egwl_log"] = np.array([lgl["n_iters_outer"], float(lgl["converged_inner"]), float(lgl["converged_outer"]), lgl["GW cost"]])
+    save["egwa_log"] = np.array([lga["n_iters_outer"], float(lga["converged_inner"]), float(lga["converged_outer"]), lga["GW cost"]])
+    save["leot_log"] = np.array([lgo["n_iters_outer"], float(lgo["converged"]), lgo["OT cost"]])
+    np.savez_compressed(os.path.join(HERE, "ott_labels.npz"), **save)
+    print("ott_labels.npz written:", save["egwl_log"], save["egwa_log"], save["leot_log"],
+          "label keys of the result dicts:", list(Tl.keys()), list(To.keys()))
+
+
 def main():
     if "--extras" in sys.argv:
         return extras()
     if "--cotl" in sys.argv:
         return cotl()
+    if "--ott-labels" in sys.argv:
+        return ott_labels()
     ref_utils = load_ref_utils()
     out = {}
 
@@ -251,6 +356,7 @@ def main():
     print("golden vectors written:", out)
     extras()
     cotl()
+    ott_labels()
 
 
 if __name__ == "__main__":

@@ -64,14 +64,48 @@ def test_no_oracle_or_cpu_fallback_in_product():
                 assert "oracle" not in text.replace("no CPU or PyTorch fallback", ""), (f, "mentions oracle")
 
 
-def test_sass_has_bulk_copy_and_cluster_barrier(native_lib):
-    """The fused sweep must really use the TMA bulk-copy engine and cluster barriers."""
+def _sass_by_kernel(native_lib):
+    """{demangled-ish kernel name: SASS text} from cuobjdump -sass of the in-tree library."""
+    import re
     out = subprocess.run(["cuobjdump", "-sass", native_lib], capture_output=True, text=True)
     if out.returncode != 0:
         pytest.skip("cuobjdump unavailable")
-    assert "UBLKCP" in out.stdout
-    assert "UCGABAR" in out.stdout
-    assert "MUFU.EX2" in out.stdout
+    parts = re.split(r"\n\s*Function : ", out.stdout)
+    return {p.split("\n", 1)[0].strip(): p for p in parts[1:]}
+
+
+SASS_OPS = ("UTCHMMA", "LDTM", "UBLKCP", "SYNCS", "UCGABAR", "MUFU.EX2", "HMMA", "DFMA")
+
+
+def test_sass_opcode_table_proves_tcgen05_tma_and_cluster_paths(native_lib):
+    """Per-kernel SASS opcode counts (also written to profiles/r02_sass_opcodes.json).  tcgen05.mma = UTCHMMA,
+    tcgen05.ld = LDTM, TMA bulk copy = UBLKCP, mbarrier = SYNCS, cluster barrier = UCGABAR (B200_PROFILING.md)."""
+    import json
+    kernels = _sass_by_kernel(native_lib)
+    table = {}
+    for name, text in kernels.items():
+        row = {op: text.count(op) for op in SASS_OPS}
+        if any(row.values()):
+            table[name] = row
+
+    def find(sub):
+        hits = [k for k in table if sub in k]
+        assert hits, (sub, sorted(table))
+        return {op: sum(table[k][op] for k in hits) for op in SASS_OPS}
+
+    for kern in ("cost_tc_kernel", "apply_tc_kernel"):  # the two tensor-core kernels
+        row = find(kern)
+        assert row["UTCHMMA"] > 0 and row["LDTM"] > 0 and row["UBLKCP"] > 0 and row["SYNCS"] > 0, (kern, row)
+        assert row["HMMA"] == row["UTCHMMA"], (kern, "legacy mma.sync found", row)  # HMMA only as a substring of UTCHMMA
+    assert find("apply_tc_kernel")["MUFU.EX2"] > 0
+    sweep = find("sweep_lite_kernel")
+    assert sweep["UBLKCP"] > 0 and sweep["UCGABAR"] > 0 and sweep["MUFU.EX2"] > 0 and sweep["SYNCS"] > 0
+    assert find("resident_kernel")["UBLKCP"] > 0
+    assert find("sinkhorn_batched_kernel")["DFMA"] > 0  # float64 arithmetic of POT's loop
+    out = os.path.join(ROOT, "profiles", "r02_sass_opcodes.json")
+    with open(out, "w") as fh:
+        json.dump({"source": "cuobjdump -sass b200ot/libb200ot.so (tests/test_abi.py)", "ops": list(SASS_OPS),
+                   "kernels": {k: table[k] for k in sorted(table)}}, fh, indent=1)
 
 
 def test_argument_validation_happens_before_any_device_work(native_lib):

@@ -101,6 +101,11 @@ def test_benchmarked_sweep_lite_q8_configuration_matches_oracle(cuda_dev, d):
                         ["sweep_lite_kernel", "cluster=8 CTAs x 256 threads", "32 cols/thread", "evict-first"], 50, d=d)
     # identical to the 65536-row configuration bench.py runs (the row count only bounds the number of clusters)
     assert desc == ops.describe_kernel(65536, 65536)
+    # two CTAs per SM: 33 clusters of 8 on a B200 (a kernel that grows past 113 KB of shared memory per CTA, static
+    # included, silently drops to one CTA per SM and half the bandwidth)
+    import re
+    nclusters = int(re.search(r"(\d+) clusters", desc).group(1))
+    assert nclusters * 8 > torch.cuda.get_device_properties(cuda_dev).multi_processor_count, desc
 
 
 def test_resident_512_thread_variant_at_8192_columns_matches_oracle(cuda_dev):

@@ -196,3 +196,27 @@ def test_cotl_sinkhorn_matches_the_reference_function(golden_dir):
     np.testing.assert_allclose(Tv, g["Tv"], rtol=0, atol=1e-12)
     for k in keys:
         np.testing.assert_allclose(Ts[k], g[f"Ts{k}"], rtol=0, atol=1e-12)
+
+
+def test_label_aware_ott_shells_match_reference_code(golden_dir):
+    """get_coupling_egw_labels_ott / get_coupling_egw_all_ott / get_coupling_leot_ott
+    (perturbot/perturbot/match/ott_egwl.py:25-127,209-297,375-454): the oracle's restatements against the golden
+    produced by the reference's own function bodies (tests/golden/make_golden.py --ott-labels: concatenation order,
+    label arrays, block-diagonal matrix, solver parameters and per-label slicing are the reference's code)."""
+    g = np.load(os.path.join(golden_dir, "ott_labels.npz"))
+    keys = [int(k) for k in g["keys"]]
+    Xd = {k: g[f"X{k}"] for k in keys}
+    Yd = {k: g[f"Y{k}"] for k in keys}
+    eps = float(g["eps"])
+    Tl, lgl = orc.get_coupling_egw_labels_ott((Xd, Yd), eps)
+    Ta, lga = orc.get_coupling_egw_all_ott((Xd, Yd), eps)
+    To, lgo = orc.get_coupling_leot_ott((Xd, Yd), eps)
+    assert [int(k) for k in Tl.keys()] == sorted(keys) == [int(k) for k in To.keys()]  # np.unique order (:124)
+    for k in keys:
+        np.testing.assert_allclose(Tl[k], g[f"egwl_T{k}"], rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(To[k], g[f"leot_T{k}"], rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(Ta, g["egwa_T"], rtol=1e-10, atol=1e-300)
+    assert lgl["n_iters_outer"] == int(g["egwl_log"][0]) and lga["n_iters_outer"] == int(g["egwa_log"][0])
+    assert lgo["n_iter"] == int(g["leot_log"][0])
+    # the constraint: all the mass sits on pairs of equal label, total mass 1
+    assert abs(sum(v.sum() for v in Tl.values()) - 1.0) < 1e-3 and abs(sum(v.sum() for v in To.values()) - 1.0) < 1e-3

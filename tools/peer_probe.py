@@ -77,6 +77,30 @@ for name, kw in (("peer", {"peer": peer}), ("nccl", {"comm": comm})):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out[name + "_ms_per_iteration"] = float(t.item())
     assert k.flags()["bad"] == 0
+# ---- where an iteration's time goes: the local sweep alone (sweep + fold of the cluster partials, no exchange,
+# the state does not advance) against the full loop above
+k = sharded.CudaShardKernels(C, a, b, prm)
+k.setup()
+k.finalize(k.prologue(), True)
+for _ in range(5):
+    k.sweep()
+dist.barrier()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters):
+    k.sweep()
+e1.record()
+torch.cuda.synchronize()
+t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+tmax = t.clone()
+dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+tmin = t.clone()
+dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+out["sweep_plus_fold_ms_max_over_ranks"] = float(tmax.item())
+out["sweep_plus_fold_ms_min_over_ranks"] = float(tmin.item())
+out["fuse"] = os.environ.get("B200OT_FUSE", "1")
+out["hbm_bytes_per_iteration_per_rank"] = 4.0 * (hi - lo) * m
 if rank == 0:
     print(json.dumps(out), flush=True)
 dist.barrier()
