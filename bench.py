@@ -359,6 +359,15 @@ def extras(torch, dist, ops, world, rank, dev, args):
         "e2e_note": "pinned embeddings -> H2D -> cost -> 200 iterations -> fused embedding (tcgen05) -> D2H, then "
                     "cost + envelope backward (one tcgen05 launch for dX and dY) -> dX D2H"}
     del C3, st3
+    # ---- C5: OT share of the end-to-end training step (reference CPU path of the OT leg vs device path)
+    if not args.no_step:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_step
+            out["c5_step"] = bench_step.measure(32, 96, steps=3, warm=2, dev=dev)
+        except Exception as exc:  # noqa: BLE001 -- informational: never lose the headline line over it
+            out["c5_step"] = {"error": repr(exc)}
+        torch.cuda.empty_cache()
     # ---- online (cost-free) solver at the headline shape
     if not args.no_online:
         from b200ot.online import OnlineSinkhorn
@@ -603,6 +612,8 @@ def run_b200(args):
         if world > 1:
             _shutdown(dist)
         return
+    from b200ot import _lib as _b200ot_lib
+    lib_counter = _b200ot_lib.load().b200ot_sinkhorn_counter
     peak, peak_src = _peaks()
     alg_bytes = 4.0 * n_loc * m  # one fp32 read of this rank's rows of C per iteration
     per_iter_s = ms_per_step * 1e-3 / iters
@@ -646,6 +657,7 @@ def run_b200(args):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "parity": parity,
+        "fused_iteration_launches": int(lib_counter(0)), "fused_iteration_fallbacks": int(lib_counter(1)),
         "extra": extra,
     }
     print(json.dumps(line), flush=True)
@@ -688,6 +700,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run value checks")
     ap.add_argument("--no-extras", action="store_true", help="skip the C2 / C3 / online measurements")
     ap.add_argument("--no-online", action="store_true", help="skip the online (cost-free) measurement")
+    ap.add_argument("--no-step", action="store_true", help="skip the C5 end-to-end training-step measurement")
     ap.add_argument("--no-sampler", action="store_true", help="diagnostic: do not sample clocks")
     args = ap.parse_args()
     if args.impl == "reference":

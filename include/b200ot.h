@@ -155,6 +155,10 @@ int b200ot_sinkhorn_enqueue(const float* C, int ldc, int n, int m, int iters, in
 int b200ot_sinkhorn_snapshot(int n, int m, void* ws, void* stream);
 int b200ot_sinkhorn_rewind(int n, int m, void* ws, void* stream);
 int b200ot_sinkhorn_peek(void* ws, int* flags8, void* stream);
+/* host-side counters of this process: which = 0 iterations launched in the fused form (sweep + fold + exchange +
+ * finalize + state machine in ONE cooperative cluster launch), 1 = fused launches that were refused and fell back
+ * to separate launches (the fused form is then disabled for the process; b200ot_last_cuda_error says why).    */
+long long b200ot_sinkhorn_counter(int which);
 /* human-readable description of the kernel configuration chosen for an n x m problem (host buffer) */
 int b200ot_sinkhorn_describe(int n, int m, char* buf_host, int buf_len);
 int b200ot_sinkhorn_finish(int n, int m, void* ws, float* f, float* g, b200ot_result* result,

@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200ot_sinkhorn_snapshot": (_i, [_i, _i, _p, _p]),
     "b200ot_sinkhorn_rewind": (_i, [_i, _i, _p, _p]),
     "b200ot_sinkhorn_peek": (_i, [_p, _p, _p]),
+    "b200ot_sinkhorn_counter": (C.c_longlong, [_i]),
     "b200ot_sinkhorn_describe": (_i, [_i, _i, C.c_char_p, _i]),
     "b200ot_sinkhorn_finish": (_i, [_i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "b200ot_sinkhorn_solve": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, C.POINTER(Params), _p, _sz, _p, _p,

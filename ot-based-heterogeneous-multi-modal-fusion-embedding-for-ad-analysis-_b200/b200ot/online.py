@@ -133,11 +133,28 @@ class OnlineSinkhorn:
         return self.finish()
 
 
-def choose_path(n: int, m: int, d: int, free_bytes: int, terms: int = 6, hbm_gbs: float = 6537.0,
-                tensor_tflops: float = 1250.0) -> str:
-    """'streaming' (materialise C once, 4nm bytes per iteration) or 'online' (2nmd*terms tensor flops per
-    iteration, no C).  The measured rates (profiles/) make streaming ~7x faster per iteration at d = 512, so the
-    rule is simply: stream whenever C and its workspace fit."""
-    if 4.0 * n * m * 1.02 + 3e8 <= free_bytes:
+# Rates measured on one B200 (round 2; bench.py `roofline` / `extra.online_c4`, profiles/r02_bench_n1.json,
+# profiles/r02_online_launches.csv).  choose_path compares the two per-iteration costs with THESE numbers, not
+# with data-sheet peaks.
+MEASURED = {
+    "stream_hbm_gbs": 5900.0,           # single-sweep kernel at 65536^2: 0.85-0.96 of the 6537 GB/s copy peak across boxes
+    "online_tflops_executed": 1000.0,   # cost_tc panels of 8192 rows + panel sweep, 6-term split (tensor pipe the bound)
+    "online_min_k": 64,                 # the GEMM pads d to its 64-wide K block
+}
+
+
+def choose_path(n: int, m: int, d: int, free_bytes: int, terms: int = 6, rates: Optional[dict] = None) -> str:
+    """'streaming' (materialise C once, 4nm bytes of HBM per iteration) or 'online' (2nm*d*terms tensor flops per
+    iteration plus one write and one read of every panel, no n x m matrix).  Counter-driven: both per-iteration
+    times are evaluated with the measured rates in ``MEASURED``.  At d = 512 with the fp32-grade 6-term split
+    streaming is ~8x faster, and because every panel is written once and read once the online path never beats
+    a resident C even for narrow embeddings: it is chosen when C and its workspace do not fit in HBM."""
+    r = dict(MEASURED if rates is None else rates)
+    nm = float(n) * float(m)
+    t_stream = 4.0 * nm / (r["stream_hbm_gbs"] * 1e9)
+    d_eff = max(int(d), int(r.get("online_min_k", 64)))
+    t_online = 2.0 * nm * d_eff * terms / (r["online_tflops_executed"] * 1e12) + 8.0 * nm / (r["stream_hbm_gbs"] * 1e9)
+    fits = 4.0 * nm * 1.02 + 3e8 <= free_bytes
+    if fits and t_stream <= t_online:
         return "streaming"
     return "online"

@@ -1504,6 +1504,7 @@ struct FuseCtx {
   unsigned epoch;
 };
 static bool g_fuse_broken = false;  // a failed cooperative cluster launch disables the fused form for the process
+static long long g_fused_launches = 0, g_fused_fallbacks = 0;  // host-side counters (b200ot_sinkhorn_counter)
 static bool fuse_wanted() {
   static int want = -1;
   if (want < 0) {
@@ -1563,9 +1564,12 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
       e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
       if (e == cudaSuccess) {
         *fused_out = true;
+        ++g_fused_launches;
       } else {  // e.g. cooperative + cluster launch refused: fall back to separate launches, for good
+        set_last_cuda_error(e, "fused-iteration launch (cooperative cluster launch)");
         (void)cudaGetLastError();
         g_fuse_broken = true;
+        ++g_fused_fallbacks;
         a.fuse = 0;
         e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
       }
@@ -1839,6 +1843,10 @@ int b200ot_sinkhorn_describe(int n, int m, char* buf, int buf_len) {
            (size_t)cfg.R * (lite ? kLiteThreads : kSweepThreads) * 4 * cfg.NCH * 4, cfg.smem,
            sweep_evict_first(n, m) ? "evict-first" : "default policy");
   return 0;
+}
+
+long long b200ot_sinkhorn_counter(int which) {
+  return which == 0 ? g_fused_launches : which == 1 ? g_fused_fallbacks : -1;
 }
 
 int b200ot_sinkhorn_peek(void* ws, int* flags8, void* stream) {

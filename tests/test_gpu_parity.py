@@ -752,6 +752,7 @@ def test_fused_iteration_with_peer_words_single_rank(cuda_dev, n, m):
     buffer, so the whole exchange protocol runs on one GPU without any kernel waiting for another launch.
     Same plan and iteration count as the oracle; equal to the separate-launch form bit for bit."""
     from b200ot import ops, sharded
+    from b200ot import _lib as _lib_mod
     X, Y = orc.synthetic_embeddings(n, m, 24, config_index=10)
     C = orc.sqeuclid_cost(X, Y)
     a = np.ones(n) / n
@@ -787,6 +788,10 @@ def test_fused_iteration_with_peer_words_single_rank(cuda_dev, n, m):
     assert _rel(ops.plan(Cd, f, g, eps).cpu().numpy(), Pref) < RTOL
     np.testing.assert_allclose(info["errs"].cpu().numpy(), lg["err"], rtol=2e-2, atol=2e-6)
     assert torch.equal(outs[1][0], f) and torch.equal(outs[1][1], g)  # same fold order in both forms
+    # the fused form really ran (a refused cooperative cluster launch would silently fall back)
+    lib = _lib_mod.load()
+    assert lib.b200ot_sinkhorn_counter(1) == 0, lib.b200ot_last_cuda_error()
+    assert lib.b200ot_sinkhorn_counter(0) >= lg["n_iter"]
 
 
 def test_sharded_solve_recovers_from_a_lost_sum(cuda_dev):

@@ -233,3 +233,86 @@ def test_two_rank_peer_exchange_loop_matches_unsharded_oracle(tmp_path, tol):
     np.testing.assert_array_equal(parts[0]["g"], parts[1]["g"])
     f = np.concatenate([p["f"] for p in parts])
     np.testing.assert_allclose(orc.plan_from_potentials(C, f, parts[0]["g"], 0.1), Pref, rtol=1e-9, atol=1e-15)
+
+
+# ---------------------------------------------------------------------------
+# recovery: a lost sum on ONE rank stops every rank, the chunk is rewound and replayed on the robust path
+# ---------------------------------------------------------------------------
+class FlakyShardKernels(NumpyShardKernels):
+    """The fast path of rank `fail_rank` loses a row sum in iteration `fail_it` (what the CUDA sweep reports as
+    `bad`).  Like the kernels, the rank then sends NaN column sums, so every rank's finalize sees NaN, raises `bad`
+    and stops in the same iteration; snapshot / rewind / use_robust_path are the C-ABI calls of CudaShardKernels."""
+
+    def __init__(self, *a, rank=0, fail_rank=1, fail_it=3, **kw):
+        super().__init__(*a, **kw)
+        self.rank, self.fail_rank, self.fail_it = rank, fail_rank, fail_it
+        self.robust, self.bad, self.replayed_from = False, 0, None
+
+    def setup(self):
+        super().setup()
+        self.bad = 0
+
+    def sweep(self):
+        s = super().sweep()
+        if not self.robust and not self.done and self.rank == self.fail_rank and self.it + 1 == self.fail_it:
+            return torch.full_like(s, float("nan"))
+        return s
+
+    def finalize(self, s_total, is_prologue):
+        if not self.done and bool(torch.isnan(s_total).any()):
+            self.bad = self.done = 1
+            return
+        super().finalize(s_total, is_prologue)
+
+    def snapshot(self):
+        self.snap = (self.f.copy(), self.g.copy(), self.it, list(self.errs))
+
+    def rewind(self):
+        self.f, self.g, self.it, self.errs = self.snap[0].copy(), self.snap[1].copy(), self.snap[2], list(self.snap[3])
+        self.done = self.converged = self.bad = 0
+        self.replayed_from = self.it
+
+    def use_robust_path(self):
+        self.robust = True
+
+    def flags(self):
+        fl = super().flags()
+        fl["bad"] = self.bad
+        return fl
+
+
+def _worker_flaky(rank, world, port, n, m, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "ot-based-heterogeneous-multi-modal-fusion-embedding-for-ad-analysis-_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from b200ot.sharded import ShardedSinkhorn, row_range
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, Y = orc.synthetic_embeddings(n, m, 16, config_index=4)
+    C = orc.sqeuclid_cost(X, Y)
+    a = np.ones(n) / n
+    b = np.ones(m) / m
+    lo, hi = row_range(n, world, rank)
+    k = FlakyShardKernels(C[lo:hi], a[lo:hi], b, 0.1, 200, 1e-3, 10, 0, rank=rank, fail_rank=1, fail_it=13)
+    f, g, info = ShardedSinkhorn(k).solve(200, check_every=10, check_phase=0)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), f=f, g=g, n_iter=info["n_iter"], converged=info["converged"],
+             replayed_from=-1 if k.replayed_from is None else k.replayed_from, robust=k.robust, bad=k.bad)
+    dist.destroy_process_group()
+
+
+def test_lost_sum_on_one_rank_rewinds_every_rank(tmp_path):
+    n, m, world = 50, 36, 2
+    port = 29500 + (os.getpid() % 500) + 7
+    mp.spawn(_worker_flaky, args=(world, port, n, m, str(tmp_path)), nprocs=world, join=True)
+    X, Y = orc.synthetic_embeddings(n, m, 16, config_index=4)
+    C = orc.sqeuclid_cost(X, Y)
+    Pref, lg = orc.sinkhorn_log(C, np.ones(n) / n, np.ones(m) / m, 0.1, max_iter=200, tol=1e-3, err_norm="l1",
+                                check_every=10, check_phase=0, log=True)
+    assert lg["n_iter"] > 13  # the failure happens before convergence
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for p in parts:  # BOTH ranks saw the failure, rewound to the start of the chunk (iteration 10) and switched path
+        assert int(p["replayed_from"]) == 10 and bool(p["robust"]) and int(p["bad"]) == 0
+        assert int(p["n_iter"]) == lg["n_iter"] and bool(p["converged"]) == lg["converged"]
+    f = np.concatenate([p["f"] for p in parts])
+    np.testing.assert_allclose(orc.plan_from_potentials(C, f, parts[0]["g"], 0.1), Pref, rtol=1e-9, atol=1e-15)
