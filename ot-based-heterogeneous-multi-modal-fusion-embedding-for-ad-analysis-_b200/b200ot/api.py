@@ -403,13 +403,19 @@ def group_features_by_label(y, p, max_samples_per_label=None):
     ``p`` by label (labels in ascending order, rows in their original order, at most ``max_samples_per_label``
     per bucket).  With CUDA tensors the buckets are built by device indexing: no device->host copy."""
     if isinstance(p, torch.Tensor):
-        y = torch.as_tensor(y, device=p.device)
-        out = {}
-        for label in torch.unique(y).tolist():
-            idx = torch.nonzero(y == label, as_tuple=False).reshape(-1)
-            if max_samples_per_label is not None and max_samples_per_label > 0:
-                idx = idx[:max_samples_per_label]
-            out[int(label)] = p.index_select(0, idx)
+        # one stable sort by label, one gather, ONE device -> host read (labels and bucket sizes together); the
+        # buckets are views of the sorted copy.  (The first version synchronised once per label.)
+        y = torch.as_tensor(y, device=p.device).reshape(-1)
+        order = torch.argsort(y, stable=True)
+        labels, counts = torch.unique_consecutive(y.index_select(0, order), return_counts=True)
+        sorted_p = p.index_select(0, order)
+        meta = torch.stack([labels.to(torch.int64), counts.to(torch.int64)]).tolist()
+        out, start = {}, 0
+        for label, cnt in zip(*meta):
+            take = cnt if not (max_samples_per_label is not None and max_samples_per_label > 0) else min(
+                cnt, int(max_samples_per_label))
+            out[int(label)] = sorted_p[start:start + take]
+            start += cnt
         return out
     y = np.asarray(y)
     p = np.asarray(p)

@@ -326,7 +326,9 @@ struct SweepArgs {
   int mode;        // 0 = normal; 1 = stream only (diagnostic: TMA ring without the arithmetic)
   // fused iteration (sweep_lite_kernel only): after the sweep the SAME launch folds the cluster partials, exchanges
   // the column sums with the peer ranks (world > 1), applies the finalize step and advances the state machine
+  int stagger_ns;  // tuning (B200OT_STAGGER): clusters with odd id start this many ns late
   int fuse;
+  int iters;       // fused form: iterations this launch runs (stops earlier when the stopping rule fires)
   float* gs0w;
   float* gs1w;
   const float* b;
@@ -657,16 +659,10 @@ constexpr size_t kLiteSmemMax = 113 * 1024;
 // advances the state machine -- exactly what finalize_kernel does, minus two kernel launches and their gaps.
 // `scratch`: >= 128 bytes of the kernel's DYNAMIC shared memory (the TMA ring is idle by now).  Static shared memory
 // would add to the 113 KB the kernel is sized for and cost the second CTA per SM.
-__device__ __noinline__ void sweep_fused_tail(const SweepArgs& p, State* st, int cur, int it0, int NC,
-                                              unsigned char* scratch) {
-  const int tid = threadIdx.x;
-  const unsigned G = gridDim.x;
-  double* sh_e = reinterpret_cast<double*>(scratch);  // [kLiteThreads / 32]
-  int& sh_bad = *reinterpret_cast<int*>(scratch + 64);
-  int& sh_last = *reinterpret_cast<int*>(scratch + 68);
+// Grid barrier of a cooperative (fully co-resident) launch: counter + generation word in the state block.
+__device__ __forceinline__ void grid_sync(State* st, unsigned G) {
   __syncthreads();
-  if (tid == 0) {
-    sh_bad = 0;
+  if (threadIdx.x == 0) {
     unsigned gen;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&st->gbar_gen) : "memory");
     __threadfence();
@@ -677,13 +673,14 @@ __device__ __noinline__ void sweep_fused_tail(const SweepArgs& p, State* st, int
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->gbar_gen), "r"(gen + 1) : "memory");
     } else {
       unsigned now;
-      long long t0 = clock64();
+      const long long t0 = clock64();
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(&st->gbar_gen) : "memory");
         if (now == gen) {
           __nanosleep(64);
           if (clock64() - t0 > 8000000000ll) {  // a lost CTA must not hang the box: poison the solve instead
             atomicExch(&st->bad, 1);
+            atomicExch(&st->done, 1);
             break;
           }
         }
@@ -692,6 +689,17 @@ __device__ __noinline__ void sweep_fused_tail(const SweepArgs& p, State* st, int
     __threadfence();
   }
   __syncthreads();
+}
+
+__device__ __noinline__ void sweep_fused_tail(const SweepArgs& p, State* st, int cur, int it0, int NC,
+                                              unsigned char* scratch) {
+  const int tid = threadIdx.x;
+  const unsigned G = gridDim.x;
+  double* sh_e = reinterpret_cast<double*>(scratch);  // [kLiteThreads / 32]
+  int& sh_bad = *reinterpret_cast<int*>(scratch + 64);
+  int& sh_last = *reinterpret_cast<int*>(scratch + 68);
+  if (tid == 0) sh_bad = 0;
+  grid_sync(st, G);  // every cluster's partial slab is complete and visible
 
   const float* gcur = cur ? p.gs1w : p.gs0w;
   float* gnext = cur ? p.gs0w : p.gs1w;
@@ -721,7 +729,7 @@ __device__ __noinline__ void sweep_fused_tail(const SweepArgs& p, State* st, int
       for (int r = 0; r < p.world; ++r) s += peer_poll(mine + (size_t)r * p.xstride, tag);
     }
     float gn;
-    e += finalize_column(s, log2f(s), p.b[j], p.log2b[j], gcur[j], norm, &gn, &bad);
+    e += finalize_column(s, log2f(s), p.b[j], p.log2b[j], __ldcg(gcur + j), norm, &gn, &bad);
     gnext[j] = gn;
   }
   e = warp_sum(e);
@@ -738,31 +746,49 @@ __device__ __noinline__ void sweep_fused_tail(const SweepArgs& p, State* st, int
     sh_last = (t == (int)G - 1);
   }
   __syncthreads();
-  if (!sh_last) return;
-  __threadfence();
-  {
+  if (sh_last) {  // the last CTA folds the error partials in fixed order and advances the state machine
+    __threadfence();
     double part = 0.0;
     for (unsigned i = tid; i < G; i += kLiteThreads) part += ((volatile double*)p.errpart)[i];
     part = warp_sum(part);
     __syncthreads();
     if ((tid & 31) == 0) sh_e[tid >> 5] = part;
     __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kLiteThreads / 32; ++w) tot += sh_e[w];
+      // NaN error (a vanished column sum, a peer that never answered): stop with bad = 1
+      const float err = (norm == B200OT_NORM_L2) ? (float)sqrt(tot) : (float)tot;
+      st->ticket = 0;
+      if (!(tot == tot)) atomicExch(&st->bad, 1);
+      __threadfence();
+      if (((volatile int*)&st->bad)[0]) {
+        st->done = 1;
+      } else {
+        State ls = *st;
+        ls.gbar_count = ((volatile State*)st)->gbar_count;  // the barrier words belong to grid_sync, not to this copy
+        ls.gbar_gen = ((volatile State*)st)->gbar_gen;
+        advance_state(ls, err, false, p.err_hist);
+        // field-wise write-back of what advance_state may change (never the barrier words, which other CTAs
+        // are updating concurrently)
+        st->it = ls.it;
+        st->cur = ls.cur;
+        st->err = ls.err;
+        st->n_err = ls.n_err;
+        st->converged = ls.converged;
+        st->fs_lo[0] = ls.fs_lo[0];
+        st->fs_lo[1] = ls.fs_lo[1];
+        st->fs_hi[0] = ls.fs_hi[0];
+        st->fs_hi[1] = ls.fs_hi[1];
+        st->best_err = ls.best_err;
+        st->stall = ls.stall;
+        st->floor_hit = ls.floor_hit;
+        __threadfence();
+        st->done = ls.done;
+      }
+    }
   }
-  if (tid != 0) return;
-  double tot = 0.0;
-  for (int w = 0; w < kLiteThreads / 32; ++w) tot += sh_e[w];
-  // NaN error (a vanished column sum, a peer that never answered): stop with bad = 1
-  const float err = (norm == B200OT_NORM_L2) ? (float)sqrt(tot) : (float)tot;
-  st->ticket = 0;
-  if (!(tot == tot)) atomicExch(&st->bad, 1);
-  __threadfence();
-  if (((volatile int*)&st->bad)[0]) {
-    st->done = 1;
-    return;
-  }
-  State ls = *st;
-  advance_state(ls, err, false, p.err_hist);
-  *st = ls;
+  grid_sync(st, G);  // the new state (iteration count, current g buffer, done) is visible to every CTA
 }
 
 // =============================================================================
@@ -780,9 +806,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
 
   State* st = p.st;
   if (st->done) return;
-  const int cur = st->cur;
   const float k = st->kscale;
-  const float* __restrict__ gs = cur ? p.gs1 : p.gs0;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -796,29 +820,13 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
   int mvalid = p.m - (int)col0;
   mvalid = mvalid < 0 ? 0 : (mvalid > p.wq ? p.wq : mvalid);
 
-  const int it0 = st->it;
-  const float flo = st->fs_lo[it0 & 1], fhi = st->fs_hi[it0 & 1];
-  const bool uniform = flo <= fhi && (fhi - flo) < 48.f;
-  const float sigma = uniform ? 0.5f * (flo + fhi) : 0.f;
-
   float* stage = reinterpret_cast<float*>(smem);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NG * W * sizeof(float));  // [8]
   uint64_t* xbar = full + 8;                                                            // [kXBuf]
   float* red = reinterpret_cast<float*>(xbar + kXBuf);  // [2][kLiteWarps]
   float* xch = red + 2 * kLiteWarps;                     // [kXBuf][kMaxCluster]
+  unsigned char* tail_scratch = reinterpret_cast<unsigned char*>(xch + kXBuf * kMaxCluster);  // 128 bytes
 
-  float gsv[CPT], acc[CPT];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int col = c * (kLiteThreads * 4) + tid * 4;
-    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col < mvalid) g4 = *reinterpret_cast<const float4*>(gs + col0 + col);
-    gsv[c * 4 + 0] = g4.x + sigma;
-    gsv[c * 4 + 1] = g4.y + sigma;
-    gsv[c * 4 + 2] = g4.z + sigma;
-    gsv[c * 4 + 3] = g4.w + sigma;
-    acc[c * 4 + 0] = acc[c * 4 + 1] = acc[c * 4 + 2] = acc[c * 4 + 3] = 0.f;
-  }
   if (tid == 0) {
     for (int s = 0; s < NG; ++s) mbar_init(smem_u32(full + s), 1);
     for (int s = 0; s < kXBuf; ++s) mbar_init(smem_u32(xbar + s), 1);
@@ -828,15 +836,25 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
   cluster_arrive();
   cluster_wait();
 
+  // One launch runs `iters` iterations when the fused tail is on (persistent form): the rows of this cluster are
+  // the same in every iteration, so the TMA ring simply keeps running across the iteration boundary -- while the
+  // grid folds, exchanges and finalizes, the first rows of the next sweep are already on their way.
+  const int n_it = p.fuse ? (p.iters > 0 ? p.iters : 1) : 1;
   const int cnt = cid < p.n ? (p.n - cid + NC - 1) / NC : 0;  // rows cid, cid + NC, ...
+  const int total_rows = cnt * n_it;  // the host keeps this below 2^30
   const uint64_t pol = p.evict_first ? policy_evict_first() : 0ull;
   const uint32_t row_bytes = (uint32_t)mvalid * 4u;
-  auto issue = [&](int i) {
-    const int s = i % NG;
+  // The two CTAs that share an SM belong to different clusters.  All clusters start together, so their
+  // exponential phases (MUFU-bound) coincide and their exchange phases (SM idle) coincide too; starting every other
+  // cluster half a row period late lets one CTA of an SM compute while the other waits for its cluster.
+  if (p.stagger_ns > 0 && (cid & 1)) __nanosleep((unsigned)p.stagger_ns);
+  // gq: running index of a row over all iterations of the launch (ring slot and phase); irow: its index in the sweep
+  auto issue = [&](int gq, int irow) {
+    const int s = gq % NG;
     const uint32_t bar = smem_u32(full + s);
     mbar_arrive_expect_tx(bar, row_bytes);
     if (row_bytes) {
-      const float* src = p.C + (long long)(cid + i * NC) * p.ldc + col0;
+      const float* src = p.C + (long long)(cid + irow * NC) * p.ldc + col0;
       const uint32_t dst = smem_u32(stage + (size_t)s * W);
       if (p.evict_first)
         bulk_g2s_hint(dst, src, row_bytes, bar, pol);
@@ -844,118 +862,156 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
         bulk_g2s(dst, src, row_bytes, bar);
     }
   };
-  if (tid == 0) {
-    const int pre = cnt < NG ? cnt : NG;
-    for (int i = 0; i < pre; ++i) issue(i);
+  if (tid == 0 && cnt > 0) {
+    const int pre = total_rows < NG ? total_rows : NG;
+    for (int gq = 0; gq < pre; ++gq) issue(gq, gq % cnt);
   }
 
   const bool last_ok = (NCH - 1) * (kLiteThreads * 4) + tid * 4 < mvalid;
   const bool last_any = __any_sync(0xffffffffu, last_ok);
-  float f_lo = INFINITY, f_hi = -INFINITY;
+  int consumed = 0;  // rows of this launch whose ring slot has been drained
 
-  auto row_loop = [&](auto uni_tag) {
-    constexpr bool UNI = decltype(uni_tag)::value;
-    float a_next = cnt > 0 ? p.a[cid] : 0.f;
-    float sh_next = (!UNI && cnt > 0) ? p.fs[cid] : sigma;
-    int qsel = 0;  // CTA of the cluster that writes this row's potential
-    for (int i = 0; i < cnt; ++i) {
-      const int row = cid + i * NC;
-      const int s = i % NG;
-      const float ar = a_next, sh = sh_next;
-      if (i + 1 < cnt) {  // prefetch the next row's scalars so their latency is off the critical path
-        a_next = p.a[row + NC];
-        if (!UNI) sh_next = p.fs[row + NC];
-      }
-      mbar_wait(smem_u32(full + s), (uint32_t)((i / NG) & 1));
-      float t[CPT];
-      const float* srow = stage + (size_t)s * W + tid * 4;
-      auto quad = [&](int c) {
-        const float4 v = *reinterpret_cast<const float4*>(srow + c * (kLiteThreads * 4));
-        if (UNI) {
-          t[c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0]));
-          t[c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1]));
-          t[c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2]));
-          t[c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3]));
-        } else {
-          t[c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + sh));
-          t[c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + sh));
-          t[c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + sh));
-          t[c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + sh));
+  for (int kit = 0; kit < n_it; ++kit) {
+    // ---- per-iteration state (rewritten by the tail of the previous iteration: read it past L1) ----
+    const int cur = ((volatile int*)&st->cur)[0];
+    const int it0 = ((volatile int*)&st->it)[0];
+    const float flo = ((volatile float*)st->fs_lo)[it0 & 1], fhi = ((volatile float*)st->fs_hi)[it0 & 1];
+    const bool uniform = flo <= fhi && (fhi - flo) < 48.f;
+    const float sigma = uniform ? 0.5f * (flo + fhi) : 0.f;
+    const float* gs = cur ? p.gs1 : p.gs0;
+    float gsv[CPT], acc[CPT];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = c * (kLiteThreads * 4) + tid * 4;
+      float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col < mvalid) g4 = __ldcg(reinterpret_cast<const float4*>(gs + col0 + col));
+      gsv[c * 4 + 0] = g4.x + sigma;
+      gsv[c * 4 + 1] = g4.y + sigma;
+      gsv[c * 4 + 2] = g4.z + sigma;
+      gsv[c * 4 + 3] = g4.w + sigma;
+      acc[c * 4 + 0] = acc[c * 4 + 1] = acc[c * 4 + 2] = acc[c * 4 + 3] = 0.f;
+    }
+    float f_lo = INFINITY, f_hi = -INFINITY;
+    const int base = consumed;
+
+    auto row_loop = [&](auto uni_tag) {
+      constexpr bool UNI = decltype(uni_tag)::value;
+      float a_next = cnt > 0 ? p.a[cid] : 0.f;
+      float sh_next = (!UNI && cnt > 0) ? __ldcg(p.fs + cid) : sigma;
+      int qsel = 0;  // CTA of the cluster that writes this row's potential
+      for (int i = 0; i < cnt; ++i) {
+        const int row = cid + i * NC;
+        const int gi = base + i;
+        const int s = gi % NG;
+        const float ar = a_next, sh = sh_next;
+        if (i + 1 < cnt) {  // prefetch the next row's scalars so their latency is off the critical path
+          a_next = p.a[row + NC];
+          if (!UNI) sh_next = __ldcg(p.fs + row + NC);
         }
-      };
-#pragma unroll
-      for (int c = 0; c < NCH - 1; ++c) quad(c);
-      if (last_any) {
-        quad(NCH - 1);
-        if (!last_ok) t[CPT - 4] = t[CPT - 3] = t[CPT - 2] = t[CPT - 1] = 0.f;
-      } else {
-        t[CPT - 4] = t[CPT - 3] = t[CPT - 2] = t[CPT - 1] = 0.f;
-      }
-      float ps = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) ps += (t[c * 4 + 0] + t[c * 4 + 1]) + (t[c * 4 + 2] + t[c * 4 + 3]);
-      ps = warp_sum(ps);
-      const int par = i & 1;
-      if (lane == 0) red[par * kLiteWarps + warp] = ps;
-      __syncthreads();  // ring stage drained by every warp; red[par] complete
-      const int xb = i % kXBuf;
-      // per-row serial chores rotate over warps (and the potential update over the CTAs of the cluster) so that
-      // no warp is systematically the last one at the next block barrier
-      if (lane == 0 && warp == ((i + 4) & (kLiteWarps - 1)) && i + NG < cnt) {
-        fence_proxy_async();
-        issue(i + NG);
-      }
-      if (warp == ((i + 6) & (kLiteWarps - 1))) {  // the row-sum exchange rotates too
-        if (lane == 0) mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
-        if (lane < Q) {
-          float v = 0.f;
-#pragma unroll
-          for (int w = 0; w < kLiteWarps; ++w) v += red[par * kLiteWarps + w];
-          st_async_f32(map_to_cta(smem_u32(xch + xb * kMaxCluster + q), (uint32_t)lane), v,
-                       map_to_cta(smem_u32(xbar + xb), (uint32_t)lane));
-        }
-      }
-      mbar_wait(smem_u32(xbar + xb), (uint32_t)((i / kXBuf) & 1));
-      float rt = 0.f;
-#pragma unroll
-      for (int qq = 0; qq < kMaxCluster; ++qq)
-        if (qq < Q) rt += xch[xb * kMaxCluster + qq];
-      const bool live = ar > 0.f;
-      const float w = live ? __fdividef(ar, rt) : 0.f;
-      if (q == qsel && lane == 0 && warp == ((i + 2) & (kLiteWarps - 1))) {
-        const float fnew = live ? sh + (log2f(ar) - log2f(rt)) : -INFINITY;
-        p.fs[row] = fnew;
-        if (live) {
-          if (fabsf(fnew) < INFINITY) {
-            f_lo = fminf(f_lo, fnew);
-            f_hi = fmaxf(f_hi, fnew);
+        mbar_wait(smem_u32(full + s), (uint32_t)((gi / NG) & 1));
+        float t[CPT];
+        const float* srow = stage + (size_t)s * W + tid * 4;
+        auto quad = [&](int c) {
+          const float4 v = *reinterpret_cast<const float4*>(srow + c * (kLiteThreads * 4));
+          if (UNI) {
+            t[c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0]));
+            t[c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1]));
+            t[c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2]));
+            t[c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3]));
           } else {
-            atomicExch(&st->bad, 1);
+            t[c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + sh));
+            t[c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + sh));
+            t[c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + sh));
+            t[c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + sh));
+          }
+        };
+#pragma unroll
+        for (int c = 0; c < NCH - 1; ++c) quad(c);
+        if (last_any) {
+          quad(NCH - 1);
+          if (!last_ok) t[CPT - 4] = t[CPT - 3] = t[CPT - 2] = t[CPT - 1] = 0.f;
+        } else {
+          t[CPT - 4] = t[CPT - 3] = t[CPT - 2] = t[CPT - 1] = 0.f;
+        }
+        float ps = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) ps += (t[c * 4 + 0] + t[c * 4 + 1]) + (t[c * 4 + 2] + t[c * 4 + 3]);
+        ps = warp_sum(ps);
+        const int par = gi & 1;
+        if (lane == 0) red[par * kLiteWarps + warp] = ps;
+        __syncthreads();  // ring stage drained by every warp; red[par] complete
+        const int xb = gi % kXBuf;
+        // per-row serial chores rotate over warps (and the potential update over the CTAs of the cluster) so that
+        // no warp is systematically the last one at the next block barrier
+        if (lane == 0 && warp == ((i + 4) & (kLiteWarps - 1)) && gi + NG < total_rows) {
+          int inext = i + NG;  // the slot just drained takes the row NG ahead -- of the NEXT sweep past the end
+          while (inext >= cnt) inext -= cnt;
+          fence_proxy_async();
+          issue(gi + NG, inext);
+        }
+        if (warp == ((i + 6) & (kLiteWarps - 1))) {  // the row-sum exchange rotates too
+          if (lane == 0) mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
+          if (lane < Q) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLiteWarps; ++w) v += red[par * kLiteWarps + w];
+            st_async_f32(map_to_cta(smem_u32(xch + xb * kMaxCluster + q), (uint32_t)lane), v,
+                         map_to_cta(smem_u32(xbar + xb), (uint32_t)lane));
           }
         }
+        mbar_wait(smem_u32(xbar + xb), (uint32_t)((gi / kXBuf) & 1));
+        float rt = 0.f;
+#pragma unroll
+        for (int qq = 0; qq < kMaxCluster; ++qq)
+          if (qq < Q) rt += xch[xb * kMaxCluster + qq];
+        const bool live = ar > 0.f;
+        const float w = live ? __fdividef(ar, rt) : 0.f;
+        if (q == qsel && lane == 0 && warp == ((i + 2) & (kLiteWarps - 1))) {
+          const float fnew = live ? sh + (log2f(ar) - log2f(rt)) : -INFINITY;
+          p.fs[row] = fnew;
+          if (live) {
+            if (fabsf(fnew) < INFINITY) {
+              f_lo = fminf(f_lo, fnew);
+              f_hi = fmaxf(f_hi, fnew);
+            } else {
+              atomicExch(&st->bad, 1);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[c], w, acc[c]);
+        qsel = (qsel + 1 == Q) ? 0 : qsel + 1;
       }
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[c], w, acc[c]);
-      qsel = (qsel + 1 == Q) ? 0 : qsel + 1;
-    }
-  };
-  if (uniform)
-    row_loop(std::true_type{});
-  else
-    row_loop(std::false_type{});
+    };
+    if (uniform)
+      row_loop(std::true_type{});
+    else
+      row_loop(std::false_type{});
+    consumed += cnt;
 
-  if (lane == 0 && f_lo <= f_hi) {  // every thread that wrote potentials
-    atomic_min_float(&st->fs_lo[(it0 + 1) & 1], f_lo);
-    atomic_max_float(&st->fs_hi[(it0 + 1) & 1], f_hi);
-  }
+    if (lane == 0 && f_lo <= f_hi) {  // every thread that wrote potentials
+      atomic_min_float(&st->fs_lo[(it0 + 1) & 1], f_lo);
+      atomic_max_float(&st->fs_hi[(it0 + 1) & 1], f_hi);
+    }
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int col = c * (kLiteThreads * 4) + tid * 4;
-    if (col < mvalid)
-      *reinterpret_cast<float4*>(p.part + (size_t)cid * p.stride + col0 + col) =
-          make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
+    for (int c = 0; c < NCH; ++c) {
+      const int col = c * (kLiteThreads * 4) + tid * 4;
+      if (col < mvalid)
+        *reinterpret_cast<float4*>(p.part + (size_t)cid * p.stride + col0 + col) =
+            make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
+    }
+    if (!p.fuse) break;
+    sweep_fused_tail(p, st, cur, it0, NC, tail_scratch);
+    if (((volatile int*)&st->done)[0]) break;  // grid-uniform: read after the tail's closing grid barrier
   }
-  if (p.fuse) sweep_fused_tail(p, st, cur, it0, NC, smem);  // every row of the ring has been consumed
+
+  // rows of sweeps that will not run (the stopping rule fired inside the launch) are still in flight: a CTA must
+  // not retire with bulk copies outstanding into its shared memory
+  if (cnt > 0) {
+    int issued = consumed + NG;
+    issued = issued > total_rows ? total_rows : issued;
+    for (int gq = consumed; gq < issued; ++gq) mbar_wait(smem_u32(full + gq % NG), (uint32_t)((gq / NG) & 1));
+  }
   cluster_arrive();
   cluster_wait();
 }
@@ -1514,9 +1570,14 @@ static bool fuse_wanted() {
   return want == 1 && !g_fuse_broken;
 }
 
+// One sweep (plain form), or -- with a FuseCtx, when the lite kernel applies -- `iters` whole iterations in ONE
+// persistent cooperative launch (*fused_out = true).  When the fused form is not available the call launches the
+// plain sweep of ONE iteration and the caller finishes it (finalize / exchange) and loops.
 static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtrs& w, int* np_out,
-                              cudaStream_t s, const FuseCtx* fc = nullptr, bool* fused_out = nullptr) {
+                              cudaStream_t s, const FuseCtx* fc = nullptr, bool* fused_out = nullptr, int iters = 1,
+                              int* iters_queued = nullptr) {
   if (fused_out) *fused_out = false;
+  if (iters_queued) *iters_queued = 1;
   // B200OT_FUSED_VARIANT: "lite" = 256-thread CTAs, two per SM; "pipe" = 512-thread software-pipelined
   static int variant = -1;
   if (variant < 0) {
@@ -1546,10 +1607,26 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
   const char* em = getenv("B200OT_FUSED_MODE");
   a.mode = em ? atoi(em) : 0;
   a.fuse = 0;
+  a.iters = 1;
+  {
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* es = getenv("B200OT_STAGGER");
+      stagger = es ? atoi(es) : 0;
+      if (stagger < 0) stagger = 0;
+    }
+    a.stagger_ns = stagger;
+  }
   cudaError_t e = cudaSuccess;
   if (lite && cfg.R == 1 && cfg.smem <= kLiteSmemMax && cfg.NCH <= kLiteMaxNch && cfg.wq <= 1024 * cfg.NCH) {
     if (fc && fused_out && fuse_wanted() && a.mode == 0) {
       a.fuse = 1;
+      a.iters = iters > 0 ? iters : 1;
+      {  // the kernel counts the rows of a launch in 32 bits
+        const int rows_per_cluster = (n + cfg.NC - 1) / cfg.NC;
+        const int cap = (1 << 30) / (rows_per_cluster > 0 ? rows_per_cluster : 1);
+        if (a.iters > cap) a.iters = cap > 0 ? cap : 1;
+      }
       a.gs0w = w.gs0;
       a.gs1w = w.gs1;
       a.b = w.b;
@@ -1564,13 +1641,15 @@ static int launch_sweep_fused(const float* C, int ldc, int n, int m, const WsPtr
       e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
       if (e == cudaSuccess) {
         *fused_out = true;
-        ++g_fused_launches;
+        g_fused_launches += a.iters;
+        if (iters_queued) *iters_queued = a.iters;
       } else {  // e.g. cooperative + cluster launch refused: fall back to separate launches, for good
         set_last_cuda_error(e, "fused-iteration launch (cooperative cluster launch)");
         (void)cudaGetLastError();
         g_fuse_broken = true;
         ++g_fused_fallbacks;
         a.fuse = 0;
+        a.iters = 1;
         e = lite_dispatch(cfg.NCH, &a, cfg.Q, cfg.NC, cfg.smem, s, nullptr);
       }
     } else {
@@ -1742,9 +1821,15 @@ int b200ot_sinkhorn_enqueue(const float* C, int ldc, int n, int m, int iters, in
     int np = 0;
     if (path == B200OT_PATH_FUSED) {
       bool fused = false;
-      rc = launch_sweep_fused(C, ldc, n, m, w, &np, s, &solo, &fused);
+      // first try: all remaining iterations as ONE persistent launch (sweeps, folds, finalizes, stopping rule)
+      int queued = 1;
+      rc = launch_sweep_fused(C, ldc, n, m, w, &np, s, fuse_wanted() ? &solo : nullptr, &fused, iters - i, &queued);
       if (rc) return rc;
-      if (!fused) rc = launch_finalize(m, w, w.part_sum, nullptr, np, w.m_pad, 0, s);
+      if (fused) {
+        i += queued - 1;
+        continue;
+      }
+      rc = launch_finalize(m, w, w.part_sum, nullptr, np, w.m_pad, 0, s);
     } else {
       rc = launch_rowpass(C, ldc, n, m, w, s);
       if (rc) return rc;
@@ -2050,11 +2135,17 @@ int b200ot_sinkhorn_shard_run_peer(const float* C, int ldc, int n_local, int m, 
   for (int i = 0; i < iters; ++i) {
     bool fused = false;
     if (can_fuse && !g_fuse_broken) {
-      // ONE launch per iteration: sweep + fold + push to the peers + poll + finalize + state machine
+      // ONE persistent launch for all `iters` iterations: sweep + fold + push to the peers + poll + finalize + state
+      // machine, the TMA ring running across the iteration boundaries
       int np = 0;
-      rc = launch_sweep_fused(C, ldc, n_local, m, w, &np, s, &fc, &fused);
+      int queued = 1;
+      rc = launch_sweep_fused(C, ldc, n_local, m, w, &np, s, &fc, &fused, iters - i, &queued);
       if (rc) return rc;
-      if (!fused) {  // the pipelined kernel ran instead (no fused tail): finish the iteration the unfused way
+      if (fused) {
+        i += queued - 1;
+        continue;
+      }
+      {  // the plain sweep of one iteration ran instead (no fused tail): finish it the unfused way
         PeerPtrs pp = fc.peers;
         reduce_push_kernel<<<(m + 255) / 256, 256, 0, s>>>(w.st, w.part_sum, nullptr, np, w.m_pad, m, pp, world, rank,
                                                            fc.xstride, fc.epoch, 0);

@@ -21,5 +21,5 @@ python bench.py --steps 1 --warmup 3 --iters 20 --no-cpu --e2e-steps 1 --no-extr
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches_bench_iters20.csv python bench.py --steps 1 --warmup 3 --iters 20 --no-cpu --e2e-steps 1 --no-extras --no-parity > $O/r2_ncu5.log 2>&1
 # 6. fused sweep, full set
 python bench.py --steps 1 --warmup 3 --iters 20 --no-cpu --e2e-steps 1 --no-extras --no-parity --graph 0 > $O/r2_plain6.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:sweep_lite_kernel -s 30 -c 2 -o $O/r02_sweep_fused python bench.py --steps 1 --warmup 3 --iters 20 --no-cpu --e2e-steps 1 --no-extras --no-parity --graph 0 > $O/r2_ncu6.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:sweep_lite_kernel -s 2 -c 1 -o $O/r02_sweep_fused python bench.py --steps 1 --warmup 3 --iters 20 --no-cpu --e2e-steps 1 --no-extras --no-parity --graph 0 > $O/r2_ncu6.log 2>&1
 tail -2 $O/r2_ncu*.log
