@@ -624,16 +624,23 @@ def run_b200(args):
         if world > 1:
             _shutdown(dist)
         return
-    from b200ot import _lib as _b200ot_lib
-    lib_counter = _b200ot_lib.load().b200ot_sinkhorn_counter
     peak, peak_src = _peaks()
     alg_bytes = 4.0 * n_loc * m  # one fp32 read of this rank's rows of C per iteration
     per_iter_s = ms_per_step * 1e-3 / iters
     achieved = alg_bytes / per_iter_s / 1e9
     # our kernels per step: init (init_state, init, colpass, finalize) + snapshot per enqueue + 2 per iteration;
     # sharded: setup (2) + prologue (colpass, reduce_parts) + finalize, then sweep + reduce_parts + finalize per iteration
+    from b200ot import _lib as _b200ot_lib
+    lib_counter = _b200ot_lib.load().b200ot_sinkhorn_counter
     n_enq = (iters // args.graph + (1 if iters % args.graph else 0)) if args.graph else 1
-    launches_per_step = (4 + n_enq + 2 * iters) if world == 1 else (5 + 3 * iters)  # peer loop: sweep, reduce+push, finalize
+    fused_form = lib_counter(0) > 0 and lib_counter(1) == 0 and (world == 1 or args.loop == "peer")
+    if fused_form:
+        # persistent fused kernel: N = 1: init (4) + per graph replay / enqueue a snapshot and ONE launch that runs its
+        # iterations; N > 1: setup (2) + first g update (3) + one launch per host window of 10 iterations
+        win = int(os.environ.get("B200OT_SHARD_WINDOW", "10"))
+        launches_per_step = (4 + 2 * n_enq) if world == 1 else (5 + (iters + win - 1) // win)
+    else:
+        launches_per_step = (4 + n_enq + 2 * iters) if world == 1 else (5 + 3 * iters)  # sweep, (reduce+push,) finalize
     if resident:
         launches_per_step = 4 + 1 + 1  # init, snapshot, one resident launch for all iterations
     c_bytes = 4.0 * n_loc * m
@@ -650,7 +657,10 @@ def run_b200(args):
                                f"(BASELINE configs[3]; single-sweep fused kernel, C resident in HBM)",
                    "n": n, "m": m, "d": D, "eps": EPS, "iterations_per_step": iters, "path": args.path,
                    "rows_per_gpu": n_loc, "kernel": kernel_desc,
-                   "launch": ("one persistent launch per solve" if resident else f"CUDA graph, {args.graph} iterations per replay" if args.graph else "eager launches")
+                   "launch": ("one persistent launch per solve" if resident else
+                              (f"CUDA graph, {args.graph} iterations per replay" if args.graph else "eager launches") +
+                              (", each replay = snapshot + ONE persistent cooperative cluster launch (sweep, fold, finalize and "
+                               "stopping rule of all its iterations)" if fused_form else ""))
                    if world == 1 else f"loop={args.loop}", "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
                    "l2": l2_note},
         "hbm_gbs": achieved * world,

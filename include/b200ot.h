@@ -295,6 +295,21 @@ int b200ot_envelope_bwd(const float* C, int ldc, int n, int m, const float* f, c
                         const float* X, int ldx, const float* Y, int ldy, int d, float scale, float* dX, int lddx,
                         float* dY, int lddy, float* rowsum_out, float* colsum_out, void* ws, size_t ws_bytes,
                         void* stream);
+/* Weighted forms of the two calls above: the contracted entries are W_ij = P_ij (w0 + w1 C_ij + wrow_i + wcol_j)
+ * (wrow: n values over the rows of C, wcol: m values over its columns, either may be NULL) instead of P_ij, and
+ * the row sums are those of W.  (w0, w1) = (0, 1) gives the C-weighted products (P o C) V; with
+ * w0 = 1, w1 = -1/eps, wrow = lambda/eps, wcol = mu/eps, where H (lambda, mu) = ((P o C) 1, (P o C)^T 1) and
+ * H = [[diag(P1), P], [P^T, diag(P^T 1)]], W is d<P, C>/dC THROUGH the Sinkhorn fixed point, so
+ * envelope_bwd_weighted returns the implicit-function-theorem gradient of the transport cost with respect to the
+ * embeddings (b200ot.torch_ops.ot_loss(value="primal", grad="implicit")).  Workspaces as for the unweighted calls. */
+int b200ot_apply_plan_tc_weighted(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                                  float w0, float w1, const float* wrow, const float* wcol, const float* V, int ldv,
+                                  int dv, int transpose, float* Z, int ldz, float* rowsum_out, void* ws,
+                                  size_t ws_bytes, void* stream);
+int b200ot_envelope_bwd_weighted(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                                 float w0, float w1, const float* wrow, const float* wcol, const float* X, int ldx,
+                                 const float* Y, int ldy, int d, float scale, float* dX, int lddx, float* dY, int lddy,
+                                 void* ws, size_t ws_bytes, void* stream);
 /* fused fusion loss of the reference forward: 1 - mean_i cos(A_i, B_i)
  * (MRI_PET_OT_nojax.py:552-560); out is one float.                                  */
 int b200ot_cosine_loss(const float* A, int lda, const float* B, int ldb, int rows, int d,

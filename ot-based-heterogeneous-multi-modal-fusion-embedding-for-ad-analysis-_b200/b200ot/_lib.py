@@ -96,6 +96,10 @@ SIGNATURES = {
     "b200ot_apply_plan_t": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _i, _i, _p, _i, _p]),
     "b200ot_apply_plan_tc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b200ot_apply_plan_tc": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p]),
+    "b200ot_apply_plan_tc_weighted": (_i, [_p, _i, _i, _i, _p, _p, _f, _f, _f, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p,
+                                           _sz, _p]),
+    "b200ot_envelope_bwd_weighted": (_i, [_p, _i, _i, _i, _p, _p, _f, _f, _f, _p, _p, _p, _i, _p, _i, _i, _f, _p, _i,
+                                          _p, _i, _p, _sz, _p]),
     "b200ot_envelope_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "b200ot_envelope_bwd": (_i, [_p, _i, _i, _i, _p, _p, _f, _p, _i, _p, _i, _i, _f, _p, _i, _p, _i, _p, _p, _p, _sz, _p]),
     "b200ot_cosine_loss": (_i, [_p, _i, _p, _i, _i, _i, _p, _p]),

@@ -458,12 +458,16 @@ def _apply_wants_tc(n: int, m: int, dv: int) -> bool:
 
 
 @on_device
-def apply_plan(Cm, f, g, eps, V, normalise=False, transpose=False, impl="auto", return_rowsum=False):
+def apply_plan(Cm, f, g, eps, V, normalise=False, transpose=False, impl="auto", return_rowsum=False, weights=None):
     """Z = P V (or P^T V with transpose=True), optionally row-normalised, without forming P.
 
     impl="tc": single-pass tcgen05 kernel (b200ot_apply_plan_tc; dv is processed in slabs of 512 columns);
     impl="simt": the generic fp32 kernel (any shape / alignment); "auto" picks by size.  With
-    ``return_rowsum`` the row sums of P (P^T when transposed) come back as well."""
+    ``return_rowsum`` the row sums of P (P^T when transposed) come back as well.
+
+    ``weights=(w0, w1, wrow, wcol)``: contract with ``W_ij = P_ij (w0 + w1 C_ij + wrow_i + wcol_j)`` instead of P
+    (tensor-core kernel only; ``wrow`` over the rows of C, ``wcol`` over its columns, either may be None): the
+    C-weighted products and the implicit-gradient weights of ``torch_ops.ot_loss(grad="implicit")``."""
     lib = _lib.load()
     Cm, ldc = _matrix(Cm, "C")
     n, m = Cm.shape
@@ -475,7 +479,25 @@ def apply_plan(Cm, f, g, eps, V, normalise=False, transpose=False, impl="auto", 
     fv, gv = _vector(f, "f", n), _vector(g, "g", m)
     Z = torch.empty((rows_out, dv), dtype=torch.float32, device=Cm.device)
     if impl == "auto":
-        impl = "tc" if _apply_wants_tc(n, m, dv) else "simt"
+        impl = "tc" if (_apply_wants_tc(n, m, dv) or weights is not None) else "simt"
+    if weights is not None:
+        if impl != "tc" or normalise:
+            raise B200OTError("weighted plan products run on the tensor-core kernel, without normalisation")
+        w0, w1, wrow, wcol = weights
+        wrow = None if wrow is None else _vector(wrow, "wrow", n)
+        wcol = None if wcol is None else _vector(wcol, "wcol", m)
+        rs = torch.empty(rows_out, dtype=torch.float32, device=Cm.device) if return_rowsum else None
+        for c0 in range(0, dv, _TC_MAX_DV):
+            dvc = min(_TC_MAX_DV, dv - c0)
+            need = lib.b200ot_apply_plan_tc_workspace_bytes(n, m, dvc, int(bool(transpose)))
+            buf, wsp = _tc_ws(need, Cm.device)
+            Vc, Zc = V[:, c0:c0 + dvc], Z[:, c0:c0 + dvc]
+            check(lib.b200ot_apply_plan_tc_weighted(_ptr(Cm), ldc, n, m, _ptr(fv), _ptr(gv), float(eps), float(w0),
+                                                    float(w1), _ptr(wrow), _ptr(wcol), _ptr(Vc), ldv, dvc,
+                                                    int(bool(transpose)), _ptr(Zc), Z.stride(0),
+                                                    _ptr(rs) if c0 == 0 else None, wsp, need, _stream()),
+                  "b200ot_apply_plan_tc_weighted")
+        return (Z, rs) if return_rowsum else Z
     if impl == "tc":
         rs = torch.empty(rows_out, dtype=torch.float32, device=Cm.device) if return_rowsum else None
         for c0 in range(0, dv, _TC_MAX_DV):
@@ -503,7 +525,7 @@ def apply_plan(Cm, f, g, eps, V, normalise=False, transpose=False, impl="auto", 
 
 
 @on_device
-def envelope_bwd(Cm, f, g, eps, x, y, scale: float = 2.0, impl="auto"):
+def envelope_bwd(Cm, f, g, eps, x, y, scale: float = 2.0, impl="auto", weights=None):
     """dX = scale (diag(P1) x - P y), dY = scale (diag(P^T 1) y - P^T x): the gradient of <P, C(x, y)> for the
     squared-Euclidean cost with the plan held fixed.  impl="tc": both halves in ONE launch of the tcgen05 kernel
     (b200ot_envelope_bwd); "simt": two plan-free products on the generic kernel."""
@@ -517,12 +539,23 @@ def envelope_bwd(Cm, f, g, eps, x, y, scale: float = 2.0, impl="auto"):
         raise B200OTError("envelope_bwd: x must be n x d and y m x d")
     fv, gv = _vector(f, "f", n), _vector(g, "g", m)
     if impl == "auto":
-        impl = "tc" if (_apply_wants_tc(n, m, d) and d <= _TC_MAX_DV) else "simt"
+        impl = "tc" if ((_apply_wants_tc(n, m, d) or weights is not None) and d <= _TC_MAX_DV) else "simt"
+    if weights is not None and impl != "tc":
+        raise B200OTError("the weighted (implicit) gradient runs on the tensor-core kernel (d <= 512)")
     if impl == "tc":
         dx = torch.empty((n, d), dtype=torch.float32, device=Cm.device)
         dy = torch.empty((m, d), dtype=torch.float32, device=Cm.device)
         need = lib.b200ot_envelope_bwd_workspace_bytes(n, m, d)
         buf, wsp = _tc_ws(need, Cm.device)
+        if weights is not None:
+            w0, w1, wrow, wcol = weights
+            wrow = None if wrow is None else _vector(wrow, "wrow", n)
+            wcol = None if wcol is None else _vector(wcol, "wcol", m)
+            check(lib.b200ot_envelope_bwd_weighted(_ptr(Cm), ldc, n, m, _ptr(fv), _ptr(gv), float(eps), float(w0),
+                                                   float(w1), _ptr(wrow), _ptr(wcol), _ptr(x), ldx, _ptr(y), ldy, d,
+                                                   float(scale), _ptr(dx), d, _ptr(dy), d, wsp, need, _stream()),
+                  "b200ot_envelope_bwd_weighted")
+            return dx, dy
         check(lib.b200ot_envelope_bwd(_ptr(Cm), ldc, n, m, _ptr(fv), _ptr(gv), float(eps), _ptr(x), ldx, _ptr(y), ldy,
                                       d, float(scale), _ptr(dx), d, _ptr(dy), d, None, None, wsp, need, _stream()),
               "b200ot_envelope_bwd")

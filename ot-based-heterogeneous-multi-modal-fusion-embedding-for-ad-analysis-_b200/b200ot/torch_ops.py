@@ -86,6 +86,57 @@ def _(C, f, g, eps, x, y):
     return torch.empty_like(x), torch.empty_like(y)
 
 
+def implicit_weights(C: Tensor, f: Tensor, g: Tensor, eps: float, tol: float = 1e-6, max_cg: int = 200):
+    """Adjoint of the Sinkhorn fixed point for the transport cost L = <P, C> (implicit function theorem).
+
+    With P = exp((f (+) g - C)/eps), r = (P o C) 1, c = (P o C)^T 1 and H = [[diag(P1), P], [P^T, diag(P^T 1)]]
+    (positive semi-definite, null space (1, -1)), H (lambda, mu) = (r, c) gives
+    dL/dC = P o (1 - C/eps + (lambda (+) mu)/eps).  The system is solved on its Schur complement
+    S mu = c - P^T (r / P1), S = diag(P^T 1) - P^T diag(1/P1) P, by conjugate gradients; every product with P or P^T
+    is one plan-free pass over C (b200ot_apply_plan / _t), the C-weighted marginals come from the weighted
+    tensor-core kernel.  Returns (w0, w1, wrow, wcol) for ops.envelope_bwd(weights=...) and the CG iteration count.
+    Exact only at a converged plan (P1 = a, P^T 1 = b); fp32 products bound the accuracy of the gradient to ~1e-3."""
+    n, m = C.shape
+    ones_m = torch.ones((m, 1), dtype=torch.float32, device=C.device)
+    ones_n = torch.ones((n, 1), dtype=torch.float32, device=C.device)
+    _, r = ops.apply_plan(C, f, g, eps, ones_m, return_rowsum=True, weights=(0.0, 1.0, None, None))
+    _, c = ops.apply_plan(C, f, g, eps, ones_n, transpose=True, return_rowsum=True, weights=(0.0, 1.0, None, None))
+    pa = ops.apply_plan(C, f, g, eps, ones_m, impl="simt").reshape(-1)                  # P 1
+    pb = ops.apply_plan(C, f, g, eps, ones_n, transpose=True, impl="simt").reshape(-1)  # P^T 1
+    pa_safe = torch.where(pa > 0, pa, torch.ones_like(pa))
+
+    def Pv(v):
+        return ops.apply_plan(C, f, g, eps, v.reshape(-1, 1).contiguous(), impl="simt").reshape(-1)
+
+    def Ptv(u):
+        return ops.apply_plan(C, f, g, eps, u.reshape(-1, 1).contiguous(), transpose=True, impl="simt").reshape(-1)
+
+    def S(v):
+        return pb * v - Ptv(Pv(v) / pa_safe)
+
+    rhs = (c - Ptv(r / pa_safe)).double()
+    rhs = rhs - rhs.mean()          # consistent right-hand side: orthogonal to the null space (constants)
+    mu = torch.zeros(m, dtype=torch.float64, device=C.device)
+    res = rhs.clone()
+    d = res.clone()
+    rr = float(res @ res)
+    rr0 = rr
+    it = 0
+    while it < max_cg and rr > (tol * tol) * rr0 and rr0 > 0:
+        Sd = S(d.float()).double()
+        Sd = Sd - Sd.mean()
+        alpha = rr / float(d @ Sd)
+        mu = mu + alpha * d
+        res = res - alpha * Sd
+        rr_new = float(res @ res)
+        d = res + (rr_new / rr) * d
+        rr = rr_new
+        it += 1
+    mu = mu.float()
+    lam = (r - Pv(mu)) / pa_safe
+    return (1.0, -1.0 / eps, lam / eps, mu / eps), it
+
+
 class OTLoss(torch.autograd.Function):
     """Entropic OT value between two embedding clouds (squared-Euclidean cost).
 
@@ -96,13 +147,15 @@ class OTLoss(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, y, a, b, eps, max_iter, tol, value):
+    def forward(ctx, x, y, a, b, eps, max_iter, tol, value, grad="envelope"):
+        ctx.implicit = (grad == "implicit")
         xd, yd = x.detach().float().contiguous(), y.detach().float().contiguous()
         C = ops.cost_matrix(xd, yd)
         f, g, info = ops.sinkhorn_potentials(C, a, b, eps, max_iter=max_iter, tol=tol)
         ctx.save_for_backward(C, f, g, xd, yd)
         ctx.eps = eps
         ctx.info = info
+        ctx.x_dtype, ctx.y_dtype = x.dtype, y.dtype
         if value == "dual":
             out = (a * f).sum() + (b * g).sum()
         else:
@@ -112,18 +165,38 @@ class OTLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         C, f, g, xd, yd = ctx.saved_tensors
-        dx, dy = torch.ops.b200ot.sinkhorn_bwd_envelope(C, f, g, ctx.eps, xd, yd)
-        return grad_out * dx, grad_out * dy, None, None, None, None, None, None
+        if ctx.implicit:
+            w, ctx.cg_iterations = implicit_weights(C, f, g, ctx.eps)
+            dx, dy = ops.envelope_bwd(C, f, g, ctx.eps, xd, yd, scale=2.0, weights=w)
+        else:
+            dx, dy = torch.ops.b200ot.sinkhorn_bwd_envelope(C, f, g, ctx.eps, xd, yd)
+        return ((grad_out * dx).to(ctx.x_dtype), (grad_out * dy).to(ctx.y_dtype), None, None, None, None, None,
+                None, None)
 
 
 def ot_loss(x: Tensor, y: Tensor, a: Tensor = None, b: Tensor = None, eps: float = 0.05, max_iter: int = 1000,
-            tol: float = 1e-6, value: str = "primal") -> Tensor:
+            tol: float = 1e-6, value: str = "dual", grad: str = "envelope") -> Tensor:
+    """Entropic OT value between two embedding clouds with its envelope gradient.
+
+    ``value="dual"`` (default): ``<a, f> + <b, g>``, the regularised OT value up to a constant -- the quantity
+    whose exact gradient the envelope theorem gives (P held at the optimum).  ``value="primal"``: the transport
+    cost ``<P, C>`` (perturbot/perturbot/match/fot.py:137); its backward is the same fixed-plan gradient, i.e. a
+    stop-gradient approximation that ignores dP/dx (the entropy term's contribution).  Gradients come back in
+    the dtype of the inputs.  ``grad="implicit"`` (with ``value="primal"``): the gradient of ``<P, C>`` THROUGH
+    the Sinkhorn fixed point by the implicit function theorem (``implicit_weights``: a conjugate-gradient solve
+    whose matrix-vector products are plan-free passes over C, then one weighted launch of the tcgen05
+    plan-application kernel for both embeddings); needs a converged solve."""
+    if grad not in ("envelope", "implicit"):
+        raise ValueError("grad must be 'envelope' or 'implicit'")
+    if grad == "implicit" and value != "primal":
+        raise ValueError("grad='implicit' differentiates the transport cost: use value='primal' "
+                         "(for value='dual' the envelope gradient is already exact)")
     n, m = x.shape[0], y.shape[0]
     if a is None:
         a = torch.full((n,), 1.0 / n, dtype=torch.float32, device=x.device)
     if b is None:
         b = torch.full((m,), 1.0 / m, dtype=torch.float32, device=x.device)
-    return OTLoss.apply(x, y, a, b, float(eps), int(max_iter), float(tol), value)
+    return OTLoss.apply(x, y, a, b, float(eps), int(max_iter), float(tol), value, grad)
 
 
 class ApplyPlan(torch.autograd.Function):

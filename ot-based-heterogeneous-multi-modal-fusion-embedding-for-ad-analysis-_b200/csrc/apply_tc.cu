@@ -63,6 +63,12 @@ struct ApplySub {
   int S, kb_per_split, nblocks;
   int mode;             // 0 raw, 1 divide by the row sum (0 -> 1e-30), 2 envelope form
   float scale;
+  // weighted plan (implicit differentiation, C-weighted products): the contracted entries are
+  // W = P * (w0 + w1 * C + wrow[output row] + wk[contracted index]) instead of P; row sums are those of W
+  int weighted;
+  float w0, w1;
+  const float* wrow;    // per output row (may be null)
+  const float* wk;      // per contracted index (may be null)
   int vec;              // 16-byte loads along the rows of C are legal
 };
 
@@ -293,6 +299,8 @@ __global__ void __launch_bounds__(AP_THREADS, 1) apply_tc_kernel(const __grid_co
         const bool okA = rowA < sp.rows, okB = rowB < sp.rows;
         const float fA = okA ? sp.frow[rowA] * k : 0.f;
         const float fB = okB ? sp.frow[rowB] * k : 0.f;
+        const float wA = (sp.weighted && sp.wrow && okA) ? sp.wrow[rowA] : 0.f;
+        const float wB = (sp.weighted && sp.wrow && okB) ? sp.wrow[rowB] : 0.f;
         const float* cA = sp.C + (okA ? rowA : (long long)sp.rows - 1) * sp.ldc;
         const float* cB = sp.C + (okB ? rowB : (long long)sp.rows - 1) * sp.ldc;
         float rsA = 0.f, rsB = 0.f;
@@ -332,6 +340,18 @@ __global__ void __launch_bounds__(AP_THREADS, 1) apply_tc_kernel(const __grid_co
             const float gs = gv[e] * k;
             pa[e] = okA ? ex2_approx(fmaf(cAv[e], -k, gs + fA)) : 0.f;
             pb[e] = okB ? ex2_approx(fmaf(cBv[e], -k, gs + fB)) : 0.f;
+          }
+          if (sp.weighted) {  // CTA-uniform
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int j = kb * AP_KC + kc * 4 + (e & 3) + (e >> 2) * 16;
+              const float wj = (sp.wk && j < sp.kdim) ? __ldg(sp.wk + j) : 0.f;
+              pa[e] *= fmaf(sp.w1, cAv[e], sp.w0 + wA + wj);
+              pb[e] *= fmaf(sp.w1, cBv[e], sp.w0 + wB + wj);
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
             rsA += pa[e];
             rsB += pb[e];
           }
@@ -376,10 +396,13 @@ __global__ void __launch_bounds__(AP_THREADS, 1) apply_tc_kernel(const __grid_co
         // Transposed (Z = P^T U): output rows are columns j of C, the contraction runs over rows i.  The plan
         // tile is written MN-major (8 consecutive j of one row i form a 16-byte unit; unit (jg, i) at
         // jg * 512 + (i / 8) * 128 + (i % 8) * 16), so the loads stay coalesced along the rows of C exactly as
-        // in the forward form.  lane = (i % 8, 8-byte half of the unit, low bit of the K group).
-        const int i8 = lane & 7, half = (lane >> 3) & 1, kgbit = lane >> 4;
+        // in the forward form.
+        // lane = (8-byte half of the unit, i % 8, low bit of the K group): consecutive lanes store consecutive
+        // addresses (ncu: the (i % 8, half, K group) order cost 7.9 M shared-store bank conflicts per launch at
+        // 16384^2, this order 1.4 M in the forward form)
+        const int half = lane & 1, i8 = (lane >> 1) & 7, kgbit = lane >> 4;
         const long long jb = (long long)rb * AP_BM;
-        float gJ[2][4], rs[2][4];
+        float gJ[2][4], rs[2][4], wJ[2][4];
         bool vecok[2];
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
@@ -388,6 +411,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) apply_tc_kernel(const __grid_co
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             gJ[jj][e] = (j0 + e < sp.rows) ? sp.frow[j0 + e] * k : -INFINITY;  // no mass beyond the last column
+            wJ[jj][e] = (sp.weighted && sp.wrow && j0 + e < sp.rows) ? sp.wrow[j0 + e] : 0.f;
             rs[jj][e] = 0.f;
           }
         }
@@ -427,7 +451,12 @@ __global__ void __launch_bounds__(AP_THREADS, 1) apply_tc_kernel(const __grid_co
             for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float v = ex2_approx(fmaf(cv[jj * 2 + kk][e], -k, fv[kk] + gJ[jj][e]));
+                float v = ex2_approx(fmaf(cv[jj * 2 + kk][e], -k, fv[kk] + gJ[jj][e]));
+                if (sp.weighted) {  // CTA-uniform
+                  const long long i = (long long)kb * AP_KC + (kgbit + 2 * kk) * 8 + i8;
+                  const float wi = (sp.wk && i < sp.kdim) ? __ldg(sp.wk + i) : 0.f;
+                  v *= fmaf(sp.w1, cv[jj * 2 + kk][e], sp.w0 + wJ[jj][e] + wi);
+                }
                 pv[jj * 2 + kk][e] = v;
                 rs[jj][e] += v;
               }
@@ -452,15 +481,15 @@ __global__ void __launch_bounds__(AP_THREADS, 1) apply_tc_kernel(const __grid_co
             phase ^= 1;
           }
         }
-        // column sums: fold over the lanes that share (unit half) -- bits 0..2 (i % 8) and 4 (K group)
+        // column sums: fold over the lanes that share (unit half) -- bits 1..3 (i % 8) and 4 (K group)
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float v = rs[jj][e];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
             v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
             if (i8 == 0 && kgbit == 0) {
               const int r = (pw * 2 + jj) * 8 + half * 4 + e;
@@ -605,9 +634,21 @@ static size_t apply_smem(const ApplyPlanCfg& a, const ApplyPlanCfg* b) {
   return (size_t)AP_STAGES * AP_PARTS * AP_A_TILE + AP_STAGES * vstage + 2 * 2 * AP_BM * 4 + (3 * AP_STAGES + 2) * 8 + 16;
 }
 
+struct ApplyWeights {  // W_ij = P_ij (w0 + w1 C_ij + wrow_i + wcol_j); wrow over the rows of C, wcol over its columns
+  int on;
+  float w0, w1;
+  const float* wrow;
+  const float* wcol;
+};
+
 static int apply_fill_sub(ApplySub& s, const ApplyPlanCfg& c, const float* C, int ldc, int n, int m, const float* f,
                           const float* g, int transpose, int dv, int mode, const float* W, int ldw, float scale,
-                          float* Z, int ldz, float* rowsum_out, uint8_t* ws) {
+                          float* Z, int ldz, float* rowsum_out, uint8_t* ws, const ApplyWeights* wt = nullptr) {
+  s.weighted = (wt && wt->on) ? 1 : 0;
+  s.w0 = s.weighted ? wt->w0 : 1.f;
+  s.w1 = s.weighted ? wt->w1 : 0.f;
+  s.wrow = s.weighted ? (transpose ? wt->wcol : wt->wrow) : nullptr;
+  s.wk = s.weighted ? (transpose ? wt->wrow : wt->wcol) : nullptr;
   s.C = C;
   s.ldc = ldc;
   s.frow = transpose ? g : f;
@@ -705,6 +746,62 @@ int b200ot_apply_plan_tc(const float* C, int ldc, int n, int m, const float* f, 
                  rowsum_out, w);
   a.items[0] = c.nblocks * c.S;
   return apply_launch(a, c, nullptr, st);
+}
+
+int b200ot_apply_plan_tc_weighted(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                                  float w0, float w1, const float* wrow, const float* wcol, const float* V, int ldv,
+                                  int dv, int transpose, float* Z, int ldz, float* rowsum_out, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  if (!C || !f || !g || !V || !Z || !ws || n <= 0 || m <= 0 || dv <= 0 || ldc < m || ldv < dv || ldz < dv ||
+      !(eps > 0.f))
+    return B200OT_E_INVALID;
+  if (dv > AP_MAX_DV) return B200OT_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return B200OT_E_INVALID;
+  const ApplyPlanCfg c = apply_cfg(transpose ? m : n, transpose ? n : m, dv);
+  if (ws_bytes < c.total) return B200OT_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* w = static_cast<uint8_t*>(ws);
+  int rc = apply_split_v(V, ldv, transpose ? n : m, dv, c, w, st);
+  if (rc) return rc;
+  ApplyWeights wt = {1, w0, w1, wrow, wcol};
+  ApplyArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nsub = 1;
+  a.k = kLog2e / eps;
+  apply_fill_sub(a.sub[0], c, C, ldc, n, m, f, g, transpose ? 1 : 0, dv, 0, nullptr, 0, 1.f, Z, ldz, rowsum_out, w, &wt);
+  a.items[0] = c.nblocks * c.S;
+  return apply_launch(a, c, nullptr, st);
+}
+
+int b200ot_envelope_bwd_weighted(const float* C, int ldc, int n, int m, const float* f, const float* g, float eps,
+                                 float w0, float w1, const float* wrow, const float* wcol, const float* X, int ldx,
+                                 const float* Y, int ldy, int d, float scale, float* dX, int lddx, float* dY, int lddy,
+                                 void* ws, size_t ws_bytes, void* stream) {
+  if (!C || !f || !g || !X || !Y || !dX || !dY || !ws || n <= 0 || m <= 0 || d <= 0 || ldc < m || ldx < d ||
+      ldy < d || lddx < d || lddy < d || !(eps > 0.f))
+    return B200OT_E_INVALID;
+  if (d > AP_MAX_DV) return B200OT_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return B200OT_E_INVALID;
+  const ApplyPlanCfg c0 = apply_cfg(n, m, d);
+  const ApplyPlanCfg c1 = apply_cfg(m, n, d);
+  if (ws_bytes < c0.total + c1.total) return B200OT_E_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* w0p = static_cast<uint8_t*>(ws);
+  uint8_t* w1p = w0p + c0.total;
+  int rc = apply_split_v(Y, ldy, m, d, c0, w0p, st);
+  if (rc) return rc;
+  rc = apply_split_v(X, ldx, n, d, c1, w1p, st);
+  if (rc) return rc;
+  ApplyWeights wt = {1, w0, w1, wrow, wcol};
+  ApplyArgs a;
+  memset(&a, 0, sizeof(a));
+  a.nsub = 2;
+  a.k = kLog2e / eps;
+  apply_fill_sub(a.sub[0], c0, C, ldc, n, m, f, g, 0, d, 2, X, ldx, scale, dX, lddx, nullptr, w0p, &wt);
+  apply_fill_sub(a.sub[1], c1, C, ldc, n, m, f, g, 1, d, 2, Y, ldy, scale, dY, lddy, nullptr, w1p, &wt);
+  a.items[0] = c0.nblocks * c0.S;
+  a.items[1] = c1.nblocks * c1.S;
+  return apply_launch(a, c0, &c1, st);
 }
 
 size_t b200ot_envelope_bwd_workspace_bytes(int n, int m, int d) {

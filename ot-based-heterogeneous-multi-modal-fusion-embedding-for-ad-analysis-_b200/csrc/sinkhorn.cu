@@ -57,6 +57,7 @@ __global__ void init_state_kernel(State* st, b200ot_params prm) {
   s.fs_hi[0] = -INFINITY;
   s.fs_lo[1] = INFINITY;
   s.fs_hi[1] = -INFINITY;
+  s.snap_it = -1;  // no snapshot yet: a failure of the first g update cannot be rewound (rewind_kernel leaves it)
   *st = s;
 }
 
@@ -798,7 +799,225 @@ __device__ __noinline__ void sweep_fused_tail(const SweepArgs& p, State* st, int
 // software pipelining: each CTA keeps ONE register set of exponentials (32 per thread), so two CTAs of
 // different clusters share an SM and one computes while the other sits in its reduction / DSMEM exchange.
 
+// The round-1 argument block, kept as it was: the code generated for the plain kernel depends on it.
+struct SweepArgsPlain {
+  const float* C;
+  long long ldc;
+  int n, m;
+  State* st;
+  float* fs;
+  const float* gs0;
+  const float* gs1;
+  const float* a;
+  float* part;  // [nclusters][stride]
+  size_t stride;
+  int ng;          // ring depth in row groups
+  int evict_first; // stream C through L2 with an evict-first policy
+  int wq;          // columns per CTA
+  int mode;        // diagnostics of the pipelined kernel; unused here
+};
+
+// Plain form: ONE sweep per launch, finalize is its own launch.  This is the round-1 kernel, kept verbatim: it sits
+// at 120 of the 128 registers that two CTAs per SM allow, and a same-box A/B showed that carrying the bookkeeping of
+// the persistent form through its row loop (more live state -> rematerialised addresses, +13 % instructions per row)
+// costs 7 % of the bandwidth (336 -> 313 it/s at 65536^2).  The persistent fused form below is a separate kernel.
+// Also measured against this kernel on one box (profiles/r02_sweep_ab.json; 333 it/s here): the three fp32 streams of
+// the row loop as f32x2 instructions (FFMA2 / FADD2: 48 instead of 127 FP32 issue slots per row) 324 it/s, the same
+// with the ring slot kept as a running counter instead of i % NG 303 it/s.  The kernel runs under the board's power
+// cap (1.73 of 1.965 GHz) and is bound by the per-row dependency chain, not by issue slots.
 template <int NCH>
+__global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_plain_kernel(const SweepArgsPlain p) {
+  constexpr int CPT = 4 * NCH;
+  constexpr int W = kLiteThreads * CPT;
+  extern __shared__ __align__(128) unsigned char smem[];
+
+  State* st = p.st;
+  if (st->done) return;
+  const int cur = st->cur;
+  const float k = st->kscale;
+  const float* __restrict__ gs = cur ? p.gs1 : p.gs0;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int q = (int)cluster_ctarank();
+  const int Q = (int)cluster_nctarank();
+  const int cid = (int)cluster_id_x();
+  const int NC = (int)cluster_nid_x();
+  const int NG = p.ng;
+
+  const long long col0 = (long long)q * p.wq;
+  int mvalid = p.m - (int)col0;
+  mvalid = mvalid < 0 ? 0 : (mvalid > p.wq ? p.wq : mvalid);
+
+  const int it0 = st->it;
+  const float flo = st->fs_lo[it0 & 1], fhi = st->fs_hi[it0 & 1];
+  const bool uniform = flo <= fhi && (fhi - flo) < 48.f;
+  const float sigma = uniform ? 0.5f * (flo + fhi) : 0.f;
+
+  float* stage = reinterpret_cast<float*>(smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NG * W * sizeof(float));  // [8]
+  uint64_t* xbar = full + 8;                                                            // [kXBuf]
+  float* red = reinterpret_cast<float*>(xbar + kXBuf);  // [2][kLiteWarps]
+  float* xch = red + 2 * kLiteWarps;                     // [kXBuf][kMaxCluster]
+
+  float gsv[CPT], acc[CPT];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * (kLiteThreads * 4) + tid * 4;
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < mvalid) g4 = *reinterpret_cast<const float4*>(gs + col0 + col);
+    gsv[c * 4 + 0] = g4.x + sigma;
+    gsv[c * 4 + 1] = g4.y + sigma;
+    gsv[c * 4 + 2] = g4.z + sigma;
+    gsv[c * 4 + 3] = g4.w + sigma;
+    acc[c * 4 + 0] = acc[c * 4 + 1] = acc[c * 4 + 2] = acc[c * 4 + 3] = 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NG; ++s) mbar_init(smem_u32(full + s), 1);
+    for (int s = 0; s < kXBuf; ++s) mbar_init(smem_u32(xbar + s), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  cluster_arrive();
+  cluster_wait();
+
+  const int cnt = cid < p.n ? (p.n - cid + NC - 1) / NC : 0;  // rows cid, cid + NC, ...
+  const uint64_t pol = p.evict_first ? policy_evict_first() : 0ull;
+  const uint32_t row_bytes = (uint32_t)mvalid * 4u;
+  auto issue = [&](int i) {
+    const int s = i % NG;
+    const uint32_t bar = smem_u32(full + s);
+    mbar_arrive_expect_tx(bar, row_bytes);
+    if (row_bytes) {
+      const float* src = p.C + (long long)(cid + i * NC) * p.ldc + col0;
+      const uint32_t dst = smem_u32(stage + (size_t)s * W);
+      if (p.evict_first)
+        bulk_g2s_hint(dst, src, row_bytes, bar, pol);
+      else
+        bulk_g2s(dst, src, row_bytes, bar);
+    }
+  };
+  if (tid == 0) {
+    const int pre = cnt < NG ? cnt : NG;
+    for (int i = 0; i < pre; ++i) issue(i);
+  }
+
+  const bool last_ok = (NCH - 1) * (kLiteThreads * 4) + tid * 4 < mvalid;
+  const bool last_any = __any_sync(0xffffffffu, last_ok);
+  float f_lo = INFINITY, f_hi = -INFINITY;
+
+  auto row_loop = [&](auto uni_tag) {
+    constexpr bool UNI = decltype(uni_tag)::value;
+    float a_next = cnt > 0 ? p.a[cid] : 0.f;
+    float sh_next = (!UNI && cnt > 0) ? p.fs[cid] : sigma;
+    int qsel = 0;  // CTA of the cluster that writes this row's potential
+    for (int i = 0; i < cnt; ++i) {
+      const int row = cid + i * NC;
+      const int s = i % NG;
+      const float ar = a_next, sh = sh_next;
+      if (i + 1 < cnt) {  // prefetch the next row's scalars so their latency is off the critical path
+        a_next = p.a[row + NC];
+        if (!UNI) sh_next = p.fs[row + NC];
+      }
+      mbar_wait(smem_u32(full + s), (uint32_t)((i / NG) & 1));
+      float t[CPT];
+      const float* srow = stage + (size_t)s * W + tid * 4;
+      auto quad = [&](int c) {
+        const float4 v = *reinterpret_cast<const float4*>(srow + c * (kLiteThreads * 4));
+        if (UNI) {
+          t[c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0]));
+          t[c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1]));
+          t[c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2]));
+          t[c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3]));
+        } else {
+          t[c * 4 + 0] = ex2_approx(fmaf(v.x, -k, gsv[c * 4 + 0] + sh));
+          t[c * 4 + 1] = ex2_approx(fmaf(v.y, -k, gsv[c * 4 + 1] + sh));
+          t[c * 4 + 2] = ex2_approx(fmaf(v.z, -k, gsv[c * 4 + 2] + sh));
+          t[c * 4 + 3] = ex2_approx(fmaf(v.w, -k, gsv[c * 4 + 3] + sh));
+        }
+      };
+#pragma unroll
+      for (int c = 0; c < NCH - 1; ++c) quad(c);
+      if (last_any) {
+        quad(NCH - 1);
+        if (!last_ok) t[CPT - 4] = t[CPT - 3] = t[CPT - 2] = t[CPT - 1] = 0.f;
+      } else {
+        t[CPT - 4] = t[CPT - 3] = t[CPT - 2] = t[CPT - 1] = 0.f;
+      }
+      float ps = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) ps += (t[c * 4 + 0] + t[c * 4 + 1]) + (t[c * 4 + 2] + t[c * 4 + 3]);
+      ps = warp_sum(ps);
+      const int par = i & 1;
+      if (lane == 0) red[par * kLiteWarps + warp] = ps;
+      __syncthreads();  // ring stage drained by every warp; red[par] complete
+      const int xb = i % kXBuf;
+      // per-row serial chores rotate over warps (and the potential update over the CTAs of the cluster) so that
+      // no warp is systematically the last one at the next block barrier
+      if (lane == 0 && warp == ((i + 4) & (kLiteWarps - 1)) && i + NG < cnt) {
+        fence_proxy_async();
+        issue(i + NG);
+      }
+      if (warp == ((i + 6) & (kLiteWarps - 1))) {  // the row-sum exchange rotates too
+        if (lane == 0) mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
+        if (lane < Q) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < kLiteWarps; ++w) v += red[par * kLiteWarps + w];
+          st_async_f32(map_to_cta(smem_u32(xch + xb * kMaxCluster + q), (uint32_t)lane), v,
+                       map_to_cta(smem_u32(xbar + xb), (uint32_t)lane));
+        }
+      }
+      mbar_wait(smem_u32(xbar + xb), (uint32_t)((i / kXBuf) & 1));
+      float rt = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < kMaxCluster; ++qq)
+        if (qq < Q) rt += xch[xb * kMaxCluster + qq];
+      const bool live = ar > 0.f;
+      const float w = live ? __fdividef(ar, rt) : 0.f;
+      if (q == qsel && lane == 0 && warp == ((i + 2) & (kLiteWarps - 1))) {
+        const float fnew = live ? sh + (log2f(ar) - log2f(rt)) : -INFINITY;
+        p.fs[row] = fnew;
+        if (live) {
+          if (fabsf(fnew) < INFINITY) {
+            f_lo = fminf(f_lo, fnew);
+            f_hi = fmaxf(f_hi, fnew);
+          } else {
+            atomicExch(&st->bad, 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[c], w, acc[c]);
+      qsel = (qsel + 1 == Q) ? 0 : qsel + 1;
+    }
+  };
+  if (uniform)
+    row_loop(std::true_type{});
+  else
+    row_loop(std::false_type{});
+
+  if (lane == 0 && f_lo <= f_hi) {  // every thread that wrote potentials
+    atomic_min_float(&st->fs_lo[(it0 + 1) & 1], f_lo);
+    atomic_max_float(&st->fs_hi[(it0 + 1) & 1], f_hi);
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * (kLiteThreads * 4) + tid * 4;
+    if (col < mvalid)
+      *reinterpret_cast<float4*>(p.part + (size_t)cid * p.stride + col0 + col) =
+          make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
+  }
+  cluster_arrive();
+  cluster_wait();
+}
+
+
+// FUSE = false: one sweep per launch (the round-1 kernel; finalize is its own launch).  FUSE = true: the persistent
+// form -- up to p.iters iterations per launch, each ending in sweep_fused_tail.  Two instantiations, because the
+// bookkeeping of the persistent form costs registers and the plain kernel sits exactly at the 128-register limit of
+// two CTAs per SM (same-box A/B: 336 vs 313 it/s when the plain path carried the persistent bookkeeping).
+template <int NCH, bool FUSE>
 __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __grid_constant__ SweepArgs p) {
   constexpr int CPT = 4 * NCH;
   constexpr int W = kLiteThreads * CPT;
@@ -825,7 +1044,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
   uint64_t* xbar = full + 8;                                                            // [kXBuf]
   float* red = reinterpret_cast<float*>(xbar + kXBuf);  // [2][kLiteWarps]
   float* xch = red + 2 * kLiteWarps;                     // [kXBuf][kMaxCluster]
-  unsigned char* tail_scratch = reinterpret_cast<unsigned char*>(xch + kXBuf * kMaxCluster);  // 128 bytes
+  // (128 bytes after xch are the scratch of the fused tail)
 
   if (tid == 0) {
     for (int s = 0; s < NG; ++s) mbar_init(smem_u32(full + s), 1);
@@ -839,7 +1058,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
   // One launch runs `iters` iterations when the fused tail is on (persistent form): the rows of this cluster are
   // the same in every iteration, so the TMA ring simply keeps running across the iteration boundary -- while the
   // grid folds, exchanges and finalizes, the first rows of the next sweep are already on their way.
-  const int n_it = p.fuse ? (p.iters > 0 ? p.iters : 1) : 1;
+  const int n_it = FUSE ? (p.iters > 0 ? p.iters : 1) : 1;
   const int cnt = cid < p.n ? (p.n - cid + NC - 1) / NC : 0;  // rows cid, cid + NC, ...
   const int total_rows = cnt * n_it;  // the host keeps this below 2^30
   const uint64_t pol = p.evict_first ? policy_evict_first() : 0ull;
@@ -848,9 +1067,8 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
   // exponential phases (MUFU-bound) coincide and their exchange phases (SM idle) coincide too; starting every other
   // cluster half a row period late lets one CTA of an SM compute while the other waits for its cluster.
   if (p.stagger_ns > 0 && (cid & 1)) __nanosleep((unsigned)p.stagger_ns);
-  // gq: running index of a row over all iterations of the launch (ring slot and phase); irow: its index in the sweep
-  auto issue = [&](int gq, int irow) {
-    const int s = gq % NG;
+  // s: ring slot; irow: index of the row in the sweep of this cluster
+  auto issue = [&](int s, int irow) {
     const uint32_t bar = smem_u32(full + s);
     mbar_arrive_expect_tx(bar, row_bytes);
     if (row_bytes) {
@@ -869,7 +1087,14 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
 
   const bool last_ok = (NCH - 1) * (kLiteThreads * 4) + tid * 4 < mvalid;
   const bool last_any = __any_sync(0xffffffffu, last_ok);
-  int consumed = 0;  // rows of this launch whose ring slot has been drained
+  // Ring / exchange bookkeeping runs over ALL rows of the launch (the ring does not restart at an iteration
+  // boundary) and is kept as incrementing warp-uniform counters: no division by the run-time ring depth per row.
+  int slot = 0;                     // ring slot of the row being consumed
+  uint32_t sphase = 0;              // its mbarrier phase
+  uint32_t rowctr = 0;              // rows consumed: parity of the row-partial buffer (bit 0), exchange buffer
+                                    // (bits 0-1, kXBuf = 4 deep) and its mbarrier phase (bit 2)
+  int to_issue = total_rows - (total_rows < NG ? total_rows : NG);  // rows still to be issued by the refill
+  int inext = cnt > 0 ? NG % cnt : 0;                               // sweep index of the next row to issue
 
   for (int kit = 0; kit < n_it; ++kit) {
     // ---- per-iteration state (rewritten by the tail of the previous iteration: read it past L1) ----
@@ -892,7 +1117,6 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
       acc[c * 4 + 0] = acc[c * 4 + 1] = acc[c * 4 + 2] = acc[c * 4 + 3] = 0.f;
     }
     float f_lo = INFINITY, f_hi = -INFINITY;
-    const int base = consumed;
 
     auto row_loop = [&](auto uni_tag) {
       constexpr bool UNI = decltype(uni_tag)::value;
@@ -901,14 +1125,13 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
       int qsel = 0;  // CTA of the cluster that writes this row's potential
       for (int i = 0; i < cnt; ++i) {
         const int row = cid + i * NC;
-        const int gi = base + i;
-        const int s = gi % NG;
+        const int s = slot;
         const float ar = a_next, sh = sh_next;
         if (i + 1 < cnt) {  // prefetch the next row's scalars so their latency is off the critical path
           a_next = p.a[row + NC];
           if (!UNI) sh_next = __ldcg(p.fs + row + NC);
         }
-        mbar_wait(smem_u32(full + s), (uint32_t)((gi / NG) & 1));
+        mbar_wait(smem_u32(full + s), sphase);
         float t[CPT];
         const float* srow = stage + (size_t)s * W + tid * 4;
         auto quad = [&](int c) {
@@ -937,17 +1160,19 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < NCH; ++c) ps += (t[c * 4 + 0] + t[c * 4 + 1]) + (t[c * 4 + 2] + t[c * 4 + 3]);
         ps = warp_sum(ps);
-        const int par = gi & 1;
+        const int par = (int)(rowctr & 1u);
+        const int xb = (int)(rowctr & (kXBuf - 1));
         if (lane == 0) red[par * kLiteWarps + warp] = ps;
         __syncthreads();  // ring stage drained by every warp; red[par] complete
-        const int xb = gi % kXBuf;
         // per-row serial chores rotate over warps (and the potential update over the CTAs of the cluster) so that
         // no warp is systematically the last one at the next block barrier
-        if (lane == 0 && warp == ((i + 4) & (kLiteWarps - 1)) && gi + NG < total_rows) {
-          int inext = i + NG;  // the slot just drained takes the row NG ahead -- of the NEXT sweep past the end
-          while (inext >= cnt) inext -= cnt;
-          fence_proxy_async();
-          issue(gi + NG, inext);
+        if (to_issue > 0) {  // the slot just drained takes the row NG ahead -- of the NEXT sweep past the end
+          if (lane == 0 && warp == ((i + 4) & (kLiteWarps - 1))) {
+            fence_proxy_async();
+            issue(s, inext);
+          }
+          --to_issue;
+          if (++inext == cnt) inext = 0;
         }
         if (warp == ((i + 6) & (kLiteWarps - 1))) {  // the row-sum exchange rotates too
           if (lane == 0) mbar_arrive_expect_tx(smem_u32(xbar + xb), (uint32_t)(Q * 4));
@@ -959,7 +1184,7 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
                          map_to_cta(smem_u32(xbar + xb), (uint32_t)lane));
           }
         }
-        mbar_wait(smem_u32(xbar + xb), (uint32_t)((gi / kXBuf) & 1));
+        mbar_wait(smem_u32(xbar + xb), (rowctr >> 2) & 1u);
         float rt = 0.f;
 #pragma unroll
         for (int qq = 0; qq < kMaxCluster; ++qq)
@@ -981,13 +1206,17 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < CPT; ++c) acc[c] = fmaf(t[c], w, acc[c]);
         qsel = (qsel + 1 == Q) ? 0 : qsel + 1;
+        if (++slot == NG) {
+          slot = 0;
+          sphase ^= 1u;
+        }
+        ++rowctr;
       }
     };
     if (uniform)
       row_loop(std::true_type{});
     else
       row_loop(std::false_type{});
-    consumed += cnt;
 
     if (lane == 0 && f_lo <= f_hi) {  // every thread that wrote potentials
       atomic_min_float(&st->fs_lo[(it0 + 1) & 1], f_lo);
@@ -1000,17 +1229,28 @@ __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_kernel(const __gri
         *reinterpret_cast<float4*>(p.part + (size_t)cid * p.stride + col0 + col) =
             make_float4(acc[c * 4 + 0], acc[c * 4 + 1], acc[c * 4 + 2], acc[c * 4 + 3]);
     }
-    if (!p.fuse) break;
-    sweep_fused_tail(p, st, cur, it0, NC, tail_scratch);
-    if (((volatile int*)&st->done)[0]) break;  // grid-uniform: read after the tail's closing grid barrier
+    if constexpr (!FUSE) {
+      break;
+    } else {
+      // (cur and it are re-read here instead of being kept live across the row loop)
+      sweep_fused_tail(p, st, ((volatile int*)&st->cur)[0], ((volatile int*)&st->it)[0], NC,
+                       smem + (size_t)NG * W * sizeof(float) + 8 * 8 + kXBuf * 8 + (2 * kLiteWarps + kXBuf * kMaxCluster) * 4);
+      if (((volatile int*)&st->done)[0]) break;  // grid-uniform: read after the tail's closing grid barrier
+    }
   }
 
   // rows of sweeps that will not run (the stopping rule fired inside the launch) are still in flight: a CTA must
   // not retire with bulk copies outstanding into its shared memory
   if (cnt > 0) {
-    int issued = consumed + NG;
-    issued = issued > total_rows ? total_rows : issued;
-    for (int gq = consumed; gq < issued; ++gq) mbar_wait(smem_u32(full + gq % NG), (uint32_t)((gq / NG) & 1));
+    // issued so far = total_rows - to_issue; the rows not consumed sit in the slots from `slot` onwards
+    const int outstanding = (total_rows - to_issue) - (int)rowctr;  // issued - consumed
+    for (int j = 0; j < outstanding; ++j) {
+      mbar_wait(smem_u32(full + slot), sphase);
+      if (++slot == NG) {
+        slot = 0;
+        sphase ^= 1u;
+      }
+    }
   }
   cluster_arrive();
   cluster_wait();
@@ -1222,6 +1462,7 @@ __global__ void snapshot_kernel(State* st, int n, int m, const float* fs, const 
 
 __global__ void rewind_kernel(State* st, int n, int m, float* fs, float* gs0, float* gs1,
                               const float* snap_fs, const float* snap_gs) {
+  if (st->snap_it < 0) return;  // nothing to go back to (the first g update itself failed): bad / done stay set
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float* gs = st->snap_cur ? gs1 : gs0;
   if (i < n) fs[i] = snap_fs[i];
@@ -1434,19 +1675,22 @@ static int pick_fused(int n, int m, FusedCfg* out) {
 // ---- lite variant host side ---------------------------------------------------------------------
 constexpr int kLiteMaxNch = 8;
 
-template <int NCH>
+template <int NCH, bool FUSE>
 static cudaError_t lite_set_attr() {
   static PerDeviceOnce attr_once;  // one per instantiation and device
   if (!attr_once.first()) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(sweep_lite_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kLiteSmemMax);
+  cudaError_t e = FUSE ? cudaFuncSetAttribute(sweep_lite_kernel<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)kLiteSmemMax)
+                       : cudaFuncSetAttribute(sweep_lite_plain_kernel<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)kLiteSmemMax);
   if (e != cudaSuccess) attr_once.undo();
   return e;
 }
 
 template <int NCH>
 static cudaError_t lite_launch_or_query(const SweepArgs* a, int Q, int NC, size_t smem, cudaStream_t s, int* nc_out) {
-  cudaError_t e = lite_set_attr<NCH>();
+  cudaError_t e = lite_set_attr<NCH, false>();
+  if (e == cudaSuccess) e = lite_set_attr<NCH, true>();
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1461,13 +1705,38 @@ static cudaError_t lite_launch_or_query(const SweepArgs* a, int Q, int NC, size_
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (!a) return cudaOccupancyMaxActiveClusters(nc_out, sweep_lite_kernel<NCH>, &cfg);
-  if (a->fuse) {  // the fused tail holds a grid barrier: every CTA must be co-resident, or the launch fails
+  if (!a) {  // co-resident clusters: the smaller answer of the two instantiations (one grid size serves both)
+    int n0 = 0, n1 = 0;
+    e = cudaOccupancyMaxActiveClusters(&n0, sweep_lite_plain_kernel<NCH>, &cfg);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveClusters(&n1, sweep_lite_kernel<NCH, true>, &cfg);
+    if (e != cudaSuccess) return e;
+    *nc_out = n0 < n1 ? n0 : n1;
+    return cudaSuccess;
+  }
+  if (a->fuse) {  // the fused tail holds grid barriers: every CTA must be co-resident, or the launch fails
     at[1].id = cudaLaunchAttributeCooperative;
     at[1].val.cooperative = 1;
     cfg.numAttrs = 2;
+    return cudaLaunchKernelEx(&cfg, sweep_lite_kernel<NCH, true>, *a);
   }
-  return cudaLaunchKernelEx(&cfg, sweep_lite_kernel<NCH>, *a);
+  SweepArgsPlain pa;
+  pa.C = a->C;
+  pa.ldc = a->ldc;
+  pa.n = a->n;
+  pa.m = a->m;
+  pa.st = a->st;
+  pa.fs = a->fs;
+  pa.gs0 = a->gs0;
+  pa.gs1 = a->gs1;
+  pa.a = a->a;
+  pa.part = a->part;
+  pa.stride = a->stride;
+  pa.ng = a->ng;
+  pa.evict_first = a->evict_first;
+  pa.wq = a->wq;
+  pa.mode = a->mode;
+  return cudaLaunchKernelEx(&cfg, sweep_lite_plain_kernel<NCH>, pa);
 }
 
 static cudaError_t lite_dispatch(int nch, const SweepArgs* a, int Q, int NC, size_t smem, cudaStream_t s, int* nc_out) {
@@ -1562,12 +1831,14 @@ struct FuseCtx {
 static bool g_fuse_broken = false;  // a failed cooperative cluster launch disables the fused form for the process
 static long long g_fused_launches = 0, g_fused_fallbacks = 0;  // host-side counters (b200ot_sinkhorn_counter)
 static bool fuse_wanted() {
-  static int want = -1;
-  if (want < 0) {
-    const char* e = getenv("B200OT_FUSE");
-    want = (e && e[0] == '0') ? 0 : 1;
-  }
-  return want == 1 && !g_fuse_broken;
+  // Default: separate launches on the plain kernel (measured faster, see sweep_lite_plain_kernel).  B200OT_FUSE=1
+  // selects the persistent fused form (one cooperative cluster launch runs sweep, fold, peer exchange, finalize and
+  // stopping rule of many iterations).  Read on every call so a test can switch it inside one process.  Nsight
+  // Compute cannot launch a cooperative CLUSTER kernel (LaunchFailed under the profiler): never under injection.
+  const char* e = getenv("B200OT_FUSE");
+  if (!(e && e[0] == '1')) return false;
+  if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) return false;
+  return !g_fuse_broken;
 }
 
 // One sweep (plain form), or -- with a FuseCtx, when the lite kernel applies -- `iters` whole iterations in ONE
@@ -1993,6 +2264,7 @@ int b200ot_sinkhorn_solve(const float* C, int ldc, int n, int m, const float* a,
         if (rc) return rc;
         B200OT_CUDA_OK(cudaMemcpyAsync(pinned + 16, ws, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
         B200OT_CUDA_OK(cudaStreamSynchronize(s));
+        if (pinned[16 + 4]) break;  // still bad: there was no snapshot to rewind to (status E_NUMERIC)
         it_enq = pinned[16];
         path = B200OT_PATH_ROBUST;
         have_prev = false;

@@ -158,3 +158,66 @@ def test_fusion_head_matches_reference_forward_arithmetic(cuda_dev):
     pet_feat.grad = None
     (attn1.sum() + l1).backward()
     assert torch.allclose(g2, pet_feat.grad, rtol=1e-3, atol=1e-5 * float(pet_feat.grad.abs().max()))
+
+
+def _unrolled_primal_value(x, y, a, b, eps, iters):
+    """float64 torch: log-domain Sinkhorn unrolled, returns <P, C> (autograd flows through the iterations)."""
+    C = (x * x).sum(1)[:, None] + (y * y).sum(1)[None, :] - 2 * x @ y.T
+    f = torch.zeros_like(a)
+    g = torch.zeros_like(b)
+    for _ in range(iters):
+        g = eps * torch.log(b) - eps * torch.logsumexp((f[:, None] - C) / eps, dim=0)
+        f = eps * torch.log(a) - eps * torch.logsumexp((g[None, :] - C) / eps, dim=1)
+    P = torch.exp((f[:, None] + g[None, :] - C) / eps)
+    return (P * C).sum()
+
+
+def test_implicit_gradient_of_the_transport_cost_matches_unrolled_autograd(cuda_dev):
+    """ot_loss(value="primal", grad="implicit"): d<P, C>/dx through the Sinkhorn fixed point (implicit function
+    theorem; CG with plan-free products + one weighted launch of the tcgen05 kernel) against float64 autograd
+    through 600 unrolled iterations.  The fixed-plan (envelope) gradient is visibly different for this value."""
+    from b200ot.torch_ops import ot_loss
+    n, m, d, eps = 160, 192, 24, 0.2
+    X, Y = orc.synthetic_embeddings(n, m, d, config_index=9)
+    a = torch.full((n,), 1.0 / n, dtype=torch.float64)
+    b = torch.full((m,), 1.0 / m, dtype=torch.float64)
+    xt = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+    yt = torch.tensor(Y, dtype=torch.float64, requires_grad=True)
+    val = _unrolled_primal_value(xt, yt, a, b, eps, 600)
+    val.backward()
+    xd = torch.tensor(X, device=cuda_dev, requires_grad=True)
+    yd = torch.tensor(Y, device=cuda_dev, requires_grad=True)
+    loss = ot_loss(xd, yd, eps=eps, max_iter=600, tol=0.0, value="primal", grad="implicit")
+    loss.backward()
+    assert abs(loss.item() - val.item()) < 1e-4 * abs(val.item())
+    gx, gy = xt.grad.numpy(), yt.grad.numpy()
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), gx, rtol=0, atol=3e-3 * np.abs(gx).max())
+    np.testing.assert_allclose(yd.grad.cpu().numpy(), gy, rtol=0, atol=3e-3 * np.abs(gy).max())
+    # the envelope gradient of the same value ignores dP/dx: it must NOT agree to that tolerance
+    xe = torch.tensor(X, device=cuda_dev, requires_grad=True)
+    ot_loss(xe, yd.detach(), eps=eps, max_iter=600, tol=0.0, value="primal").backward()
+    assert np.abs(xe.grad.cpu().numpy() - gx).max() > 3e-2 * np.abs(gx).max()
+
+
+def test_weighted_plan_products_match_float64(cuda_dev):
+    """b200ot_apply_plan_tc_weighted: W = P o (w0 + w1 C + wrow (+) wcol), both forms, against NumPy."""
+    from b200ot import ops
+    rng = np.random.default_rng(31)
+    n, m, dv = 300, 520, 40
+    C = rng.random((n, m))
+    f = rng.standard_normal(n) * 0.05
+    g = rng.standard_normal(m) * 0.05
+    eps = 0.3
+    P = orc.plan_from_potentials(C, f, g, eps)
+    wr, wc = rng.standard_normal(n), rng.standard_normal(m)
+    Wm = P * (0.7 - 1.3 * C + wr[:, None] + wc[None, :])
+    V, U = rng.standard_normal((m, dv)), rng.standard_normal((n, dv))
+    dev = cuda_dev
+    t = lambda z: torch.tensor(z, dtype=torch.float32, device=dev)  # noqa: E731
+    Z, rs = ops.apply_plan(t(C), t(f), t(g), eps, t(V), weights=(0.7, -1.3, t(wr), t(wc)), return_rowsum=True)
+    np.testing.assert_allclose(Z.double().cpu().numpy(), Wm @ V, rtol=0, atol=1e-4 * np.abs(Wm @ V).max())
+    np.testing.assert_allclose(rs.double().cpu().numpy(), Wm.sum(1), rtol=0, atol=1e-4 * np.abs(Wm.sum(1)).max())
+    Zt, cs = ops.apply_plan(t(C), t(f), t(g), eps, t(U), transpose=True, weights=(0.7, -1.3, t(wr), t(wc)),
+                            return_rowsum=True)
+    np.testing.assert_allclose(Zt.double().cpu().numpy(), Wm.T @ U, rtol=0, atol=1e-4 * np.abs(Wm.T @ U).max())
+    np.testing.assert_allclose(cs.double().cpu().numpy(), Wm.sum(0), rtol=0, atol=1e-4 * np.abs(Wm.sum(0)).max())

@@ -747,8 +747,8 @@ def test_eot_and_egw_default_entry_points(cuda_dev):
 
 @pytest.mark.parametrize("n,m", [(520, 4096), (301, 12288)])
 def test_fused_iteration_with_peer_words_single_rank(cuda_dev, n, m):
-    """shard_run_peer at world = 1: ONE launch per iteration (sweep + fold + tagged-word push + poll + finalize +
-    state machine in the sweep's own cooperative launch).  With a single rank the push and the poll hit the same
+    """shard_run_peer at world = 1 with B200OT_FUSE=1: ONE persistent launch for the queued iterations (sweep + fold
+    + tagged-word push + poll + finalize + state machine in the sweep's own cooperative cluster launch).  With a single rank the push and the poll hit the same
     buffer, so the whole exchange protocol runs on one GPU without any kernel waiting for another launch.
     Same plan and iteration count as the oracle; equal to the separate-launch form bit for bit."""
     from b200ot import ops, sharded
@@ -764,8 +764,11 @@ def test_fused_iteration_with_peer_words_single_rank(cuda_dev, n, m):
     prm = ops.make_params(eps, 60, 1e-4, 10, 0, "l1", False, "auto")
     buf = torch.zeros(sharded.PeerExchange.nbytes(1, m), dtype=torch.uint8, device=cuda_dev)
     outs = []
+    lib = _lib_mod.load()
+    launches0 = lib.b200ot_sinkhorn_counter(0)
     for fuse in ("1", "0"):
         os.environ["B200OT_RESIDENT"] = "0"
+        os.environ["B200OT_FUSE"] = fuse  # the persistent fused form is opt-in (default: separate launches)
         try:
             k = sharded.CudaShardKernels(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), prm)
             pe = sharded.PeerExchange(m, local_bufs=[buf], rank=0)
@@ -783,15 +786,15 @@ def test_fused_iteration_with_peer_words_single_rank(cuda_dev, n, m):
             outs.append(k.finish())
         finally:
             del os.environ["B200OT_RESIDENT"]
+            del os.environ["B200OT_FUSE"]
     f, g, info = outs[0]
     assert info["n_iter"] == lg["n_iter"] and info["converged"] == lg["converged"] and info["status"] == 0
     assert _rel(ops.plan(Cd, f, g, eps).cpu().numpy(), Pref) < RTOL
     np.testing.assert_allclose(info["errs"].cpu().numpy(), lg["err"], rtol=2e-2, atol=2e-6)
     assert torch.equal(outs[1][0], f) and torch.equal(outs[1][1], g)  # same fold order in both forms
     # the fused form really ran (a refused cooperative cluster launch would silently fall back)
-    lib = _lib_mod.load()
     assert lib.b200ot_sinkhorn_counter(1) == 0, lib.b200ot_last_cuda_error()
-    assert lib.b200ot_sinkhorn_counter(0) >= lg["n_iter"]
+    assert lib.b200ot_sinkhorn_counter(0) - launches0 >= 1
 
 
 def test_sharded_solve_recovers_from_a_lost_sum(cuda_dev):
