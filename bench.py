@@ -32,9 +32,9 @@ D = 512
 
 def _traffic(kernel_desc, n_loc, m):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r01_traffic.json), when this run uses the captured configuration."""
+    (profiles/r02_traffic.json), when this run uses the captured configuration."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as fh:
             for rec in json.load(fh):
                 if rec["n_local"] == n_loc and rec["m"] == m and rec["kernel"] in kernel_desc:
                     return rec["dram_bytes_per_launch"]
@@ -667,7 +667,7 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": _traffic(kernel_desc, n_loc, m),
                      "traffic_source": "static: dram__bytes_read+write per launch from the committed ncu --set full capture "
-                                       "of this kernel configuration (profiles/r01_traffic.json); not re-measured in this run",
+                                       "of this kernel configuration (profiles/r02_traffic.json); not re-measured in this run",
                      "peak_source": peak_src,
                      "note": "achieved = 4*n_local*m bytes per iteration / (step time / iterations); the step time "
                              "includes the finalize kernel and, for N>1, the exchange of the column sums (peer-memory push or NCCL)"},
