@@ -824,7 +824,10 @@ struct SweepArgsPlain {
 // Also measured against this kernel on one box (profiles/r02_sweep_ab.json; 333 it/s here): the three fp32 streams of
 // the row loop as f32x2 instructions (FFMA2 / FADD2: 48 instead of 127 FP32 issue slots per row) 324 it/s, the same
 // with the ring slot kept as a running counter instead of i % NG 303 it/s.  The kernel runs under the board's power
-// cap (1.73 of 1.965 GHz) and is bound by the per-row dependency chain, not by issue slots.
+// cap (1.73 of 1.965 GHz) and is bound by the per-row dependency chain, not by issue slots.  Diagnostic builds on
+// another box (339 it/s): without the cluster exchange (wrong sums) 363 it/s, without the warp reduction either 373
+// it/s = 0.98 of the measured HBM peak at 1.67 GHz -- the ceiling of this decomposition under the power cap; folding
+// the 256 partials in one warp after the barrier instead of a shuffle tree in every warp: 338 it/s (no change).
 template <int NCH>
 __global__ void __launch_bounds__(kLiteThreads, 2) sweep_lite_plain_kernel(const SweepArgsPlain p) {
   constexpr int CPT = 4 * NCH;
