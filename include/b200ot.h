@@ -121,6 +121,14 @@ int b200ot_fot_cost(const float* A, int lda, const float* B, int ldb, const floa
                     const float* w1, const float* w2, int n, int n2, int d, int d2, float* M,
                     int ldm, float* tmp, void* stream);
 
+/* The same feature cost with both contractions on tcgen05 (the split / GEMM pair of b200ot_cost, 6-term bf16 split,
+ * fp32-grade): G = -2 B^T Ts^T, then M = t1 (+) t2 - 2 A^T (-G/2)^T.  SURVEY 8(f-1): the device-resident caller's
+ * X^T.Ts.Y chain.  `ws` (1024-byte aligned) needs b200ot_fot_cost_tc_workspace_bytes bytes.            */
+size_t b200ot_fot_cost_tc_workspace_bytes(int n, int n2, int d, int d2);
+int b200ot_fot_cost_tc(const float* A, int lda, const float* B, int ldb, const float* Ts, int ldt,
+                       const float* w1, const float* w2, int n, int n2, int d, int d2, float* M,
+                       int ldm, void* ws, size_t ws_bytes, void* stream);
+
 /* max of a matrix (ott Geometry(scale_cost="max_cost"), fot.py:129-133) and in-place scale */
 int b200ot_matrix_max(const float* C, int ldc, int n, int m, float* out_max, void* stream);
 int b200ot_matrix_scale_by_inv(float* C, int ldc, int n, int m, const float* denom, void* stream);

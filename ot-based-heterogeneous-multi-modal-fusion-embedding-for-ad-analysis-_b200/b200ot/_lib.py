@@ -55,6 +55,8 @@ SIGNATURES = {
     "b200ot_cost_gemm": (_i, [_p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
     "b200ot_cost_simt": (_i, [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p]),
     "b200ot_fot_cost": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p]),
+    "b200ot_fot_cost_tc_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "b200ot_fot_cost_tc": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p, _sz, _p]),
     "b200ot_matrix_max": (_i, [_p, _i, _i, _i, _p, _p]),
     "b200ot_matrix_scale_by_inv": (_i, [_p, _i, _i, _i, _p, _p]),
     "b200ot_sinkhorn_workspace_bytes": (_sz, [_i, _i]),

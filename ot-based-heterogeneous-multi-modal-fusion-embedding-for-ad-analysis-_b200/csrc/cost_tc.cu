@@ -45,7 +45,7 @@ constexpr int TC_GROUP_N = 16;  // n-blocks per raster group (keeps a 12 MiB sla
 __global__ void __launch_bounds__(256) split_tiles_kernel(const float* __restrict__ X, long long ldx, int rows,
                                                           int d, int tile_rows, int kblocks, int rows_pad,
                                                           int cosine, int nparts, uint8_t* __restrict__ out,
-                                                          float* __restrict__ norms) {
+                                                          float* __restrict__ norms, float prescale) {
   const int row = (blockIdx.x * 256 + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows_pad) return;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) split_tiles_kernel(const float* __restric
     for (int k = lane; k < d; k += 32) ss = fmaf(x[k], x[k], ss);
   ss = warp_sum(ss);
   if (live && lane == 0) norms[row] = cosine ? 1.f : ss;
-  const float scale = cosine ? (ss > 0.f ? rsqrtf(ss) : 0.f) : 1.f;
+  const float scale = cosine ? (ss > 0.f ? rsqrtf(ss) : 0.f) : prescale;  // prescale: a power of two (exact)
   const int rb = row / tile_rows, rin = row % tile_rows;
   const size_t tile_bytes = (size_t)tile_rows * 128;
   const int nchunks = kblocks * 8;
@@ -304,6 +304,36 @@ static CostWs cost_ws(int n, int m, int d) {
   return w;
 }
 
+// out (cols x rows) = X^T for a rows x cols row-major matrix (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) fot_prep_kernel(const float* __restrict__ X, long long ldx, int rows, int cols,
+                                                       float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int row = r0 + r, col = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (row < rows && col < cols) ? X[(long long)row * ldx + col] : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.y; c < 32; c += 8) {
+    const int col = c0 + c, row = r0 + threadIdx.x;
+    if (col < cols && row < rows) out[(long long)col * rows + row] = tile[threadIdx.x][c];
+  }
+}
+
+// out[k] = sum_i XT(k, i)^2 w_i for the transposed matrix XT (feat x samples, contiguous): one warp per feature
+__global__ void __launch_bounds__(256) fot_wnorm_kernel(const float* __restrict__ XT, int samples, int feat,
+                                                        const float* __restrict__ w, float* __restrict__ out) {
+  const int k = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= feat) return;
+  float acc = 0.f;
+  for (int i = lane; i < samples; i += 32) {
+    const float v = XT[(long long)k * samples + i];
+    acc = fmaf(v * v, w[i], acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[k] = acc;
+}
+
 }  // namespace b200ot
 
 using namespace b200ot;
@@ -332,9 +362,9 @@ int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, 
   float* xn = reinterpret_cast<float*>(base + w.norm_off);
   float* yn = xn + n;
   const int cosine = kind == B200OT_COST_COSINE ? 1 : 0;
-  split_tiles_kernel<<<(w.n_pad * 32 + 255) / 256, 256, 0, s>>>(X, ldx, n, d, TC_BM, w.kblocks, w.n_pad, cosine, nparts, Ap, xn);
+  split_tiles_kernel<<<(w.n_pad * 32 + 255) / 256, 256, 0, s>>>(X, ldx, n, d, TC_BM, w.kblocks, w.n_pad, cosine, nparts, Ap, xn, 1.f);
   B200OT_LAUNCH_OK();
-  split_tiles_kernel<<<(w.m_pad * 32 + 255) / 256, 256, 0, s>>>(Y, ldy, m, d, TC_BN, w.kblocks, w.m_pad, cosine, nparts, Bp, yn);
+  split_tiles_kernel<<<(w.m_pad * 32 + 255) / 256, 256, 0, s>>>(Y, ldy, m, d, TC_BN, w.kblocks, w.m_pad, cosine, nparts, Bp, yn, 1.f);
   B200OT_LAUNCH_OK();
   static PerDeviceOnce attr_once;  // function attributes are per device
   if (attr_once.first()) {
@@ -383,7 +413,7 @@ int b200ot_cost_split(const float* X, int ldx, int rows, int d, int kind, int te
   const int kblocks = (d + TC_BK - 1) / TC_BK;
   split_tiles_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       X, ldx, rows, d, tile, kblocks, rows_pad, kind == B200OT_COST_COSINE ? 1 : 0, nparts,
-      static_cast<uint8_t*>(parts), norms);
+      static_cast<uint8_t*>(parts), norms, 1.f);
   B200OT_LAUNCH_OK();
   return 0;
 }
@@ -421,6 +451,95 @@ int b200ot_cost_gemm(const void* partsA, const float* normsA, int row_tile0, int
   cost_tc_kernel<<<grid, TC_THREADS, TC_SMEM, static_cast<cudaStream_t>(stream)>>>(a);
   B200OT_LAUNCH_OK();
   return 0;
+}
+
+// ---- FOT feature cost as a tcgen05 chain ---------------------------------------------------------
+// M = (A.^2)^T w1 (+) (B.^2)^T w2 - 2 A^T Ts B  (MRI_PET_OT_nojax.py:121-136; perturbot/perturbot/match/fot.py:118-128;
+// utils.py:125-184) with A n x d, B n2 x d2, Ts n x n2: two contractions on the tensor cores through the same split /
+// GEMM pair as b200ot_cost.  G = -2 B^T Ts^T (d2 x n; norms 0), then M = t1 (+) t2 - 2 A^T (-G/2)^T: the factor -1/2
+// is folded into the split of G (a power of two, exact).
+struct FotWs {
+  size_t t1, t2, zeros, scratch, AT, BT, G, pBT, pTs, pAT, pG, total;
+};
+static FotWs fot_ws(int n, int n2, int d, int d2) {
+  FotWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 1023) / 1024 * 1024;
+    return o;
+  };
+  const size_t rmax = (size_t)((d > d2 ? d : d2) > n ? (d > d2 ? d : d2) : n) + TC_BN;
+  w.t1 = take(sizeof(float) * ((size_t)d + TC_BM));
+  w.t2 = take(sizeof(float) * ((size_t)d2 + TC_BN));
+  w.zeros = take(sizeof(float) * rmax);
+  w.scratch = take(sizeof(float) * rmax);
+  w.AT = take(sizeof(float) * (size_t)d * n);
+  w.BT = take(sizeof(float) * (size_t)d2 * n2);
+  w.G = take(sizeof(float) * (size_t)d2 * n);
+  w.pBT = take(b200ot_cost_parts_bytes(d2, n2, 0));
+  w.pTs = take(b200ot_cost_parts_bytes(n, n2, 1));
+  w.pAT = take(b200ot_cost_parts_bytes(d, n, 0));
+  w.pG = take(b200ot_cost_parts_bytes(d2, n, 1));
+  w.total = off;
+  return w;
+}
+
+size_t b200ot_fot_cost_tc_workspace_bytes(int n, int n2, int d, int d2) {
+  if (n <= 0 || n2 <= 0 || d <= 0 || d2 <= 0) return 0;
+  return fot_ws(n, n2, d, d2).total;
+}
+
+int b200ot_fot_cost_tc(const float* A, int lda, const float* B, int ldb, const float* Ts, int ldt, const float* w1,
+                       const float* w2, int n, int n2, int d, int d2, float* M, int ldm, void* ws, size_t ws_bytes,
+                       void* stream) {
+  if (!A || !B || !Ts || !w1 || !w2 || !M || !ws || n <= 0 || n2 <= 0 || d <= 0 || d2 <= 0 || lda < d || ldb < d2 ||
+      ldt < n2 || ldm < d2)
+    return B200OT_E_INVALID;
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return B200OT_E_INVALID;
+  const FotWs w = fot_ws(n, n2, d, d2);
+  if (ws_bytes < w.total) return B200OT_E_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  float* t1 = reinterpret_cast<float*>(base + w.t1);
+  float* t2 = reinterpret_cast<float*>(base + w.t2);
+  float* zeros = reinterpret_cast<float*>(base + w.zeros);
+  float* scratch = reinterpret_cast<float*>(base + w.scratch);
+  float* AT = reinterpret_cast<float*>(base + w.AT);
+  float* BT = reinterpret_cast<float*>(base + w.BT);
+  float* G = reinterpret_cast<float*>(base + w.G);
+  B200OT_CUDA_OK(cudaMemsetAsync(zeros, 0, w.scratch - w.zeros, s));
+  // t1_k = sum_i A(i,k)^2 w1_i, t2_l = sum_j B(j,l)^2 w2_j; transposes (contraction index last) in the same pass
+  fot_prep_kernel<<<dim3((d + 31) / 32, (n + 31) / 32), dim3(32, 8), 0, s>>>(A, lda, n, d, AT);
+  B200OT_LAUNCH_OK();
+  fot_prep_kernel<<<dim3((d2 + 31) / 32, (n2 + 31) / 32), dim3(32, 8), 0, s>>>(B, ldb, n2, d2, BT);
+  B200OT_LAUNCH_OK();
+  fot_wnorm_kernel<<<(d * 32 + 255) / 256, 256, 0, s>>>(AT, n, d, w1, t1);
+  B200OT_LAUNCH_OK();
+  fot_wnorm_kernel<<<(d2 * 32 + 255) / 256, 256, 0, s>>>(BT, n2, d2, w2, t2);
+  B200OT_LAUNCH_OK();
+  const int terms = 6, nparts = 3;
+  auto split = [&](const float* X, int ldx, int rows, int K, int side, size_t off, float prescale) {
+    const int tile = side ? TC_BN : TC_BM;
+    const int rows_pad = (rows + tile - 1) / tile * tile;
+    const int kblocks = (K + TC_BK - 1) / TC_BK;
+    split_tiles_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, s>>>(X, ldx, rows, K, tile, kblocks, rows_pad, 0, nparts,
+                                                                   reinterpret_cast<uint8_t*>(base + off), scratch,
+                                                                   prescale);
+  };
+  split(BT, n2, d2, n2, 0, w.pBT, 1.f);
+  B200OT_LAUNCH_OK();
+  split(Ts, ldt, n, n2, 1, w.pTs, 1.f);
+  B200OT_LAUNCH_OK();
+  int rc = b200ot_cost_gemm(base + w.pBT, zeros, 0, d2, base + w.pTs, zeros, n, n2, B200OT_COST_SQEUCLIDEAN, terms, G,
+                            n, stream);
+  if (rc) return rc;
+  split(AT, n, d, n, 0, w.pAT, 1.f);
+  B200OT_LAUNCH_OK();
+  split(G, n, d2, n, 1, w.pG, -0.5f);
+  B200OT_LAUNCH_OK();
+  return b200ot_cost_gemm(base + w.pAT, t1, 0, d, base + w.pG, t2, d2, n, B200OT_COST_SQEUCLIDEAN, terms, M, ldm,
+                          stream);
 }
 
 }  // extern "C"

@@ -79,19 +79,44 @@ def test_cost_tensor_core_split_is_fp32_accurate(cuda_dev, n, m, d):
     assert np.abs(Cs - ref).max() < 4e-6
 
 
-def test_fot_cost_matches_reference_construction(cuda_dev, golden_dir):
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_fot_cost_matches_reference_construction(cuda_dev, golden_dir, impl):
+    """b200ot_fot_cost (fp32 FMA) and b200ot_fot_cost_tc (both contractions on tcgen05, 6-term bf16 split) against
+    the reference construction (MRI_PET_OT_nojax.py:121-136) and the reference's own init_matrix_np output."""
     from b200ot import ops
     g = _load(golden_dir, "c1_sample_64.npz")
     Ts = np.eye(64) / 64
     M = ops.fot_cost(_dev(g["X"], cuda_dev), _dev(g["Y"], cuda_dev), _dev(Ts, cuda_dev),
-                     _dev(Ts.sum(1), cuda_dev), _dev(Ts.sum(0), cuda_dev)).cpu().numpy()
+                     _dev(Ts.sum(1), cuda_dev), _dev(Ts.sum(0), cuda_dev), impl=impl).cpu().numpy()
     ref = orc.fot_cost_pot(g["X"], g["Y"], Ts)
-    np.testing.assert_allclose(M, ref, rtol=0, atol=1e-7)
+    np.testing.assert_allclose(M, ref, rtol=0, atol=1e-7 if impl == "simt" else 4e-7 * float(np.abs(ref).max()))
     h = _load(golden_dir, "helpers.npz")  # init_matrix_np of the reference, rectangular
     T = np.random.default_rng(3).random((6, 5))
     Mg = ops.fot_cost(_dev(h["X1"].T, cuda_dev), _dev(h["X2"].T, cuda_dev), _dev(T, cuda_dev),
-                      _dev(h["v1"], cuda_dev), _dev(h["v2"], cuda_dev)).cpu().numpy()
+                      _dev(h["v1"], cuda_dev), _dev(h["v2"], cuda_dev), impl=impl).cpu().numpy()
     np.testing.assert_allclose(Mg, h["constC"] - h["hC1"] @ T @ h["hC2"].T, rtol=0, atol=2e-5)
+
+
+def test_fot_cost_tensor_core_chain_ragged_shapes(cuda_dev):
+    """The tcgen05 chain at the reference-native feature width (d' = 2048) with ragged sample counts, an unaligned
+    leading dimension and a dense, non-symmetric sample coupling; float64 NumPy is the reference."""
+    from b200ot import ops
+    rng = np.random.default_rng(11)
+    n, n2, d, d2 = 100, 90, 300, 2048
+    A = rng.standard_normal((n, d))
+    B = rng.standard_normal((n2, d2)) * 0.7 + 0.2
+    T = rng.random((n, n2))
+    T /= T.sum()
+    w1, w2 = T.sum(1), T.sum(0)
+    ref = (A * A).T @ w1[:, None] + ((B * B).T @ w2)[None, :] - 2.0 * A.T @ T @ B
+    Ad = torch.zeros(n, d + 3, device=cuda_dev)[:, :d]
+    Ad.copy_(_dev(A, cuda_dev))
+    scale = float(np.abs(ref).max())
+    for impl in ("tc", "simt", "auto"):
+        M = ops.fot_cost(Ad, _dev(B, cuda_dev), _dev(T, cuda_dev), _dev(w1, cuda_dev), _dev(w2, cuda_dev),
+                         impl=impl).double().cpu().numpy()
+        assert M.shape == (d, d2)
+        assert float(np.abs(M - ref).max()) <= 2e-6 * scale, impl
 
 
 # ---------------------------------------------------------------------------
