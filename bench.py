@@ -640,7 +640,10 @@ def run_b200(args):
         win = int(os.environ.get("B200OT_SHARD_WINDOW", "10"))
         launches_per_step = (4 + 2 * n_enq) if world == 1 else (5 + (iters + win - 1) // win)
     else:
-        launches_per_step = (4 + n_enq + 2 * iters) if world == 1 else (5 + 3 * iters)  # sweep, (reduce+push,) finalize
+        # N = 1: sweep + finalize; peer loop: sweep + ONE fold / push / poll / finalize launch (peer_tail_kernel);
+        # NCCL / Python loops and B200OT_PEER_TAIL=0: sweep, reduce(+push), finalize
+        merged_tail = args.loop == "peer" and os.environ.get("B200OT_PEER_TAIL", "1") != "0"
+        launches_per_step = (4 + n_enq + 2 * iters) if world == 1 else (5 + (2 if merged_tail else 3) * iters)
     if resident:
         launches_per_step = 4 + 1 + 1  # init, snapshot, one resident launch for all iterations
     c_bytes = 4.0 * n_loc * m

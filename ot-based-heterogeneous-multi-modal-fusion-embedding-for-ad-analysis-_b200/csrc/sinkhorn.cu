@@ -1313,6 +1313,96 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// reduce_push + finalize of one single-sweep iteration in ONE launch (row-sharded peer loop, default path): thread j
+// folds the rank's cluster slabs of column j, stores the tagged word into every peer's buffer, polls the world's
+// words of column j in its own buffer, applies the finalize step; the last block (ticket) folds the error partials
+// and advances the state machine.  Every block pushes before it polls and the whole grid is co-resident (m / 128
+// blocks of 128 threads), so no rank can wait on a word whose producer has not been scheduled.
+constexpr int kPeerTailThreads = 128;
+__global__ void __launch_bounds__(kPeerTailThreads)
+    peer_tail_kernel(State* st, const float* __restrict__ part_sum, int np, size_t stride, int m,
+                     const float* __restrict__ b, const float* __restrict__ log2b, float* gs0, float* gs1,
+                     double* errpart, float* err_hist, PeerPtrs peers, int world, int rank, size_t xstride,
+                     unsigned epoch) {
+  if (st->done) return;
+  const int j = blockIdx.x * kPeerTailThreads + threadIdx.x;
+  const int x = st->it + 1;
+  const unsigned tag = peer_tag(epoch, x);
+  const int cur = st->cur;
+  const float* gcur = cur ? gs1 : gs0;
+  float* gnext = cur ? gs0 : gs1;
+  const int norm = st->err_norm;
+  double e = 0.0;
+  int bad = 0;
+  if (j < m) {
+    float acc = 0.f;
+    int p = 0;
+    for (; p + 8 <= np; p += 8) {  // eight independent loads in flight, added in slab order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = part_sum[(size_t)(p + u) * stride + j];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; p < np; ++p) acc += part_sum[(size_t)p * stride + j];
+    if (st->bad) acc = __int_as_float(0x7fc00000);  // a lost sum on this rank stops every rank
+    const unsigned long long word = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(acc);
+    const size_t par = (size_t)(x & 1) * world;
+    for (int r = 0; r < world; ++r) {
+      const int dst = (rank + r) % world;  // spread the ranks over the links: everyone starts with itself
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(peers.buf[dst] + (par + rank) * xstride + j), "l"(word)
+                   : "memory");
+    }
+    const unsigned long long* mine = peers.buf[rank] + par * xstride + j;
+    float sum = 0.f;
+    bool any_nan = false;
+    for (int r = 0; r < world; ++r) {  // rank order: the same fold on every rank (g bit-equal across ranks)
+      const float v = r == rank ? acc : peer_poll(mine + (size_t)r * xstride, tag);
+      any_nan |= (v != v);
+      sum += v;
+    }
+    if (any_nan) sum = __int_as_float(0x7fc00000);
+    e = finalize_column(sum, log2f(sum), b[j], log2b[j], gcur[j], norm, gnext + j, &bad);
+  }
+  __shared__ double sh[kPeerTailThreads / 32];
+  __shared__ int shbad, is_last;
+  if (threadIdx.x == 0) shbad = 0;
+  __syncthreads();
+  e = warp_sum(e);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = e;
+  if (bad) shbad = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < kPeerTailThreads / 32; ++w) tot += sh[w];
+    errpart[blockIdx.x] = tot;
+    if (shbad) atomicExch(&st->bad, 1);
+    __threadfence();
+    is_last = (atomicAdd(&st->ticket, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double part = 0.0;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += kPeerTailThreads) part += ((volatile double*)errpart)[i];
+  part = warp_sum(part);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double tot = 0.0;
+  for (int w = 0; w < kPeerTailThreads / 32; ++w) tot += sh[w];
+  const float err = (norm == B200OT_NORM_L2) ? (float)sqrt(tot) : (float)tot;
+  st->ticket = 0;
+  if (((volatile int*)&st->bad)[0]) {  // fast path lost a sum: stop here, the host rewinds and replays robustly
+    st->done = 1;
+    return;
+  }
+  State ls = *st;
+  advance_state(ls, err, false, err_hist);
+  *st = ls;
+}
+
 // =============================================================================
 // ROBUST kernels (running-max logsumexp, any shape / alignment)
 // =============================================================================
@@ -2389,12 +2479,19 @@ int b200ot_sinkhorn_shard_finalize_peer(int n_local, int m, void* ws, const void
                          epoch & 0x7ffu);
 }
 
+// B200OT_PEER_TAIL=0: keep reduce_push and finalize as two launches (A/B switch; re-read on every call)
+static bool peer_tail_wanted() {
+  const char* e = getenv("B200OT_PEER_TAIL");
+  return !(e && e[0] == '0');
+}
+
 int b200ot_sinkhorn_shard_run_peer(const float* C, int ldc, int n_local, int m, int iters, int path, void* ws,
                                    void* const* peer_bufs, int world, int rank, unsigned epoch, void* stream) {
   if (iters < 0 || !peer_bufs || rank < 0 || rank >= world || world > kMaxPeers) return B200OT_E_INVALID;
   int rc = check_problem(C, ldc, n_local, m, ws);
   if (rc) return rc;
-  const bool can_fuse = resolve_path(path, C, ldc, n_local, m) == B200OT_PATH_FUSED && fuse_wanted();
+  const bool single_sweep = resolve_path(path, C, ldc, n_local, m) == B200OT_PATH_FUSED;
+  const bool can_fuse = single_sweep && fuse_wanted();
   const WsPtrs w = ws_ptrs(ws, ws_layout(n_local, m));
   FuseCtx fc;
   memset(&fc, 0, sizeof(fc));
@@ -2428,6 +2525,17 @@ int b200ot_sinkhorn_shard_run_peer(const float* C, int ldc, int n_local, int m, 
         rc = b200ot_sinkhorn_shard_finalize_peer(n_local, m, ws, peer_bufs[rank], world, epoch, 0, stream);
         if (rc) return rc;
       }
+      continue;
+    }
+    if (single_sweep && m <= 4096 * kPeerTailThreads && peer_tail_wanted()) {
+      // default: the plain sweep, then ONE launch that folds, pushes, polls and finalizes
+      int np = 0;
+      rc = launch_sweep_fused(C, ldc, n_local, m, w, &np, s);
+      if (rc) return rc;
+      peer_tail_kernel<<<(m + kPeerTailThreads - 1) / kPeerTailThreads, kPeerTailThreads, 0, s>>>(
+          w.st, w.part_sum, np, w.m_pad, m, w.b, w.log2b, w.gs0, w.gs1, w.errpart, w.err_hist, fc.peers, world, rank,
+          fc.xstride, fc.epoch);
+      B200OT_LAUNCH_OK();
       continue;
     }
     rc = b200ot_sinkhorn_shard_push(C, ldc, n_local, m, path, ws, peer_bufs, world, rank, epoch, 0, stream);

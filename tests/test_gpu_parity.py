@@ -791,18 +791,20 @@ def test_fused_iteration_with_peer_words_single_rank(cuda_dev, n, m):
     outs = []
     lib = _lib_mod.load()
     launches0 = lib.b200ot_sinkhorn_counter(0)
-    for fuse in ("1", "0"):
+    for fuse in ("1", "0", "tail"):
         os.environ["B200OT_RESIDENT"] = "0"
-        os.environ["B200OT_FUSE"] = fuse  # the persistent fused form is opt-in (default: separate launches)
+        # the persistent fused form is opt-in; "tail" = the default of run_peer: plain sweep + ONE fold / push / poll /
+        # finalize launch per iteration; "0" = the three separate launches
+        os.environ["B200OT_FUSE"] = "1" if fuse == "1" else "0"
         try:
             k = sharded.CudaShardKernels(Cd, _dev(a, cuda_dev), _dev(b, cuda_dev), prm)
             pe = sharded.PeerExchange(m, local_bufs=[buf], rank=0)
-            pe.epoch = 7 if fuse == "1" else 8
+            pe.epoch = {"1": 7, "0": 8, "tail": 9}[fuse]
             k.setup()
             k.push(pe, True)
             k.finalize_peer(pe, True)
-            if fuse == "1":
-                k.run_peer(35, pe)   # fused launches
+            if fuse in ("1", "tail"):
+                k.run_peer(35, pe)   # fused launches / sweep + merged tail
                 k.run_peer(35, pe)   # past convergence: no-ops
             else:
                 for _ in range(60):  # the separate-launch form of the same loop
@@ -816,7 +818,9 @@ def test_fused_iteration_with_peer_words_single_rank(cuda_dev, n, m):
     assert info["n_iter"] == lg["n_iter"] and info["converged"] == lg["converged"] and info["status"] == 0
     assert _rel(ops.plan(Cd, f, g, eps).cpu().numpy(), Pref) < RTOL
     np.testing.assert_allclose(info["errs"].cpu().numpy(), lg["err"], rtol=2e-2, atol=2e-6)
-    assert torch.equal(outs[1][0], f) and torch.equal(outs[1][1], g)  # same fold order in both forms
+    for other in outs[1:]:  # same fold order in all three forms
+        assert torch.equal(other[0], f) and torch.equal(other[1], g)
+        assert other[2]["n_iter"] == info["n_iter"]
     # the fused form really ran (a refused cooperative cluster launch would silently fall back)
     assert lib.b200ot_sinkhorn_counter(1) == 0, lib.b200ot_last_cuda_error()
     assert lib.b200ot_sinkhorn_counter(0) - launches0 >= 1
