@@ -404,10 +404,11 @@ def _online_extra(torch, ops, dev, args, out):
         executed = sol.tensor_flops_per_iteration / ms_o / 1e9
         out["online_c4"] = {
             "workload": f"cost-free Sinkhorn n=m={n} d={D}: C rebuilt per iteration on tcgen05 in {sol.panel_rows}-row panels "
-                        f"({sol.panel.numel() * 4 >> 20} MiB scratch, 6-term bf16 split), consumed by the single-sweep "
+                        f"({sol.panel.numel() * 4 >> 20} MiB scratch, {sol.products}-product "
+                        f"{'fp16' if sol.products in (3, 4) and sol.terms >= 19 else 'bf16'} split), consumed by the single-sweep "
                         f"kernel; the n x m matrix is never materialised",
             "iterations_per_s": 1e3 / ms_o, "ms_per_iteration": ms_o,
-            "tensor_tflops_executed": executed, "tensor_tflops_algorithmic": executed / sol.terms,
+            "tensor_tflops_executed": executed, "tensor_tflops_algorithmic": executed / sol.products,
             "tensor_frac_of_sustained_bf16_peak": executed / tf_peak, "tensor_peak_tflops": tf_peak,
             "streaming_is_faster_by": None}
     return out

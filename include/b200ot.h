@@ -96,15 +96,21 @@ const char* b200ot_last_cuda_error(void);
  * with an fp32-accurate split over bf16 parts x = x1 + x2 + x3: terms = 6 evaluates
  * x1.y3 + x3.y1 + x2.y2 + x1.y2 + x2.y1 + x1.y1 (fp32-grade, the default of the Python host),
  * terms = 3 drops the first three (error ~2^-17 per product), terms = 1 is the plain bf16 product.
+ * terms = B200OT_TERMS_F16_3 (the Python host's default) scales every row by a power of two (largest entry into
+ * [2^9, 2^10)), splits it into TWO fp16 parts (11 + 11 bits) and evaluates x1.y2 + x2.y1 + x1.y1: representation
+ * error <= 2^-23 of the row maximum per entry -- fp32-grade relative to |x||y| -- at half the tensor work of
+ * terms = 6; B200OT_TERMS_F16_4 adds x2.y2.
  * `ws` (1024-byte aligned) needs b200ot_cost_workspace_bytes(n, m, d) bytes.
  * cost_simt is the fp32 FMA version; `norms` is scratch for n + m floats.          */
+#define B200OT_TERMS_F16_3 19
+#define B200OT_TERMS_F16_4 20
 size_t b200ot_cost_workspace_bytes(int n, int m, int d);
 int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, int d, int kind,
                 float* C, int ldc, void* ws, size_t ws_bytes, int terms, void* stream);
 /* The two halves of b200ot_cost for callers that keep the bf16 parts resident (the online solver re-builds
  * row panels of C every iteration but splits X and Y once).  side = 0: rows of X (128-row tiles), 1: rows of Y
  * (256-row tiles).  parts needs b200ot_cost_parts_bytes bytes (1024-byte aligned), norms rows (padded to the
- * tile) floats.  cost_gemm builds n rows of C starting at 128-row tile `row_tile0` of the X parts.        */
+ * tile) floats -- TWICE that with the fp16 terms, which store {norm, 2^-s} per row.  cost_gemm builds n rows of C starting at 128-row tile `row_tile0` of the X parts.        */
 size_t b200ot_cost_parts_bytes(int rows, int d, int side);
 int b200ot_cost_split(const float* X, int ldx, int rows, int d, int kind, int terms, int side, void* parts,
                       float* norms, void* stream);

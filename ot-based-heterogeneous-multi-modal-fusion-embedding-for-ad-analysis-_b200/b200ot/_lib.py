@@ -20,6 +20,19 @@ COST_SQEUCLIDEAN, COST_COSINE = 0, 1
 OT_COST_DOUBLES = 1 + 148 * 8 + 1  # B200OT_OT_COST_DOUBLES
 NORMS = {"l2": NORM_L2, "l2sq": NORM_L2SQ, "l1": NORM_L1}
 PATHS = {"auto": PATH_AUTO, "fused": PATH_FUSED, "robust": PATH_ROBUST}
+TERMS_F16_3, TERMS_F16_4 = 19, 20  # b200ot.h: two fp16 parts per operand, 3 / 4 products
+
+
+def split_terms(terms):
+    """(code for the C ABI, tensor products per element, fp16?) of a `terms` argument: 1 / 3 / 6 = bf16 parts,
+    "f16" or 19 = two fp16 parts and 3 products, "f16x4" or 20 = the same plus x2.y2."""
+    table = {1: (1, 1, False), 3: (3, 3, False), 6: (6, 6, False), "f16": (19, 3, True), 19: (19, 3, True),
+             "f16x4": (20, 4, True), 20: (20, 4, True)}
+    if terms not in table:
+        raise ValueError(f"terms must be one of {sorted(map(str, table))}, got {terms!r}")
+    return table[terms]
+
+
 COSTS = {"sqeuclidean": COST_SQEUCLIDEAN, "cosine": COST_COSINE}
 
 

@@ -102,13 +102,17 @@ def aligned_copy(Cm: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # cost construction
 # ---------------------------------------------------------------------------
+# two fp16 parts per operand, 3 products: fp32-grade relative to |x||y| at half the tensor work of the 6-term bf16
+# split (tests/test_gpu_parity.py::test_cost_fp16_split_scales_every_row)
+DEFAULT_COST_TERMS = "f16"
 @on_device
 def cost_matrix(x: torch.Tensor, y: torch.Tensor, kind: str = "sqeuclidean",
-                out: Optional[torch.Tensor] = None, impl: str = "auto", terms: int = 6) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, impl: str = "auto", terms=DEFAULT_COST_TERMS) -> torch.Tensor:
     """C_ij = |x_i|^2 + |y_j|^2 - 2 x_i.y_j  or  1 - cos(x_i, y_j).
 
-    impl="tc": tcgen05 split-bf16 GEMM (b200ot_cost); impl="simt": fp32 FMA kernel
-    (b200ot_cost_simt); "auto" picks the tensor-core kernel once the problem fills the GPU."""
+    impl="tc": tcgen05 split GEMM (b200ot_cost); impl="simt": fp32 FMA kernel (b200ot_cost_simt); "auto" picks the
+    tensor-core kernel once the problem fills the GPU.  terms: "f16" = rows scaled by a power of two and split into
+    two fp16 parts, 3 products (fp32-grade relative to |x||y|, half the tensor work of 6); 6 / 3 / 1 = bf16 parts."""
     lib = _lib.load()
     x, ldx = _matrix(x, "x")
     y, ldy = _matrix(y, "y")
@@ -126,7 +130,7 @@ def cost_matrix(x: torch.Tensor, y: torch.Tensor, kind: str = "sqeuclidean",
         ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
         wsp = C.c_void_p((ws.data_ptr() + 1023) // 1024 * 1024)
         check(lib.b200ot_cost(_ptr(x), ldx, _ptr(y), ldy, n, m, d, _lib.COSTS[kind], _ptr(out), ldc, wsp,
-                              need, int(terms), _stream()), "b200ot_cost")
+                              need, _lib.split_terms(terms)[0], _stream()), "b200ot_cost")
     elif impl == "simt":
         norms = torch.empty(n + m, dtype=torch.float32, device=x.device)
         check(lib.b200ot_cost_simt(_ptr(x), ldx, _ptr(y), ldy, n, m, d, _lib.COSTS[kind], _ptr(out), ldc,

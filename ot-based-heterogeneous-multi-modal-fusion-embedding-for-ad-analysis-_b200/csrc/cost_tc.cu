@@ -10,6 +10,11 @@
 //     terms = 3:  x.y ~= x1.y2 + x2.y1 + x1.y1                          (error ~2^-17 per product)
 //     terms = 6:  ... + x1.y3 + x3.y1 + x2.y2                           (error ~2^-24: fp32 grade)
 // which is an ordinary bf16 GEMM with K' = terms * K over concatenated parts.
+// fp16 mode (B200OT_TERMS_F16_3 / _4): every row is scaled by a power of two so that its largest entry lies in
+// [2^9, 2^10) and split into two fp16 parts x = x1 + x2 (11 + 11 significand bits, |x2| <= 2^-11 |x|max; the scaling
+// keeps x2 out of the fp16 subnormals), 3 products x1.y2 + x2.y1 + x1.y1 (+ x2.y2): representation error
+// <= 2^-23 of the row maximum per entry, i.e. fp32-grade relative to |x||y|, at HALF the tensor work of the 6-term
+// bf16 split.  The accumulator is rescaled by 2^-(s_i + t_j) in the epilogue.
 // A pre-pass splits the fp32 embeddings and writes the parts *pre-tiled*: every
 // (ROWS x 64) operand tile is one contiguous block already in the canonical no-swizzle K-major
 // UMMA shared-memory layout (8 x 16-byte core matrices), so the GEMM feeds shared memory with
@@ -21,6 +26,7 @@
 //                                        fp32 accumulators in TMEM, two accumulator stages
 //   warps 2-5 epilogue       tcgen05.ld -> |x|^2 + |y|^2 - 2 acc -> smem transpose -> coalesced stores
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -32,6 +38,8 @@ constexpr int TC_BM = 128;   // tile rows (UMMA M)
 constexpr int TC_BN = 256;   // tile cols (UMMA N)
 constexpr int TC_BK = 64;    // K elements per stage (bf16: 128 B per row)
 constexpr int TC_STAGES = 4;
+constexpr int TC_EPI_STRIDE = 36;  // floats per staged row of a 32 x 32 chunk: 16-byte accesses stay conflict-free
+constexpr int TC_EPI_FLOATS = 32 * TC_EPI_STRIDE + 2 * 256;  // per epilogue warp: chunk staging + column terms of a tile
 constexpr int TC_THREADS = 192;
 constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KiB
 constexpr uint32_t TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KiB
@@ -45,18 +53,32 @@ constexpr int TC_GROUP_N = 16;  // n-blocks per raster group (keeps a 12 MiB sla
 __global__ void __launch_bounds__(256) split_tiles_kernel(const float* __restrict__ X, long long ldx, int rows,
                                                           int d, int tile_rows, int kblocks, int rows_pad,
                                                           int cosine, int nparts, uint8_t* __restrict__ out,
-                                                          float* __restrict__ norms, float prescale) {
+                                                          float* __restrict__ norms, float prescale, int f16) {
   const int row = (blockIdx.x * 256 + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows_pad) return;
   const bool live = row < rows;
   const float* x = X + (long long)row * ldx;
-  float ss = 0.f;
+  float ss = 0.f, mx = 0.f;
   if (live)
-    for (int k = lane; k < d; k += 32) ss = fmaf(x[k], x[k], ss);
+    for (int k = lane; k < d; k += 32) {
+      ss = fmaf(x[k], x[k], ss);
+      mx = fmaxf(mx, fabsf(x[k]));
+    }
   ss = warp_sum(ss);
-  if (live && lane == 0) norms[row] = cosine ? 1.f : ss;
-  const float scale = cosine ? (ss > 0.f ? rsqrtf(ss) : 0.f) : prescale;  // prescale: a power of two (exact)
+  float scale = cosine ? (ss > 0.f ? rsqrtf(ss) : 0.f) : prescale;  // prescale: a power of two (exact)
+  if (f16) {
+    // fp16 mode: norms holds {norm, 2^-s} per row; s puts the row maximum into [2^9, 2^10)
+    mx = warp_max(mx) * fabsf(scale);
+    const int sexp = (mx > 0.f && mx < INFINITY) ? 9 - ilogbf(mx) : 0;
+    if (live && lane == 0) {
+      norms[2 * row] = cosine ? 1.f : ss;
+      norms[2 * row + 1] = ldexpf(1.f, -sexp);
+    }
+    scale *= ldexpf(1.f, sexp);
+  } else if (live && lane == 0) {
+    norms[row] = cosine ? 1.f : ss;
+  }
   const int rb = row / tile_rows, rin = row % tile_rows;
   const size_t tile_bytes = (size_t)tile_rows * 128;
   const int nchunks = kblocks * 8;
@@ -67,6 +89,14 @@ __global__ void __launch_bounds__(256) split_tiles_kernel(const float* __restric
     for (int e = 0; e < 8; ++e) {
       const int k = c * 8 + e;
       const float v = (live && k < d) ? x[k] * scale : 0.f;
+      if (f16) {  // same 16-bit containers, fp16 bit patterns
+        const __half h = __float2half_rn(v);
+        const __half h2 = __float2half_rn(v - __half2float(h));  // the residual is exact in fp32
+        p1[e] = __ushort_as_bfloat16(__half_as_ushort(h));
+        p2[e] = __ushort_as_bfloat16(__half_as_ushort(h2));
+        p3[e] = __ushort_as_bfloat16((unsigned short)0);
+        continue;
+      }
       const __nv_bfloat16 h = __float2bfloat16_rn(v);
       const float r1 = v - __bfloat162float(h);  // exact in fp32
       const __nv_bfloat16 h2 = __float2bfloat16_rn(r1);
@@ -95,14 +125,32 @@ struct CostTcArgs {
   long long ldc;
   int n, m, kblocks, nseg, nparts, cosine;
   int tiles_m, tiles_n;
+  int f16;  // fp16 parts: xn / yn hold {norm, 2^-s} per row, the accumulator is rescaled in the epilogue
+  int vec_ok;  // C is 16-byte aligned with ldc % 4 == 0: rows are stored as float4
 };
+
+// segment -> (part of X, part of Y): smallest cross terms first, the x1.y1 term last
+__device__ __forceinline__ void tc_segment(int nseg, int seg, int& pa, int& pb) {
+  pa = 0;
+  pb = 0;
+  if (nseg == 3) {  // x1.y2, x2.y1, x1.y1
+    pa = seg == 1 ? 1 : 0;
+    pb = seg == 0 ? 1 : 0;
+  } else if (nseg == 4) {  // x2.y2, x1.y2, x2.y1, x1.y1
+    pa = (seg == 0 || seg == 2) ? 1 : 0;
+    pb = (seg == 0 || seg == 1) ? 1 : 0;
+  } else if (nseg == 6) {  // x1.y3, x3.y1, x2.y2, x1.y2, x2.y1, x1.y1
+    pa = seg == 1 ? 2 : ((seg == 2 || seg == 4) ? 1 : 0);
+    pb = seg == 0 ? 2 : ((seg == 2 || seg == 3) ? 1 : 0);
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1) cost_tc_kernel(const CostTcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint8_t* sA = smem;                                    // TC_STAGES x 16 KiB
   uint8_t* sB = smem + TC_STAGES * TC_A_BYTES;           // TC_STAGES x 32 KiB
-  float* sEpi = reinterpret_cast<float*>(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES));  // 4 x 32 x 33 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * 32 * 33);
+  float* sEpi = reinterpret_cast<float*>(smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES));  // per-warp epilogue scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * TC_EPI_FLOATS);
   uint64_t* full = bars;                 // [TC_STAGES]
   uint64_t* empty = bars + TC_STAGES;    // [TC_STAGES]
   uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]
@@ -170,15 +218,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cost_tc_kernel(const CostTcArgs
         for (int ks = 0; ks < ksteps; ++ks) {
           const int seg = ks / p.kblocks, kblk = ks - seg * p.kblocks;
           // segment -> (part of X, part of Y): smallest cross terms first, the x1.y1 term last
-          int pa = 0, pb = 0;
-          if (p.nseg == 3) {
-            pa = seg == 1 ? 1 : 0;
-            pb = seg == 0 ? 1 : 0;
-          } else if (p.nseg == 6) {
-            // x1.y3, x3.y1, x2.y2, x1.y2, x2.y1, x1.y1
-            pa = seg == 1 ? 2 : ((seg == 2 || seg == 4) ? 1 : 0);
-            pb = seg == 0 ? 2 : ((seg == 2 || seg == 3) ? 1 : 0);
-          }
+          int pa, pb;
+          tc_segment(p.nseg, seg, pa, pb);
           mbar_wait(smem_u32(empty + stage), phase ^ 1);
           const uint32_t bar = smem_u32(full + stage);
           mbar_arrive_expect_tx(bar, TC_A_BYTES + TC_B_BYTES);
@@ -197,7 +238,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cost_tc_kernel(const CostTcArgs
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 256, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+      // (fp16 parts: A / B format fields 0 instead of 1)
+      const uint32_t idesc = (1u << 4) | (p.f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(TC_BN >> 3) << 17) |
                              ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -235,38 +277,95 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cost_tc_kernel(const CostTcArgs
   } else {
     // ===================== epilogue warps (2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    float* sm = sEpi + (warp - 2) * (32 * 33);
+    float* sm = sEpi + (warp - 2) * TC_EPI_FLOATS;  // [32][36] chunk staging
+    float* sy = sm + 32 * TC_EPI_STRIDE;            // [2][256] column terms of the tile
     int as = 0;
     uint32_t aphase = 0;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int mb, nb;
       tile_coords_exact(t, mb, nb);
-      mbar_wait(smem_u32(tfull + as), aphase);
-      tc_fence_after();
-      const int row0 = mb * TC_BM + q * 32;
-      const float xn_l = (row0 + lane < p.n) ? p.xn[row0 + lane] : 0.f;
-#pragma unroll 1
-      for (int c = 0; c < TC_BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * TC_BN + (uint32_t)c * 32, v);
-        tmem_ld_wait();
+      // tcgen05.ld 32x32b hands lane l the 32 consecutive columns of row (quarter * 32 + l).  Every lane finishes
+      // its own row (row terms are its own registers; the 256 column terms of the tile are staged in shared memory
+      // while the tile's MMAs are still running and read back as broadcast float4) and writes the 32 results into a
+      // [32][36] staging block; the warp then reads the block back with 8 lanes per row and stores 4 full 128-byte
+      // lines per instruction.  The TMEM load of the next chunk is in flight while a chunk is finished.
+      // History (profiles/r02_cost_tc_f16_16384_*.txt): (1) transposing scalar by scalar with two shuffles, 64-bit
+      // address arithmetic and a branch per row and chunk cost ~30 instructions per row: 20 us per tile, tensor pipe
+      // capped at 37 % with three K segments; (2) storing 16 bytes per lane straight from the TMEM registers needs
+      // no staging but every store instruction touches 32 half-filled sectors: 14 us per tile, 59 %.
+      const int row = mb * TC_BM + q * 32 + lane;
+      const bool rok = row < p.n;
+      float xn_l = 0.f, xs_l = 1.f;
+      if (rok) {
+        xn_l = p.f16 ? p.xn[2 * row] : p.xn[row];
+        if (p.f16) xs_l = p.xn[2 * row + 1];
+      }
+      __syncwarp();  // the previous tile's readers are done with the scratch
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sm[lane * 33 + j] = __uint_as_float(v[j]);
-        __syncwarp();
+      for (int c = 0; c < TC_BN / 32; ++c) {
         const int col = nb * TC_BN + c * 32 + lane;
         const bool cok = col < p.m;
-        const float yn_c = cok ? p.yn[col] : 0.f;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const float acc = sm[r * 33 + lane];
-          const float xr = __shfl_sync(0xffffffffu, xn_l, r);
-          const int row = row0 + r;
-          if (cok && row < p.n) {
-            const float out = p.cosine ? (1.f - acc) : ((xr + yn_c) - 2.f * acc);
-            p.C[(long long)row * p.ldc + col] = out;
+        sy[c * 32 + lane] = (cok && !p.cosine) ? (p.f16 ? p.yn[2 * col] : p.yn[col]) : 0.f;
+        sy[TC_BN + c * 32 + lane] = (cok && p.f16) ? p.yn[2 * col + 1] : 1.f;
+      }
+      __syncwarp();
+      const float mul_l = p.cosine ? -xs_l : -2.f * xs_l;  // powers of two times -1 / -2: exact
+      const float base_l = p.cosine ? 1.f : xn_l;
+      // read-back role of this lane: row (lane / 8) + 4 i of the chunk, columns (lane % 8) * 4 .. + 3
+      const int rb_row = lane >> 3, rb_col = (lane & 7) * 4;
+      const int row_q0 = mb * TC_BM + q * 32;
+      const bool tile_fast = p.vec_ok && row_q0 + 32 <= p.n;  // full rows, aligned: the coalesced path
+      mbar_wait(smem_u32(tfull + as), aphase);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)as * TC_BN;
+      auto finish = [&](int c, const uint32_t (&v)[32]) {
+        const int col0 = nb * TC_BN + c * 32;
+        const float* syc = sy + c * 32;
+        float o[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 y4 = *reinterpret_cast<const float4*>(syc + 4 * j4);
+          float4 m4 = make_float4(mul_l, mul_l, mul_l, mul_l);
+          if (p.f16) {
+            const float4 s4 = *reinterpret_cast<const float4*>(syc + TC_BN + 4 * j4);
+            m4 = make_float4(mul_l * s4.x, mul_l * s4.y, mul_l * s4.z, mul_l * s4.w);
           }
+          o[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), m4.x, base_l + y4.x);
+          o[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), m4.y, base_l + y4.y);
+          o[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), m4.z, base_l + y4.z);
+          o[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), m4.w, base_l + y4.w);
         }
-        __syncwarp();
+        if (tile_fast && col0 + 32 <= p.m) {
+          __syncwarp();  // the previous chunk has been read back
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(sm + lane * TC_EPI_STRIDE + 4 * j4) =
+                make_float4(o[4 * j4 + 0], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
+          __syncwarp();
+          float* dst = p.C + (long long)(row_q0 + rb_row) * p.ldc + col0 + rb_col;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 w4 = *reinterpret_cast<const float4*>(sm + (rb_row + 4 * i) * TC_EPI_STRIDE + rb_col);
+            *reinterpret_cast<float4*>(dst) = w4;
+            dst += 4 * p.ldc;
+          }
+        } else if (rok) {
+          float* crow = p.C + (long long)row * p.ldc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.m) crow[col0 + j] = o[j];
+        }
+      };
+      uint32_t va[32], vb[32];
+      tmem_ld32(tacc, va);
+#pragma unroll 1
+      for (int c = 0; c < TC_BN / 32; c += 2) {
+        tmem_ld_wait();
+        tmem_ld32(tacc + (uint32_t)(c + 1) * 32, vb);
+        finish(c, va);
+        tmem_ld_wait();
+        if (c + 2 < TC_BN / 32) tmem_ld32(tacc + (uint32_t)(c + 2) * 32, va);
+        finish(c + 1, vb);
       }
       tc_fence_before();
       if (lane == 0) mbar_arrive(smem_u32(tempty + as));
@@ -284,7 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) cost_tc_kernel(const CostTcArgs
   }
 }
 
-constexpr size_t TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 4 * 32 * 33 * 4 + (2 * TC_STAGES + 4) * 8 + 16;
+constexpr size_t TC_SMEM = TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + 4 * TC_EPI_FLOATS * 4 + (2 * TC_STAGES + 4) * 8 + 16;
 
 struct CostWs {
   size_t a_off, b_off, norm_off, total;
@@ -300,7 +399,7 @@ static CostWs cost_ws(int n, int m, int d) {
   w.a_off = 0;
   w.b_off = (a_bytes + 1023) / 1024 * 1024;
   w.norm_off = w.b_off + (b_bytes + 1023) / 1024 * 1024;
-  w.total = w.norm_off + ((size_t)(n + m) * 4 + 1023) / 1024 * 1024;
+  w.total = w.norm_off + ((size_t)(n + m) * 8 + 1023) / 1024 * 1024;  // {norm, 2^-s} per row in fp16 mode
   return w;
 }
 
@@ -334,6 +433,21 @@ __global__ void __launch_bounds__(256) fot_wnorm_kernel(const float* __restrict_
   if (lane == 0) out[k] = acc;
 }
 
+// `terms` of the C ABI -> K segments, parts per operand, fp16 parts
+struct TermCfg {
+  int nseg, nparts, f16;
+};
+static bool decode_terms(int terms, TermCfg* c) {
+  switch (terms) {
+    case 1: *c = {1, 1, 0}; return true;
+    case 3: *c = {3, 2, 0}; return true;
+    case 6: *c = {6, 3, 0}; return true;
+    case B200OT_TERMS_F16_3: *c = {3, 2, 1}; return true;
+    case B200OT_TERMS_F16_4: *c = {4, 2, 1}; return true;
+    default: return false;
+  }
+}
+
 }  // namespace b200ot
 
 using namespace b200ot;
@@ -350,8 +464,9 @@ int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, 
   if (!X || !Y || !C || !ws || n <= 0 || m <= 0 || d <= 0 || ldx < d || ldy < d || ldc < m)
     return B200OT_E_INVALID;
   if (kind != B200OT_COST_SQEUCLIDEAN && kind != B200OT_COST_COSINE) return B200OT_E_INVALID;
-  if (terms != 1 && terms != 3 && terms != 6) return B200OT_E_INVALID;
-  const int nparts = terms == 1 ? 1 : terms == 3 ? 2 : 3;
+  TermCfg tc;
+  if (!decode_terms(terms, &tc)) return B200OT_E_INVALID;
+  const int nparts = tc.nparts;
   if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return B200OT_E_INVALID;
   const CostWs w = cost_ws(n, m, d);
   if (ws_bytes < w.total) return B200OT_E_WORKSPACE;
@@ -360,11 +475,11 @@ int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, 
   uint8_t* Ap = base + w.a_off;
   uint8_t* Bp = base + w.b_off;
   float* xn = reinterpret_cast<float*>(base + w.norm_off);
-  float* yn = xn + n;
+  float* yn = xn + (tc.f16 ? 2 * (size_t)n : (size_t)n);
   const int cosine = kind == B200OT_COST_COSINE ? 1 : 0;
-  split_tiles_kernel<<<(w.n_pad * 32 + 255) / 256, 256, 0, s>>>(X, ldx, n, d, TC_BM, w.kblocks, w.n_pad, cosine, nparts, Ap, xn, 1.f);
+  split_tiles_kernel<<<(w.n_pad * 32 + 255) / 256, 256, 0, s>>>(X, ldx, n, d, TC_BM, w.kblocks, w.n_pad, cosine, nparts, Ap, xn, 1.f, tc.f16);
   B200OT_LAUNCH_OK();
-  split_tiles_kernel<<<(w.m_pad * 32 + 255) / 256, 256, 0, s>>>(Y, ldy, m, d, TC_BN, w.kblocks, w.m_pad, cosine, nparts, Bp, yn, 1.f);
+  split_tiles_kernel<<<(w.m_pad * 32 + 255) / 256, 256, 0, s>>>(Y, ldy, m, d, TC_BN, w.kblocks, w.m_pad, cosine, nparts, Bp, yn, 1.f, tc.f16);
   B200OT_LAUNCH_OK();
   static PerDeviceOnce attr_once;  // function attributes are per device
   if (attr_once.first()) {
@@ -380,9 +495,11 @@ int b200ot_cost(const float* X, int ldx, const float* Y, int ldy, int n, int m, 
   a.n = n;
   a.m = m;
   a.kblocks = w.kblocks;
-  a.nseg = terms;
+  a.nseg = tc.nseg;
   a.nparts = nparts;
   a.cosine = cosine;
+  a.f16 = tc.f16;
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc & 3) == 0) ? 1 : 0;
   a.tiles_m = w.n_pad / TC_BM;
   a.tiles_n = w.m_pad / TC_BN;
   const long long tiles = (long long)a.tiles_m * a.tiles_n;
@@ -405,15 +522,16 @@ size_t b200ot_cost_parts_bytes(int rows, int d, int side) {
 int b200ot_cost_split(const float* X, int ldx, int rows, int d, int kind, int terms, int side, void* parts,
                       float* norms, void* stream) {
   if (!X || !parts || !norms || rows <= 0 || d <= 0 || ldx < d) return B200OT_E_INVALID;
-  if (terms != 1 && terms != 3 && terms != 6) return B200OT_E_INVALID;
+  TermCfg tc;
+  if (!decode_terms(terms, &tc)) return B200OT_E_INVALID;
   if ((reinterpret_cast<uintptr_t>(parts) & 1023) != 0) return B200OT_E_INVALID;
-  const int nparts = terms == 1 ? 1 : terms == 3 ? 2 : 3;
+  const int nparts = tc.nparts;
   const int tile = side ? TC_BN : TC_BM;
   const int rows_pad = (rows + tile - 1) / tile * tile;
   const int kblocks = (d + TC_BK - 1) / TC_BK;
   split_tiles_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       X, ldx, rows, d, tile, kblocks, rows_pad, kind == B200OT_COST_COSINE ? 1 : 0, nparts,
-      static_cast<uint8_t*>(parts), norms, 1.f);
+      static_cast<uint8_t*>(parts), norms, 1.f, tc.f16);
   B200OT_LAUNCH_OK();
   return 0;
 }
@@ -423,26 +541,29 @@ int b200ot_cost_gemm(const void* partsA, const float* normsA, int row_tile0, int
                      const float* normsB, int m, int d, int kind, int terms, float* C, int ldc, void* stream) {
   if (!partsA || !normsA || !partsB || !normsB || !C || n <= 0 || m <= 0 || d <= 0 || ldc < m || row_tile0 < 0)
     return B200OT_E_INVALID;
-  if (terms != 1 && terms != 3 && terms != 6) return B200OT_E_INVALID;
+  TermCfg tc;
+  if (!decode_terms(terms, &tc)) return B200OT_E_INVALID;
   static PerDeviceOnce attr_once;  // function attributes are per device
   if (attr_once.first()) {
     B200OT_CUDA_OK(cudaFuncSetAttribute(cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   }
-  const int nparts = terms == 1 ? 1 : terms == 3 ? 2 : 3;
+  const int nparts = tc.nparts;
   const int kblocks = (d + TC_BK - 1) / TC_BK;
   CostTcArgs a;
   a.A = static_cast<const uint8_t*>(partsA) + (size_t)row_tile0 * nparts * kblocks * TC_A_BYTES;
   a.B = static_cast<const uint8_t*>(partsB);
-  a.xn = normsA + (size_t)row_tile0 * TC_BM;
+  a.xn = normsA + (size_t)row_tile0 * TC_BM * (tc.f16 ? 2 : 1);
   a.yn = normsB;
   a.C = C;
   a.ldc = ldc;
   a.n = n;
   a.m = m;
   a.kblocks = kblocks;
-  a.nseg = terms;
+  a.nseg = tc.nseg;
   a.nparts = nparts;
   a.cosine = kind == B200OT_COST_COSINE ? 1 : 0;
+  a.f16 = tc.f16;
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc & 3) == 0) ? 1 : 0;
   a.tiles_m = (n + TC_BM - 1) / TC_BM;
   a.tiles_n = (m + TC_BN - 1) / TC_BN;
   const long long tiles = (long long)a.tiles_m * a.tiles_n;
@@ -525,7 +646,7 @@ int b200ot_fot_cost_tc(const float* A, int lda, const float* B, int ldb, const f
     const int kblocks = (K + TC_BK - 1) / TC_BK;
     split_tiles_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, s>>>(X, ldx, rows, K, tile, kblocks, rows_pad, 0, nparts,
                                                                    reinterpret_cast<uint8_t*>(base + off), scratch,
-                                                                   prescale);
+                                                                   prescale, 0);
   };
   split(BT, n2, d2, n2, 0, w.pBT, 1.f);
   B200OT_LAUNCH_OK();

@@ -77,6 +77,45 @@ def test_cost_tensor_core_split_is_fp32_accurate(cuda_dev, n, m, d):
     assert np.abs(Cc - orc.cosine_cost(X, Y)).max() < 3e-6
     Cs = ops.cost_matrix(xd, yd, impl="simt").cpu().numpy()
     assert np.abs(Cs - ref).max() < 4e-6
+    # two fp16 parts per operand (rows scaled by a power of two), 3 products: same grade at half the tensor work
+    Ch = ops.cost_matrix(xd, yd, impl="tc", terms="f16").cpu().numpy()
+    assert np.abs(Ch - ref).max() < 1.5e-6
+    Ch4 = ops.cost_matrix(xd, yd, impl="tc", terms="f16x4").cpu().numpy()
+    assert np.abs(Ch4 - ref).max() < 1.5e-6
+    Chc = ops.cost_matrix(xd, yd, kind="cosine", impl="tc", terms="f16").cpu().numpy()
+    assert np.abs(Chc - orc.cosine_cost(X, Y)).max() < 3e-6
+
+
+def test_cost_fp16_split_scales_every_row(cuda_dev):
+    """The fp16 split must not depend on the magnitude of the data: rows spanning 1e-18 .. 1e+15, a heavy-tailed row
+    (one entry 1e4 times the rest), a zero row and an unaligned leading dimension.  Error bound: 2e-6 |x_i||y_j|
+    (representation error 2^-23 of the row maximum per entry, worst case sqrt(d) of it in the dot product)."""
+    from b200ot import ops
+    rng = np.random.default_rng(5)
+    n, m, d = 384, 640, 200
+    X = rng.standard_normal((n, d))
+    Y = rng.standard_normal((m, d))
+    X *= 10.0 ** rng.uniform(-18, 15, size=(n, 1))
+    Y *= 10.0 ** rng.uniform(-3, 3, size=(m, 1))
+    X[7, 3] *= 1e4
+    X[11] = 0.0
+    Y[5, :] = 0.0
+    X = X.astype(np.float32).astype(np.float64)
+    Y = Y.astype(np.float32).astype(np.float64)
+    xd = torch.zeros(n, d + 5, device=cuda_dev)[:, :d]
+    xd.copy_(_dev(X, cuda_dev))
+    ref = (X * X).sum(1)[:, None] + (Y * Y).sum(1)[None, :] - 2.0 * X @ Y.T
+    bound = np.linalg.norm(X, axis=1)[:, None] * np.linalg.norm(Y, axis=1)[None, :]
+    for terms in ("f16", "f16x4", 6):
+        Cm = ops.cost_matrix(xd, _dev(Y, cuda_dev), impl="tc", terms=terms).double().cpu().numpy()
+        assert np.isfinite(Cm).all()
+        # fp32 rounding of |x|^2 + |y|^2 itself is 2^-24 of the larger norm: allow it on top of the product bound
+        tol = 2e-6 * bound + 2.5e-7 * ((X * X).sum(1)[:, None] + (Y * Y).sum(1)[None, :]) + 1e-37
+        assert (np.abs(Cm - ref) <= tol).all(), (terms, float((np.abs(Cm - ref) / tol).max()))
+    cref = 1.0 - (X / np.maximum(np.linalg.norm(X, axis=1, keepdims=True), 1e-300)) @ \
+        (Y / np.maximum(np.linalg.norm(Y, axis=1, keepdims=True), 1e-300)).T
+    Cc = ops.cost_matrix(xd, _dev(Y, cuda_dev), kind="cosine", impl="tc", terms="f16").double().cpu().numpy()
+    assert np.abs(Cc - cref).max() < 3e-6
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
