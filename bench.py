@@ -494,6 +494,37 @@ def run_b200(args):
 
     prm = ops.make_params(EPS, iters, 0.0, 10, 1, "l2", False, args.path)
     kern = sharded.CudaShardKernels(Cmat, a_loc, b, prm, path=args.path)
+    balance = None
+    if world > 1 and not args.no_balance:
+        # Setup, outside the timed region: every iteration ends in an exchange of all ranks, so the loop runs at the
+        # pace of the slowest GPU.  Time the local sweep of every rank (all ranks at once, clocks settled), split the
+        # rows in proportion to the measured rates and rebuild this rank's rows of C when the split moves by > 2 %
+        # (boxes with a 7 % spread between GPUs were seen; on a box with 1.8 % the repartition gained nothing:
+        # profiles/r02_bench_n8_final.json).
+        kern.setup()
+        kern.finalize(kern.prologue(), True)
+        dist.barrier()
+        rate = sharded.measure_sweep_rate(kern)
+        rates = [torch.zeros(1, device=dev) for _ in range(world)]
+        dist.all_gather(rates, torch.tensor([rate], device=dev))
+        rates = [float(r.item()) for r in rates]
+        bounds = sharded.balanced_bounds(n, rates)
+        moved = max(abs((bh - bl) - (sharded.row_range(n, world, r)[1] - sharded.row_range(n, world, r)[0]))
+                    for r, (bl, bh) in enumerate(bounds)) / (n / world)
+        balance = {"rows_per_ms_by_rank": [round(r, 1) for r in rates], "rows_by_rank": [bh - bl for bl, bh in bounds],
+                   "applied": bool(moved > 0.02),
+                   "note": "rows proportional to the measured local sweep rate of each GPU (setup, not timed)"}
+        if balance["applied"]:
+            del kern, Cmat
+            torch.cuda.empty_cache()
+            lo, hi = bounds[rank]
+            Xh, Yh = synthetic_rows(n, m, lo, hi, seed, dev)
+            Xp, Yp = Xh.pin_memory(), Yh.pin_memory()
+            n_loc = hi - lo
+            a_loc = torch.full((n_loc,), 1.0 / n, dtype=torch.float32, device=dev)
+            Cmat = ops.cost_matrix(Xp.to(dev), Yp.to(dev))
+            torch.cuda.synchronize()
+            kern = sharded.CudaShardKernels(Cmat, a_loc, b, prm, path=args.path)
     comm = sharded.NcclComm() if (world > 1 and args.loop == "c") else None
     peer = None
     if world > 1 and args.loop == "peer":
@@ -626,7 +657,7 @@ def run_b200(args):
             _shutdown(dist)
         return
     peak, peak_src = _peaks()
-    alg_bytes = 4.0 * n_loc * m  # one fp32 read of this rank's rows of C per iteration
+    alg_bytes = 4.0 * (n / world) * m  # one fp32 read of C per iteration, per GPU (mean rows per rank)
     per_iter_s = ms_per_step * 1e-3 / iters
     achieved = alg_bytes / per_iter_s / 1e9
     # our kernels per step: init (init_state, init, colpass, finalize) + snapshot per enqueue + 2 per iteration;
@@ -660,7 +691,8 @@ def run_b200(args):
         "config": {"workload": f"log-domain Sinkhorn n=m={n} d={D} eps={EPS}, {iters} iterations per solve "
                                f"(BASELINE configs[3]; single-sweep fused kernel, C resident in HBM)",
                    "n": n, "m": m, "d": D, "eps": EPS, "iterations_per_step": iters, "path": args.path,
-                   "rows_per_gpu": n_loc, "kernel": kernel_desc,
+                   "rows_per_gpu": n_loc if balance is None or not balance["applied"] else balance["rows_by_rank"],
+                   "balance": balance, "kernel": kernel_desc,
                    "launch": ("one persistent launch per solve" if resident else
                               (f"CUDA graph, {args.graph} iterations per replay" if args.graph else "eager launches") +
                               (", each replay = snapshot + ONE persistent cooperative cluster launch (sweep, fold, finalize and "
@@ -728,6 +760,8 @@ def main():
     ap.add_argument("--no-online", action="store_true", help="skip the online (cost-free) measurement")
     ap.add_argument("--no-step", action="store_true", help="skip the C5 end-to-end training-step measurement")
     ap.add_argument("--no-sampler", action="store_true", help="diagnostic: do not sample clocks")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N > 1: keep the even row split instead of rows proportional to the measured sweep rate of each GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         pin_host_threads()  # before numpy / BLAS load: torchrun exports OMP_NUM_THREADS=1

@@ -15,13 +15,13 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
 from . import _lib, ops
-from ._lib import check
+from ._lib import B200OTError, check
 
 
 def row_range(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -32,6 +32,44 @@ def row_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     lo_g = rank * base + min(rank, extra)
     hi_g = lo_g + base + (1 if rank < extra else 0)
     return min(lo_g * 4, n), min(hi_g * 4, n)
+
+
+def balanced_bounds(n: int, weights: Sequence[float]) -> List[Tuple[int, int]]:
+    """Contiguous row blocks whose sizes are proportional to `weights` (measured sweep rates of the ranks), in
+    groups of 4 rows like ``row_range``.  Every iteration of the sharded loop ends in an exchange of all ranks, so
+    the loop runs at the pace of the slowest GPU; on a box whose GPUs differ (7 % between the fastest and the
+    slowest of eight was measured, same binary, same shard) an even split wastes the difference."""
+    world = len(weights)
+    w = [max(float(x), 0.0) for x in weights]
+    if world < 1 or not sum(w) > 0.0:
+        raise B200OTError("balanced_bounds needs positive weights")
+    groups = (n + 3) // 4
+    total = sum(w)
+    cuts, acc = [0], 0.0
+    for r in range(world - 1):
+        acc += w[r]
+        g = int(round(groups * acc / total))
+        if groups >= world:  # every rank keeps at least one group
+            g = min(max(g, cuts[-1] + 1), groups - (world - 1 - r))
+        cuts.append(min(max(g, cuts[-1]), groups))
+    cuts.append(groups)
+    return [(min(cuts[r] * 4, n), min(cuts[r + 1] * 4, n)) for r in range(world)]
+
+
+def measure_sweep_rate(kern, sweeps: int = 200, warm: int = 100) -> float:
+    """Rows per millisecond of this rank's local sweep (no exchange; the state does not advance), timed with CUDA
+    events after `warm` untimed sweeps so that the clocks have settled under load.  `kern` must be set up
+    (setup + first g update)."""
+    for _ in range(warm):
+        kern.sweep()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(sweeps):
+        kern.sweep()
+    e1.record()
+    torch.cuda.synchronize()
+    return kern.n * sweeps / max(e0.elapsed_time(e1), 1e-6)
 
 
 class NcclComm:

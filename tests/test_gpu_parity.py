@@ -112,6 +112,10 @@ def test_cost_fp16_split_scales_every_row(cuda_dev):
         # fp32 rounding of |x|^2 + |y|^2 itself is 2^-24 of the larger norm: allow it on top of the product bound
         tol = 2e-6 * bound + 2.5e-7 * ((X * X).sum(1)[:, None] + (Y * Y).sum(1)[None, :]) + 1e-37
         assert (np.abs(Cm - ref) <= tol).all(), (terms, float((np.abs(Cm - ref) / tol).max()))
+    # an output with an odd leading dimension takes the scalar store path of the epilogue
+    odd = torch.empty(n, m + 1, device=cuda_dev)[:, :m]
+    Co = ops.cost_matrix(xd, _dev(Y, cuda_dev), out=odd, impl="tc", terms="f16")
+    assert Co.stride(0) == m + 1 and torch.equal(Co, ops.cost_matrix(xd, _dev(Y, cuda_dev), impl="tc", terms="f16"))
     cref = 1.0 - (X / np.maximum(np.linalg.norm(X, axis=1, keepdims=True), 1e-300)) @ \
         (Y / np.maximum(np.linalg.norm(Y, axis=1, keepdims=True), 1e-300)).T
     Cc = ops.cost_matrix(xd, _dev(Y, cuda_dev), kind="cosine", impl="tc", terms="f16").double().cpu().numpy()

@@ -17,6 +17,26 @@ import torch.multiprocessing as mp
 from oracle import ot_oracle as orc
 
 
+def test_balanced_bounds_follow_the_measured_rates():
+    """Rows proportional to the ranks' sweep rates, contiguous, in groups of 4, covering everything; equal rates
+    reproduce the even split."""
+    from b200ot.sharded import balanced_bounds, row_range
+    n = 65536
+    assert balanced_bounds(n, [1.0] * 8) == [row_range(n, 8, r) for r in range(8)]
+    rates = [341.0, 350.0, 365.0, 345.0, 350.0, 352.0, 348.0, 360.0]
+    b = balanced_bounds(n, rates)
+    assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(7))
+    assert all((hi - lo) % 4 == 0 for lo, hi in b)
+    times = [(hi - lo) / r for (lo, hi), r in zip(b, rates)]
+    assert max(times) / min(times) < 1.002                       # every rank finishes its sweep together
+    even = [8192 / r for r in rates]
+    assert max(times) < max(even) * 0.975                         # 7 % spread: the slowest rank gated the even split (-2.9 %)
+    for n2, w in ((100, [1, 2, 3]), (4096, [1, 1]), (12, [5, 1, 1])):
+        bb = balanced_bounds(n2, w)
+        assert bb[0][0] == 0 and bb[-1][1] == n2 and all(bb[i][1] == bb[i + 1][0] for i in range(len(w) - 1))
+        assert all(hi > lo for lo, hi in bb)
+
+
 def test_row_range_partitions_everything():
     from b200ot.sharded import row_range
     for n in (1, 3, 4, 7, 64, 65, 1000, 65536):
