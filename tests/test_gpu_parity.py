@@ -869,6 +869,32 @@ def test_fused_iteration_with_peer_words_single_rank(cuda_dev, n, m):
     assert lib.b200ot_sinkhorn_counter(0) - launches0 >= 1
 
 
+def test_measured_sweep_rate_feeds_the_balanced_split(cuda_dev):
+    """sharded.measure_sweep_rate times the local sweep of a set-up shard (rows per ms, state not advancing);
+    balanced_bounds turns the ranks' rates into row ranges.  One GPU: two shards of the same problem measured in
+    turn must give comparable rates, an (almost) even split, and the solver state must be untouched."""
+    from b200ot import ops, sharded
+    n, m = 1024, 8192
+    X, Y = orc.synthetic_embeddings(n, m, 32, config_index=6)
+    Cd = ops.cost_matrix(_dev(X, cuda_dev), _dev(Y, cuda_dev))
+    b = torch.full((m,), 1.0 / m, device=cuda_dev)
+    prm = ops.make_params(0.05, 100, 0.0, 10, 1, "l2", False, "auto")
+    rates = []
+    os.environ["B200OT_RESIDENT"] = "0"
+    try:
+        for lo, hi in (sharded.row_range(n, 2, 0), sharded.row_range(n, 2, 1)):
+            k = sharded.CudaShardKernels(Cd[lo:hi], torch.full((hi - lo,), 1.0 / n, device=cuda_dev), b, prm)
+            k.setup()
+            k.finalize(k.prologue(), True)
+            rates.append(sharded.measure_sweep_rate(k, sweeps=50, warm=10))
+            assert k.flags()["it"] == 0 and k.flags()["bad"] == 0
+    finally:
+        del os.environ["B200OT_RESIDENT"]
+    assert all(r > 0 for r in rates) and max(rates) / min(rates) < 1.5
+    bounds = sharded.balanced_bounds(n, rates)
+    assert bounds[0][0] == 0 and bounds[1][1] == n and bounds[0][1] == bounds[1][0]
+
+
 def test_sharded_solve_recovers_from_a_lost_sum(cuda_dev):
     """eps = 1e-3 on a max-scaled cost: the single-sweep kernel loses row sums in the first iterations.  The
     sharded driver must do what b200ot_sinkhorn_solve does: rewind to the chunk snapshot and replay on the robust
