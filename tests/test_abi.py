@@ -155,3 +155,24 @@ def test_host_api_rejects_cpu_tensors_and_bad_shapes(native_lib):
         ops.egw_batched([], [])
     with pytest.raises(B200OTError):
         ops.egw_batched([x], [x, x])
+
+
+def test_cost_split_codes_and_path_rule(native_lib):
+    """Host logic without a device: the `terms` argument of the cost construction maps to the C-ABI codes of
+    include/b200ot.h, and the streaming / online rule evaluates both per-iteration costs with the measured rates."""
+    from b200ot import _lib
+    from b200ot.online import MEASURED, choose_path
+    src = open(HEADER).read()
+    assert int(re.search(r"#define B200OT_TERMS_F16_3 (\d+)", src).group(1)) == _lib.TERMS_F16_3 == _lib.split_terms("f16")[0]
+    assert int(re.search(r"#define B200OT_TERMS_F16_4 (\d+)", src).group(1)) == _lib.TERMS_F16_4 == _lib.split_terms("f16x4")[0]
+    assert _lib.split_terms(6) == (6, 6, False) and _lib.split_terms("f16") == (19, 3, True)
+    assert _lib.split_terms("f16x4")[1] == 4 and _lib.split_terms(1)[1] == 1
+    with pytest.raises(ValueError):
+        _lib.split_terms(5)
+    # C fits: stream (4nm bytes per iteration beat 2nmd * products flops at the measured rates); C does not fit: online
+    assert choose_path(65536, 65536, 512, 180 << 30) == "streaming"
+    assert choose_path(300000, 300000, 512, 180 << 30) == "online"
+    assert choose_path(65536, 65536, 8, 180 << 30) == "streaming"  # every panel is also written and read once
+    fast_tensor = dict(MEASURED, online_tflops_executed=1e9)       # rule is driven by the rates, not hard-wired
+    assert choose_path(65536, 65536, 512, 180 << 30, rates=fast_tensor) == "streaming"
+    assert choose_path(65536, 65536, 512, 8 << 30) == "online"       # 16 GiB of C into 8 GiB of free memory
